@@ -1,0 +1,221 @@
+// Kernel group (1): master-frame building and per-light calibration fused with the
+// grayscale conversion.  HBM-streaming, 128-bit vectorised, one pass.
+//
+// Replaces (reference, libstacker/src/):
+//   convertAndScaleImage      util.cpp:429-463   v -> float(v) * float(1/65535)
+//   stackBias/Darks/DarkFlats/Flats util.cpp:584-722
+//   getCalibratedImage        util.cpp:266-274   ((x - bias) - dark) / flat
+//   cvtColor(BGR2GRAY)        stardetector.cpp:110-116
+#pragma once
+#include "common.cuh"
+
+namespace oss {
+
+#define OSS_MAX_BATCH 16
+struct FramePtrs { const void *p[OSS_MAX_BATCH]; };
+
+template <typename T> struct Sample;
+template <> struct Sample<uint16_t> {
+    static constexpr int PX = 8;
+    __device__ static __forceinline__ float conv(uint16_t v) { return __fmul_rn((float)v, (float)(1 / 65535.0)); }
+};
+template <> struct Sample<uint8_t> {
+    static constexpr int PX = 16;
+    __device__ static __forceinline__ float conv(uint8_t v) { return __fmul_rn((float)v, (float)(1 / 255.0)); }
+};
+template <> struct Sample<float> {
+    static constexpr int PX = 8;
+    __device__ static __forceinline__ float conv(float v) { return v; }
+};
+
+// streaming 16-byte load that does not allocate in L1 (each raw sample is read once)
+__device__ __forceinline__ uint4 ld_stream16(const void *p)
+{
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+
+// N samples of T starting at a 16-byte aligned address -> converted floats
+template <typename T, int N>
+__device__ __forceinline__ void load_samples(const T *src, float *v)
+{
+    constexpr int BYTES = N * (int)sizeof(T);
+    static_assert(BYTES % 16 == 0, "vector path needs whole 16-byte words");
+    union { uint4 q[BYTES / 16]; T s[N]; } u;
+#pragma unroll
+    for (int i = 0; i < BYTES / 16; i++) u.q[i] = ld_stream16((const char *)src + 16 * i);
+#pragma unroll
+    for (int i = 0; i < N; i++) v[i] = Sample<T>::conv(u.s[i]);
+}
+
+template <int N>
+__device__ __forceinline__ void load_f32(const float *src, float *v)
+{
+#pragma unroll
+    for (int i = 0; i < N / 4; i++) {
+        float4 q = __ldg((const float4 *)src + i);
+        v[4 * i] = q.x; v[4 * i + 1] = q.y; v[4 * i + 2] = q.z; v[4 * i + 3] = q.w;
+    }
+}
+
+template <int N>
+__device__ __forceinline__ void store_f32(float *dst, const float *v)
+{
+#pragma unroll
+    for (int i = 0; i < N / 4; i++) ((float4 *)dst)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+}
+
+// ---------------------------------------------------------------------------------------
+// K1  calibrate + gray.  grid = (ceil(P / (256*PX)), frames).  Each thread owns PX
+// consecutive pixels: raw in (2C B/px), up to three f32 masters in, calibrated f32 out,
+// gray f32 out (C == 3 only; for mono the calibrated plane IS the gray plane).
+template <typename T, int C, bool HAS_B, bool HAS_D, bool HAS_F>
+__global__ void __launch_bounds__(256)
+k_calibrate_gray(const __grid_constant__ FramePtrs raws, const float *__restrict__ bias, const float *__restrict__ dark,
+                 const float *__restrict__ flat, float *__restrict__ cal, long long strideCal,
+                 float *__restrict__ gray, long long strideGray, long long P)
+{
+    constexpr int PX = Sample<T>::PX, N = PX * C;
+    const long long p0 = ((long long)blockIdx.x * 256 + threadIdx.x) * PX;
+    if (p0 >= P) return;
+    const T *raw = (const T *)raws.p[blockIdx.y] + p0 * C;
+    float *out = cal + (long long)blockIdx.y * strideCal + p0 * C;
+    float v[N];
+    if (p0 + PX <= P) {
+        load_samples<T, N>(raw, v);
+        float m[N];
+        if (HAS_B) {
+            load_f32<N>(bias + p0 * C, m);
+#pragma unroll
+            for (int i = 0; i < N; i++) v[i] = __fsub_rn(v[i], m[i]);
+        }
+        if (HAS_D) {
+            load_f32<N>(dark + p0 * C, m);
+#pragma unroll
+            for (int i = 0; i < N; i++) v[i] = __fsub_rn(v[i], m[i]);
+        }
+        if (HAS_F) {
+            load_f32<N>(flat + p0 * C, m);
+#pragma unroll
+            for (int i = 0; i < N; i++) v[i] = __fdiv_rn(v[i], m[i]);
+        }
+        store_f32<N>(out, v);
+        if (C == 3) {
+            float g[PX];
+#pragma unroll
+            for (int i = 0; i < PX; i++)
+                g[i] = __fadd_rn(__fadd_rn(__fmul_rn(v[3 * i], 0.114f), __fmul_rn(v[3 * i + 1], 0.587f)),
+                                 __fmul_rn(v[3 * i + 2], 0.299f));
+            store_f32<PX>(gray + (long long)blockIdx.y * strideGray + p0, g);
+        }
+    } else { // ragged tail of the frame
+        for (long long p = p0; p < P; p++) {
+            float c[3];
+            for (int ch = 0; ch < C; ch++) {
+                long long i = p * C + ch;
+                float x = Sample<T>::conv(((const T *)raws.p[blockIdx.y])[i]);
+                if (HAS_B) x = __fsub_rn(x, bias[i]);
+                if (HAS_D) x = __fsub_rn(x, dark[i]);
+                if (HAS_F) x = __fdiv_rn(x, flat[i]);
+                cal[(long long)blockIdx.y * strideCal + i] = x;
+                c[ch] = x;
+            }
+            if (C == 3)
+                gray[(long long)blockIdx.y * strideGray + p] =
+                    __fadd_rn(__fadd_rn(__fmul_rn(c[0], 0.114f), __fmul_rn(c[1], 0.587f)), __fmul_rn(c[2], 0.299f));
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// K0  master accumulation: acc = sum_f ((conv(raw_f) - sub1) - sub2), frames added in
+// order, then (last pass) acc *= r with r = float(1.0 / n_total)   [util.cpp:584-722].
+// Up to OSS_MAX_BATCH frames per launch so each master pixel is read/written once per
+// launch instead of once per calibration frame.
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_master_accumulate(const __grid_constant__ FramePtrs frames, int n, const float *__restrict__ sub1, const float *__restrict__ sub2,
+                    float *__restrict__ acc, int first, int last, float r, long long count)
+{
+    constexpr int N = Sample<T>::PX; // samples per thread
+    const long long i0 = ((long long)blockIdx.x * 256 + threadIdx.x) * N;
+    if (i0 >= count) return;
+    if (i0 + N <= count) {
+        float a[N], s1[N], s2[N], v[N];
+        if (sub1) load_f32<N>(sub1 + i0, s1);
+        if (sub2) load_f32<N>(sub2 + i0, s2);
+        if (!first) load_f32<N>(acc + i0, a);
+        for (int f = 0; f < n; f++) {
+            load_samples<T, N>((const T *)frames.p[f] + i0, v);
+#pragma unroll
+            for (int i = 0; i < N; i++) {
+                float x = v[i];
+                if (sub1) x = __fsub_rn(x, s1[i]);
+                if (sub2) x = __fsub_rn(x, s2[i]);
+                a[i] = (first && f == 0) ? x : __fadd_rn(a[i], x);
+            }
+        }
+        if (last) {
+#pragma unroll
+            for (int i = 0; i < N; i++) a[i] = __fmul_rn(a[i], r);
+        }
+        store_f32<N>(acc + i0, a);
+    } else {
+        for (long long i = i0; i < count; i++) {
+            float a = first ? 0.f : acc[i];
+            for (int f = 0; f < n; f++) {
+                float x = Sample<T>::conv(((const T *)frames.p[f])[i]);
+                if (sub1) x = __fsub_rn(x, sub1[i]);
+                if (sub2) x = __fsub_rn(x, sub2[i]);
+                a = (first && f == 0) ? x : __fadd_rn(a, x);
+            }
+            if (last) a = __fmul_rn(a, r);
+            acc[i] = a;
+        }
+    }
+}
+
+// flat /= mean(channel 0)  [util.cpp:686-688]: fp64 sum of channel 0 in a fixed order
+// (per-block partials, then one block), float avg, r = float(1.0 / double(avg)).
+__global__ void __launch_bounds__(256)
+k_channel0_partial(const float *__restrict__ img, long long P, int C, double *__restrict__ partial)
+{
+    double s = 0.0;
+    for (long long p = (long long)blockIdx.x * 256 + threadIdx.x; p < P; p += (long long)gridDim.x * 256)
+        s += (double)img[p * C];
+    __shared__ double sh[256];
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int k = 128; k > 0; k >>= 1) {
+        if (threadIdx.x < k) sh[threadIdx.x] += sh[threadIdx.x + k];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
+}
+
+__global__ void k_flat_ratio(const double *__restrict__ partial, int n, long long P, float *__restrict__ r_out)
+{
+    if (threadIdx.x || blockIdx.x) return;
+    double s = 0.0;
+    for (int i = 0; i < n; i++) s += partial[i];
+    float avg = (float)(s * (1.0 / (double)P));
+    *r_out = (float)(1.0 / (double)avg);
+}
+
+__global__ void __launch_bounds__(256)
+k_scale_by(float *__restrict__ img, long long count, const float *__restrict__ r_dev, float r_imm)
+{
+    const float r = r_dev ? *r_dev : r_imm;
+    const long long i0 = ((long long)blockIdx.x * 256 + threadIdx.x) * 4;
+    if (i0 + 4 <= count) {
+        float4 q = ((float4 *)(img + i0))[0];
+        q.x = __fmul_rn(q.x, r); q.y = __fmul_rn(q.y, r); q.z = __fmul_rn(q.z, r); q.w = __fmul_rn(q.w, r);
+        ((float4 *)(img + i0))[0] = q;
+    } else {
+        for (long long i = i0; i < count; i++) img[i] = __fmul_rn(img[i], r);
+    }
+}
+
+}  // namespace oss

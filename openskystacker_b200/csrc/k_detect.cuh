@@ -1,0 +1,514 @@
+// Kernel group (2b): thresholding, ordered compaction of candidate pixels, connected
+// components, deblending and flux-weighted centroids.
+//
+// Replaces (reference, libstacker/src/):
+//   getAdjoiningPixels / detectAdjoiningPixel   stardetector.cpp:192-246
+//   AdjoiningPixel::deblend / extract / isAdjoining / getGravityCenter  adjoiningpixel.cpp:41-118,172-202
+//   AdjoiningPixel::createStar                  adjoiningpixel.cpp:120-150
+// The reference's result depends on its traversal orders (raster order of components,
+// DFS order of pixels, peel order of the deblender); SURVEY.md Appendix D is the
+// behavioural spec.  Here:
+//   - candidates (pixels > threshold) are compacted in raster order with per-segment
+//     bit masks + an exclusive scan, so "position in the list" == raster rank;
+//   - a union-find over the sparse list labels components by their raster-first pixel,
+//     which reproduces the reference's component order;
+//   - one thread per component replays the reference's DFS and peel loops over
+//     precomputed neighbour links (no image access, no coordinate searches).
+#pragma once
+#include "common.cuh"
+
+namespace oss {
+
+// ---- generic batched exclusive scan of int32 (3 phases) -------------------------------
+// n may be device-resident (n_dev[f]) or a host constant (n_dev == nullptr).
+#define SCAN_ITEMS 4096 // per block: 1024 threads x 4
+
+__device__ __forceinline__ int block_exclusive_scan_1024(int v, int *total)
+{
+    __shared__ int wsum[32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) wsum[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        int s = wsum[lane], si = s;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, si, o);
+            if (lane >= o) si += t;
+        }
+        wsum[lane] = si - s; // exclusive warp offsets
+        if (lane == 31) *total = si;
+    }
+    __syncthreads();
+    int r = wsum[w] + inc - v;
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(1024)
+k_scan_phase1(const int *__restrict__ in, long long strideIn, int *__restrict__ out, long long strideOut,
+              const int *__restrict__ n_dev, int n_dev_stride, int n_host, int *__restrict__ blocksum, long long strideBS)
+{
+    const int f = blockIdx.y;
+    const int n = n_dev ? n_dev[(long long)f * n_dev_stride] : n_host;
+    const long long base = (long long)blockIdx.x * SCAN_ITEMS;
+    if (base >= n) return;
+    const int *src = in + f * strideIn;
+    int *dst = out + f * strideOut;
+    int v[4], s = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        long long i = base + threadIdx.x * 4 + k;
+        v[k] = i < n ? src[i] : 0;
+        s += v[k];
+    }
+    __shared__ int total;
+    int ex = block_exclusive_scan_1024(s, &total);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        long long i = base + threadIdx.x * 4 + k;
+        if (i < n) dst[i] = ex;
+        ex += v[k];
+    }
+    if (threadIdx.x == 0) blocksum[f * strideBS + blockIdx.x] = total;
+}
+
+// one block per frame: exclusive scan of the block sums, total to out[n] and *total_out
+__global__ void __launch_bounds__(1024)
+k_scan_phase2(int *__restrict__ blocksum, long long strideBS, const int *__restrict__ n_dev, int n_dev_stride,
+              int n_host, int *__restrict__ out, long long strideOut, int write_total_at_n, int *__restrict__ total_out,
+              int total_stride)
+{
+    const int f = blockIdx.x;
+    const int n = n_dev ? n_dev[(long long)f * n_dev_stride] : n_host;
+    const int nb = (n + SCAN_ITEMS - 1) / SCAN_ITEMS;
+    int *bs = blocksum + f * strideBS;
+    __shared__ int total;
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < nb; base += 1024) {
+        int i = base + threadIdx.x;
+        int v = i < nb ? bs[i] : 0;
+        int ex = block_exclusive_scan_1024(v, &total);
+        if (i < nb) bs[i] = ex + carry;
+        __syncthreads();
+        if (threadIdx.x == 0) carry += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        if (write_total_at_n) out[f * strideOut + n] = carry;
+        if (total_out) total_out[(long long)f * total_stride] = carry;
+    }
+}
+
+__global__ void __launch_bounds__(1024)
+k_scan_phase3(int *__restrict__ out, long long strideOut, const int *__restrict__ n_dev, int n_dev_stride, int n_host,
+              const int *__restrict__ blocksum, long long strideBS)
+{
+    const int f = blockIdx.y;
+    const int n = n_dev ? n_dev[(long long)f * n_dev_stride] : n_host;
+    const long long base = (long long)blockIdx.x * SCAN_ITEMS;
+    if (base >= n || blockIdx.x == 0) return;
+    const int add = blocksum[f * strideBS + blockIdx.x];
+    int *dst = out + f * strideOut;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        long long i = base + threadIdx.x * 4 + k;
+        if (i < n) dst[i] += add;
+    }
+}
+
+// ---- K4a  per-segment candidate masks ---------------------------------------------------
+// A segment is 32 consecutive pixels of one row.  Segments whose maximum (from K3) does not
+// exceed the threshold are skipped without touching the image: at t=20 that is > 99.9 %.
+__global__ void __launch_bounds__(256)
+k_segment_masks(const float *__restrict__ stars, long long strideStars, const float *__restrict__ segmax,
+                long long strideSeg, uint32_t *__restrict__ segmask, int *__restrict__ segcount,
+                const DetectState *__restrict__ ds, Geom g)
+{
+    const int f = blockIdx.y;
+    const long long nsegs = (long long)g.H * g.nseg;
+    const long long s = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (s >= nsegs) return;
+    const float th = ds[f].threshold;
+    uint32_t m = 0;
+    if (segmax[f * strideSeg + s] > th) {
+        const int y = (int)(s / g.nseg), sx = (int)(s - (long long)y * g.nseg);
+        const float *row = stars + f * strideStars + (long long)y * g.W + sx * OSS_SEG;
+        const int n = min(OSS_SEG, g.W - sx * OSS_SEG);
+        for (int b = 0; b < n; b++)
+            if (row[b] > th) m |= 1u << b;
+    }
+    segmask[f * strideSeg + s] = m;
+    segcount[f * (strideSeg + 1) + s] = __popc(m);
+}
+
+// ---- K4c  ordered compaction -----------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_compact_candidates(const float *__restrict__ stars, long long strideStars, const uint32_t *__restrict__ segmask,
+                     long long strideSeg, const int *__restrict__ segoff, int *__restrict__ cand_idx,
+                     float *__restrict__ cand_val, int *__restrict__ owner, DetectState *__restrict__ ds, Geom g)
+{
+    const int f = blockIdx.y;
+    const long long nsegs = (long long)g.H * g.nseg;
+    const long long s = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (s >= nsegs) return;
+    if (s == 0) {
+        int total = segoff[f * (strideSeg + 1) + nsegs];
+        ds[f].ncand = total;
+        if (total > g.cap) ds[f].overflow = 1;
+    }
+    uint32_t m = segmask[f * strideSeg + s];
+    if (!m) return;
+    int o = segoff[f * (strideSeg + 1) + s];
+    const int y = (int)(s / g.nseg), sx = (int)(s - (long long)y * g.nseg);
+    const int lin0 = y * g.W + sx * OSS_SEG;
+    const float *row = stars + f * strideStars + lin0;
+    while (m) {
+        int b = __ffs(m) - 1;
+        m &= m - 1;
+        if (o < g.cap) {
+            long long q = (long long)f * g.cap + o;
+            cand_idx[q] = lin0 + b;
+            cand_val[q] = row[b];
+            owner[q] = -3; // not yet visited by the component walk
+        }
+        o++;
+    }
+}
+
+// position of pixel (x, y) in the candidate list, or -1
+__device__ __forceinline__ int cand_lookup(const uint32_t *segmask, const int *segoff, int nseg, int x, int y)
+{
+    long long s = (long long)y * nseg + (x >> 5);
+    uint32_t m = segmask[s];
+    int b = x & 31;
+    if (!((m >> b) & 1u)) return -1;
+    return segoff[s] + __popc(m & ((1u << b) - 1u));
+}
+
+// ---- K5a  neighbour links + union-find init -------------------------------------------
+// nbr = (up, left, right, down) positions, the reference's push order (stardetector.cpp:231-242)
+__global__ void __launch_bounds__(256)
+k_links(const int *__restrict__ cand_idx, const uint32_t *__restrict__ segmask, long long strideSeg,
+        const int *__restrict__ segoff, int4 *__restrict__ nbr, int *__restrict__ parent,
+        int *__restrict__ comp_size, int *__restrict__ comp_peak, const DetectState *__restrict__ ds, Geom g)
+{
+    const int f = blockIdx.y;
+    if (ds[f].overflow) return;
+    const int n = ds[f].ncand;
+    const uint32_t *mk = segmask + f * strideSeg;
+    const int *so = segoff + f * (strideSeg + 1);
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+        long long q = (long long)f * g.cap + i;
+        int lin = cand_idx[q];
+        int y = lin / g.W, x = lin - y * g.W;
+        int4 nb;
+        nb.x = y > 0 ? cand_lookup(mk, so, g.nseg, x, y - 1) : -1;
+        nb.y = x > 0 ? cand_lookup(mk, so, g.nseg, x - 1, y) : -1;
+        nb.z = x + 1 < g.W ? cand_lookup(mk, so, g.nseg, x + 1, y) : -1;
+        nb.w = y + 1 < g.H ? cand_lookup(mk, so, g.nseg, x, y + 1) : -1;
+        nbr[q] = nb;
+        parent[q] = i;
+        comp_size[q] = 0;
+        comp_peak[q] = 0;
+    }
+}
+
+__device__ __forceinline__ int uf_find(int *parent, int i)
+{
+    int p = parent[i];
+    while (p != i) { i = p; p = parent[i]; }
+    return i;
+}
+
+__device__ __forceinline__ void uf_union(int *parent, int a, int b)
+{
+    for (;;) {
+        a = uf_find(parent, a);
+        b = uf_find(parent, b);
+        if (a == b) return;
+        if (a < b) { int t = a; a = b; b = t; } // a > b: hook the larger root under the smaller
+        int old = atomicMin(&parent[a], b);
+        if (old == a) return;
+        a = old;
+    }
+}
+
+// ---- K5b  union with the up and left neighbours (4-connectivity) ------------------------
+__global__ void __launch_bounds__(256)
+k_ccl_union(const int4 *__restrict__ nbr, int *__restrict__ parent, const DetectState *__restrict__ ds, Geom g)
+{
+    const int f = blockIdx.y;
+    if (ds[f].overflow) return;
+    const int n = ds[f].ncand;
+    int *par = parent + (long long)f * g.cap;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+        int4 nb = nbr[(long long)f * g.cap + i];
+        if (nb.x >= 0) uf_union(par, i, nb.x);
+        if (nb.y >= 0) uf_union(par, i, nb.y);
+    }
+}
+
+// ---- K5c  flatten labels, component size and peak (label = raster-first pixel) ----------
+__global__ void __launch_bounds__(256)
+k_ccl_flatten(int *__restrict__ parent, const float *__restrict__ cand_val, int *__restrict__ comp_size,
+              int *__restrict__ comp_peak, const DetectState *__restrict__ ds, Geom g)
+{
+    const int f = blockIdx.y;
+    if (ds[f].overflow) return;
+    const int n = ds[f].ncand;
+    int *par = parent + (long long)f * g.cap;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+        int r = uf_find(par, i);
+        par[i] = r; // benign race: every writer stores a valid ancestor, roots never change here
+        atomicAdd(&comp_size[(long long)f * g.cap + r], 1);
+        // candidates are > threshold >= 0, so their bit patterns order like ints
+        atomicMax(&comp_peak[(long long)f * g.cap + r], __float_as_int(cand_val[(long long)f * g.cap + i]));
+    }
+}
+
+// flag[i] = 1 for roots whose component passes peak > minPeak (stardetector.cpp:201);
+// flag2[i] = component pixel count for those roots (scanned into scratch offsets)
+__global__ void __launch_bounds__(256)
+k_root_flags(const int *__restrict__ parent, const int *__restrict__ comp_size, const int *__restrict__ comp_peak,
+             int *__restrict__ flag, int *__restrict__ flag2, const DetectState *__restrict__ ds, Geom g)
+{
+    const int f = blockIdx.y;
+    if (ds[f].overflow) return;
+    const int n = ds[f].ncand;
+    const float minpeak = ds[f].minpeak;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+        long long q = (long long)f * g.cap + i;
+        int keep = parent[q] == i && __int_as_float(comp_peak[q]) > minpeak;
+        flag[q] = keep;
+        flag2[q] = keep ? comp_size[q] : 0;
+    }
+}
+
+// comp_root[c] = list position of component c's first pixel, comp_off[c] = scratch offset
+__global__ void __launch_bounds__(256)
+k_gather_roots(const int *__restrict__ flag, const int *__restrict__ flagscan, const int *__restrict__ sizescan,
+               int *__restrict__ comp_root, int *__restrict__ comp_off, const DetectState *__restrict__ ds, Geom g)
+{
+    const int f = blockIdx.y;
+    if (ds[f].overflow) return;
+    const int n = ds[f].ncand;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+        long long q = (long long)f * g.cap + i;
+        if (flag[q]) {
+            long long c = (long long)f * g.cap + flagscan[q];
+            comp_root[c] = i;
+            comp_off[c] = sizescan[q];
+        }
+    }
+}
+
+// ---- K6  per-component replay of the reference's sequential logic -----------------------
+struct CompScratch {
+    int *list;    // [n]   pixels in the reference's DFS order
+    int *stack;   // [4n+1]
+    int *S;       // [n]   current peeled region, extraction order
+    int *sorted;  // [n]
+    int *acc_gx, *acc_gy, *stamp; // [n] per accepted region
+};
+
+// createStar (adjoiningpixel.cpp:120-150) over region S[0..ns) (positions into the lists)
+__device__ oss_star create_star(const int *S, int ns, int *sorted, const int *__restrict__ cand_idx,
+                                const float *__restrict__ cand_val, int W)
+{
+    oss_star st;
+    st.area = ns;
+    float peak = 0.f, value = 0.f;
+    for (int q = 0; q < ns; q++) {
+        float v = cand_val[S[q]];
+        if (q == 0 || peak < v) peak = v;
+        value = __fadd_rn(value, v);
+        sorted[q] = q;
+    }
+    st.peak = peak;
+    st.value = value;
+    // ascending by (value, extraction order): heap sort on indices into S
+    auto less = [&](int a, int b) {
+        float va = cand_val[S[a]], vb = cand_val[S[b]];
+        return va < vb || (va == vb && a < b);
+    };
+    auto sift = [&](int start, int end) {
+        int root = start;
+        for (;;) {
+            int child = 2 * root + 1;
+            if (child > end) break;
+            if (child + 1 <= end && less(sorted[child], sorted[child + 1])) child++;
+            if (less(sorted[root], sorted[child])) {
+                int t = sorted[root]; sorted[root] = sorted[child]; sorted[child] = t;
+                root = child;
+            } else break;
+        }
+    };
+    if (ns <= 24) { // insertion sort
+        for (int i = 1; i < ns; i++) {
+            int key = sorted[i], j = i - 1;
+            while (j >= 0 && less(key, sorted[j])) { sorted[j + 1] = sorted[j]; j--; }
+            sorted[j + 1] = key;
+        }
+    } else {
+        for (int start = (ns - 2) / 2; start >= 0; start--) sift(start, ns - 1);
+        for (int end = ns - 1; end > 0; end--) {
+            int t = sorted[0]; sorted[0] = sorted[end]; sorted[end] = t;
+            sift(0, end - 1);
+        }
+    }
+    float xa = 0.f, ya = 0.f, wt = 0.f;
+    for (int q = 0; q < ns; q++) {
+        int i = S[sorted[q]];
+        int lin = cand_idx[i];
+        int y = lin / W, x = lin - y * W;
+        double v = (double)cand_val[i];
+        xa = (float)__dadd_rn((double)xa, __dmul_rn((double)x + 0.5, v));
+        ya = (float)__dadd_rn((double)ya, __dmul_rn((double)y + 0.5, v));
+        wt = __fadd_rn(wt, cand_val[i]);
+    }
+    st.x = (int)__fdiv_rn(xa, wt);
+    st.y = (int)__fdiv_rn(ya, wt);
+    return st;
+}
+
+__global__ void __launch_bounds__(64)
+k_components(const int *__restrict__ cand_idx, const float *__restrict__ cand_val, const int4 *__restrict__ nbr,
+             int *__restrict__ owner, const int *__restrict__ comp_size, const int *__restrict__ comp_root,
+             const int *__restrict__ comp_off, int *__restrict__ comp_nstar, int *__restrict__ scratch,
+             oss_star *__restrict__ star_tmp, const DetectState *__restrict__ ds, Geom g)
+{
+    const int f = blockIdx.y;
+    if (ds[f].overflow) return;
+    const int ncomp = ds[f].ncomp;
+    const long long fb = (long long)f * g.cap;
+    const int *cidx = cand_idx + fb;
+    const float *cval = cand_val + fb;
+    const int4 *nb = nbr + fb;
+    int *own = owner + fb;
+    int *scr = scratch + 12 * fb;
+    const float step = ds[f].threshold;
+
+    for (int c = blockIdx.x * 64 + threadIdx.x; c < ncomp; c += gridDim.x * 64) {
+        const int root = comp_root[fb + c];
+        const int n = comp_size[fb + root];
+        const int off = comp_off[fb + c];
+        int *list = scr + off;
+        int *S = scr + g.cap + off;
+        int *sorted = scr + 2 * (long long)g.cap + off;
+        int *acc_gx = scr + 3 * (long long)g.cap + off;
+        int *acc_gy = scr + 4 * (long long)g.cap + off;
+        int *stamp = scr + 5 * (long long)g.cap + off;
+        int *stack = scr + 6 * (long long)g.cap + 4 * (long long)off + c; // 4n+1 entries
+        oss_star *out = star_tmp + fb + off;
+
+        // detectAdjoiningPixel: explicit-stack DFS, push order up, left, right, down
+        int np = 0, sp = 0;
+        stack[sp++] = root;
+        while (sp > 0) {
+            int i = stack[--sp];
+            if (own[i] != -3) continue;
+            own[i] = -1; // REMAINING (for the deblender)
+            list[np++] = i;
+            int4 q = nb[i];
+            if (q.x >= 0 && own[q.x] == -3) stack[sp++] = q.x;
+            if (q.y >= 0 && own[q.y] == -3) stack[sp++] = q.y;
+            if (q.z >= 0 && own[q.z] == -3) stack[sp++] = q.z;
+            if (q.w >= 0 && own[q.w] == -3) stack[sp++] = q.w;
+        }
+
+        int nout = 0;
+        if (n >= OSS_DEBLEND_MAX) { // adjoiningpixel.cpp:45-48
+            out[nout++] = create_star(list, n, sorted, cidx, cval, g.W);
+            comp_nstar[fb + c] = nout;
+            continue;
+        }
+        int left = n, nacc = 0, iter = 0;
+        while (left > 0) {
+            iter++;
+            int pk = -1;
+            float mx = 0.f;
+            for (int q = 0; q < n; q++) { // getPeak: first maximum in list order
+                int i = list[q];
+                if (own[i] != -1) continue;
+                float v = cval[i];
+                if (pk < 0 || mx < v) { pk = i; mx = v; }
+            }
+            // adjoiningpixel.cpp:57
+            float T = (float)__dsub_rn((double)mx, __dmul_rn((double)step, sqrt(__dadd_rn((double)__fdiv_rn(mx, step), 1.0))));
+            // extract(): recursive pre-order up, left, right, down == stack with reversed pushes
+            int ns = 0;
+            sp = 0;
+            stack[sp++] = pk;
+            while (sp > 0) {
+                int i = stack[--sp];
+                if (own[i] != -1 || !(cval[i] > T)) continue;
+                own[i] = -2; // DROPPED unless accepted below
+                S[ns++] = i;
+                int4 q = nb[i];
+                if (q.w >= 0 && own[q.w] == -1) stack[sp++] = q.w;
+                if (q.z >= 0 && own[q.z] == -1) stack[sp++] = q.z;
+                if (q.y >= 0 && own[q.y] == -1) stack[sp++] = q.y;
+                if (q.x >= 0 && own[q.x] == -1) stack[sp++] = q.x;
+            }
+            if (ns == 0) break; // step <= 0 or NaN: the reference would never terminate
+            left -= ns;
+            // getGravityCenter (adjoiningpixel.cpp:104-118): fp32, list order, truncated
+            float gx = 0.f, gy = 0.f, gw = 0.f;
+            for (int q = 0; q < ns; q++) {
+                int i = S[q];
+                int lin = cidx[i];
+                int y = lin / g.W, x = lin - y * g.W;
+                float v = cval[i];
+                gx = __fadd_rn(gx, __fmul_rn(v, (float)x));
+                gy = __fadd_rn(gy, __fmul_rn(v, (float)y));
+                gw = __fadd_rn(gw, v);
+            }
+            int cx = (int)__fdiv_rn(gx, gw), cy = (int)__fdiv_rn(gy, gw);
+            // isAdjoining against every accepted region
+            for (int q = 0; q < ns; q++) {
+                int4 t = nb[S[q]];
+                if (t.x >= 0 && own[t.x] >= 0) stamp[own[t.x]] = iter;
+                if (t.y >= 0 && own[t.y] >= 0) stamp[own[t.y]] = iter;
+                if (t.z >= 0 && own[t.z] >= 0) stamp[own[t.z]] = iter;
+                if (t.w >= 0 && own[t.w] >= 0) stamp[own[t.w]] = iter;
+            }
+            int blending = 0;
+            for (int a = 0; a < nacc; a++)
+                if (stamp[a] == iter || (acc_gx[a] == cx && acc_gy[a] == cy)) blending++;
+            if (blending == 0) {
+                for (int q = 0; q < ns; q++) own[S[q]] = nacc;
+                acc_gx[nacc] = cx; acc_gy[nacc] = cy; stamp[nacc] = 0;
+                nacc++;
+                out[nout++] = create_star(S, ns, sorted, cidx, cval, g.W);
+            }
+        }
+        comp_nstar[fb + c] = nout;
+    }
+}
+
+// final ordered star list: stars of component c go to star_out[staroff[c] ...]
+__global__ void __launch_bounds__(256)
+k_gather_stars(const oss_star *__restrict__ star_tmp, const int *__restrict__ comp_off,
+               const int *__restrict__ comp_nstar, const int *__restrict__ comp_staroff,
+               oss_star *__restrict__ star_out, const DetectState *__restrict__ ds, Geom g)
+{
+    const int f = blockIdx.y;
+    if (ds[f].overflow) return;
+    const int ncomp = ds[f].ncomp;
+    const long long fb = (long long)f * g.cap;
+    for (int c = blockIdx.x * 256 + threadIdx.x; c < ncomp; c += gridDim.x * 256) {
+        int n = comp_nstar[fb + c], so = comp_staroff[fb + c], off = comp_off[fb + c];
+        for (int s = 0; s < n; s++) star_out[fb + so + s] = star_tmp[fb + off + s];
+    }
+}
+
+}  // namespace oss

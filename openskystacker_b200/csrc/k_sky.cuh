@@ -1,0 +1,235 @@
+// Kernel group (2a): sky-background estimation, sky subtraction and the ROI statistics.
+//
+// Replaces (reference, libstacker/src/stardetector.cpp):
+//   generateSkyBackground :158-171  resize(W/8,H/8) -> medianBlur 5 -> resize(W,H) -> GaussianBlur 31x31
+//   stars = gray - sky    :120
+//   meanStdDev over Rect(W/20, H/20, int(.9W), int(.9H)), threshold / minPeak  :121-129
+// Operation orders are the bit-exact models of SURVEY.md Appendix B.3-B.6 (no FMA).
+#pragma once
+#include "common.cuh"
+
+namespace oss {
+
+// One tap pair of cv::resize INTER_LINEAR along one axis (Appendix B.3).
+struct ResizeTap { int i0, i1; float w0, w1; };
+
+// axis_is_x: x zeroes the fraction at the borders, y keeps it but clamps the rows.
+__global__ void k_resize_taps(ResizeTap *__restrict__ taps, int src_n, int dst_n, int axis_is_x)
+{
+    int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= dst_n) return;
+    double scale = (double)src_n / (double)dst_n;
+    float f = (float)(((double)d + 0.5) * scale - 0.5);
+    int s = (int)floorf(f);
+    f = __fsub_rn(f, (float)s);
+    ResizeTap t;
+    if (axis_is_x) {
+        if (s < 0) { f = 0.f; s = 0; }
+        if (s >= src_n - 1) { f = 0.f; s = src_n - 1; }
+        t.i0 = s;
+        t.i1 = min(s + 1, src_n - 1);
+    } else {
+        t.i0 = min(max(s, 0), src_n - 1);
+        t.i1 = min(max(s + 1, 0), src_n - 1);
+    }
+    t.w0 = __fsub_rn(1.f, f);
+    t.w1 = f;
+    taps[d] = t;
+}
+
+__device__ __forceinline__ float lerp2(float a, float w0, float b, float w1)
+{
+    return __fadd_rn(__fmul_rn(a, w0), __fmul_rn(b, w1));
+}
+
+// resize gray (W,H) -> (lw,lh): horizontal lerp of both source rows, then vertical.
+__global__ void __launch_bounds__(256)
+k_resize_down(const float *__restrict__ gray, long long strideGray, int W, const ResizeTap *__restrict__ tx,
+              const ResizeTap *__restrict__ ty, float *__restrict__ lo, long long strideLo, int lw, int lh)
+{
+    int dx = blockIdx.x * 32 + (threadIdx.x & 31), dy = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (dx >= lw || dy >= lh) return;
+    const float *g = gray + blockIdx.z * strideGray;
+    ResizeTap a = tx[dx], b = ty[dy];
+    const float *r0 = g + (long long)b.i0 * W, *r1 = g + (long long)b.i1 * W;
+    float h0 = lerp2(__ldg(r0 + a.i0), a.w0, __ldg(r0 + a.i1), a.w1);
+    float h1 = lerp2(__ldg(r1 + a.i0), a.w0, __ldg(r1 + a.i1), a.w1);
+    lo[blockIdx.z * strideLo + (long long)dy * lw + dx] = lerp2(h0, b.w0, h1, b.w1);
+}
+
+// medianBlur ksize 5, BORDER_REPLICATE: exact median of 25 (Appendix B.4)
+__global__ void __launch_bounds__(256)
+k_median5(const float *__restrict__ lo, float *__restrict__ med, long long strideLo, int lw, int lh)
+{
+    int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= lw || y >= lh) return;
+    const float *s = lo + blockIdx.z * strideLo;
+    float v[25];
+#pragma unroll
+    for (int dy = -2; dy <= 2; dy++) {
+        int yy = min(max(y + dy, 0), lh - 1);
+#pragma unroll
+        for (int dx = -2; dx <= 2; dx++) {
+            int xx = min(max(x + dx, 0), lw - 1);
+            v[(dy + 2) * 5 + dx + 2] = __ldg(s + (long long)yy * lw + xx);
+        }
+    }
+    // 13 rounds of min-extraction, fully unrolled so v[] stays in registers
+#pragma unroll
+    for (int i = 0; i <= 12; i++) {
+#pragma unroll
+        for (int j = i + 1; j < 25; j++) {
+            float lo_ = fminf(v[i], v[j]), hi_ = fmaxf(v[i], v[j]);
+            v[i] = lo_; v[j] = hi_;
+        }
+    }
+    med[blockIdx.z * strideLo + (long long)y * lw + x] = v[12];
+}
+
+// cv::getGaussianKernel(31, sigma 5.0, CV_32F) as cv2 4.13 returns it (taps 0..15; symmetric)
+__constant__ float c_gauss[31];
+static const uint32_t kGaussBits[16] = {
+    0x3a68cc99u, 0x3acfe4e8u, 0x3b325fb9u, 0x3b930b60u, 0x3be8ede4u, 0x3c314133u,
+    0x3c819931u, 0x3cb61437u, 0x3cf5c7e8u, 0x3d1f615cu, 0x3d4699a0u, 0x3d6dc47au,
+    0x3d88bfb5u, 0x3d972180u, 0x3da079edu, 0x3da3b7d6u};
+
+// ---------------------------------------------------------------------------------------
+// K3  sky_sub_stats.  One CTA produces a 64x64 tile of stars = gray - sky:
+//   phase 1  upsample the median grid (resize taps) over the tile + 15 px apron, with the
+//            Gaussian's BORDER_REFLECT_101 applied to the FULL-RES coordinates;
+//   phase 2  31-tap row filter, taps accumulated k = 0..30 in order;
+//   phase 3  column filter as centre + 15 symmetric pairs; subtract from gray; write;
+//            fp64 sum / sum-of-squares over the statistics ROI; per-32-px-segment maximum
+//            (lets the thresholding pass skip empty segments).
+// HBM traffic: gray read once (4 B/px), stars written once (4 B/px).  The arithmetic
+// (about 110 non-fusable fp32 ops per pixel) makes this kernel ALU-bound, not HBM-bound.
+#define SKY_T 64
+#define SKY_R 15
+#define SKY_A (SKY_T + 2 * SKY_R) // 94
+#define SKY_UP_LD 96
+constexpr int kSkySmemBytes = (SKY_A * SKY_UP_LD + SKY_A * SKY_T) * 4 + 2 * SKY_A * (int)sizeof(ResizeTap);
+
+__global__ void __launch_bounds__(256)
+k_sky_sub_stats(const float *__restrict__ gray, long long strideGray, const float *__restrict__ med,
+                long long strideLo, int lw, const ResizeTap *__restrict__ ux, const ResizeTap *__restrict__ uy,
+                float *__restrict__ stars, long long strideStars, float *__restrict__ segmax, long long strideSeg,
+                int nseg, double *__restrict__ partials, long long stridePart, Geom g)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *up = (float *)smem_raw;              // [SKY_A][SKY_UP_LD]
+    float *rf = up + SKY_A * SKY_UP_LD;         // [SKY_A][SKY_T]
+    ResizeTap *tcol = (ResizeTap *)(rf + SKY_A * SKY_T); // [SKY_A]
+    ResizeTap *trow = tcol + SKY_A;             // [SKY_A]
+
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * SKY_T, y0 = blockIdx.y * SKY_T, f = blockIdx.z;
+    const float *L = med + f * strideLo;
+
+    for (int i = tid; i < 2 * SKY_A; i += 256) {
+        if (i < SKY_A) tcol[i] = ux[reflect101(x0 - SKY_R + i, g.W)];
+        else trow[i - SKY_A] = uy[reflect101(y0 - SKY_R + (i - SKY_A), g.H)];
+    }
+    __syncthreads();
+
+    // phase 1: up[r][c] = resize(med)(reflect(y0-15+r), reflect(x0-15+c))
+    for (int i = tid; i < SKY_A * SKY_A; i += 256) {
+        int r = i / SKY_A, c = i - r * SKY_A;
+        ResizeTap a = tcol[c], b = trow[r];
+        const float *r0 = L + (long long)b.i0 * lw, *r1 = L + (long long)b.i1 * lw;
+        float h0 = lerp2(__ldg(r0 + a.i0), a.w0, __ldg(r0 + a.i1), a.w1);
+        float h1 = lerp2(__ldg(r1 + a.i0), a.w0, __ldg(r1 + a.i1), a.w1);
+        up[r * SKY_UP_LD + c] = lerp2(h0, b.w0, h1, b.w1);
+    }
+    __syncthreads();
+
+    // phase 2: row filter
+    for (int i = tid; i < SKY_A * SKY_T; i += 256) {
+        int r = i >> 6, c = i & 63;
+        const float *u = up + r * SKY_UP_LD + c;
+        float s = __fmul_rn(c_gauss[0], u[0]);
+#pragma unroll
+        for (int j = 1; j < 31; j++) s = __fadd_rn(s, __fmul_rn(c_gauss[j], u[j]));
+        rf[i] = s;
+    }
+    __syncthreads();
+
+    // phase 3: column filter, subtract, statistics
+    double sum = 0.0, sq = 0.0;
+    const float *G = gray + f * strideGray;
+    float *S = stars + f * strideStars;
+    for (int i = tid; i < SKY_T * SKY_T; i += 256) {
+        int r = i >> 6, c = i & 63;
+        const float *q = rf + (r + SKY_R) * SKY_T + c;
+        float s = __fmul_rn(c_gauss[15], q[0]);
+#pragma unroll
+        for (int j = 1; j <= 15; j++)
+            s = __fadd_rn(s, __fmul_rn(c_gauss[15 + j], __fadd_rn(q[j * SKY_T], q[-j * SKY_T])));
+        int x = x0 + c, y = y0 + r;
+        float v = -INFINITY;
+        if (x < g.W && y < g.H) {
+            long long p = (long long)y * g.W + x;
+            v = __fsub_rn(__ldg(G + p), s);
+            S[p] = v;
+            if (x >= g.roi_x && x < g.roi_x + g.roi_w && y >= g.roi_y && y < g.roi_y + g.roi_h) {
+                double d = (double)v;
+                sum += d;
+                sq += d * d;
+            }
+        }
+        float m = v;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if ((tid & 31) == 0 && y < g.H && (x >> 5) < nseg)
+            segmax[f * strideSeg + (long long)y * nseg + (x >> 5)] = m;
+    }
+    // block reduction of the fp64 partial sums, fixed order
+    __shared__ double sh[2][8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    }
+    if ((tid & 31) == 0) { sh[0][tid >> 5] = sum; sh[1][tid >> 5] = sq; }
+    __syncthreads();
+    if (tid == 0) {
+        double a = 0.0, b = 0.0;
+        for (int w = 0; w < 8; w++) { a += sh[0][w]; b += sh[1][w]; }
+        long long blk = (long long)blockIdx.y * gridDim.x + blockIdx.x;
+        partials[f * stridePart + 2 * blk] = a;
+        partials[f * stridePart + 2 * blk + 1] = b;
+    }
+}
+
+// sigma, threshold = float(sigma*t*1.5), minPeak = float(sigma*t*2.0)  [stardetector.cpp:125-129]
+__global__ void k_finalize_stats(const double *__restrict__ partials, long long stridePart, int nblocks,
+                                 DetectState *__restrict__ ds, int threshold_coeff, Geom g)
+{
+    const int f = blockIdx.x;
+    __shared__ double sh[2][256];
+    double a = 0.0, b = 0.0;
+    for (int i = threadIdx.x; i < nblocks; i += 256) {
+        a += partials[f * stridePart + 2 * i];
+        b += partials[f * stridePart + 2 * i + 1];
+    }
+    sh[0][threadIdx.x] = a; sh[1][threadIdx.x] = b;
+    __syncthreads();
+    for (int k = 128; k > 0; k >>= 1) {
+        if (threadIdx.x < k) { sh[0][threadIdx.x] += sh[0][threadIdx.x + k]; sh[1][threadIdx.x] += sh[1][threadIdx.x + k]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        double scale = 1.0 / ((double)g.roi_w * (double)g.roi_h);
+        double m = __dmul_rn(sh[0][0], scale);
+        double var = __dsub_rn(__dmul_rn(sh[1][0], scale), __dmul_rn(m, m));
+        if (var < 0.0) var = 0.0;
+        double sigma = sqrt(var);
+        DetectState d;
+        d.mean = m; d.sigma = sigma;
+        d.threshold = (float)(sigma * (double)threshold_coeff * 1.5);
+        d.minpeak = (float)(sigma * (double)threshold_coeff * 2.0);
+        d.ncand = 0; d.nroots = 0; d.ncomp = 0; d.nstars = 0; d.overflow = 0; d.pad = 0;
+        ds[f] = d;
+    }
+}
+
+}  // namespace oss

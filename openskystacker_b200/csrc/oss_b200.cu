@@ -1,0 +1,1008 @@
+// liboss_b200.so — host side of the C ABI declared in include/oss_b200.h.
+// Orchestrates the sm_100a kernels of k_*.cuh on one GPU: stream-ordered, batched over
+// frames, no host round trip inside a batch.  There is no CPU fallback anywhere in this
+// file: without a CUDA device every entry point fails with OSS_E_CUDA.
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "k_calibrate.cuh"
+#include "k_detect.cuh"
+#include "k_focas.cuh"
+#include "k_sky.cuh"
+#include "k_warp.cuh"
+
+using namespace oss;
+
+// ----------------------------------------------------------------------------------------
+struct ProfEntry { std::string name; double ms; int launches; };
+struct ProfPending { int entry; cudaEvent_t a, b; };
+
+struct NcclApi {
+    void *handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Reduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+static NcclApi g_nccl;
+
+static bool nccl_load(std::string *why)
+{
+    if (g_nccl.handle) return true;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    void *h = nullptr;
+    for (const char *n : names) {
+        h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (h) break;
+    }
+    if (!h) { *why = std::string("cannot load NCCL: ") + dlerror(); return false; }
+#define SYM(field, name) *(void **)(&g_nccl.field) = dlsym(h, name); if (!g_nccl.field) { *why = "NCCL symbol missing: " name; return false; }
+    SYM(GetUniqueId, "ncclGetUniqueId")
+    SYM(CommInitRank, "ncclCommInitRank")
+    SYM(CommDestroy, "ncclCommDestroy")
+    SYM(Broadcast, "ncclBroadcast")
+    SYM(Reduce, "ncclReduce")
+    SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+    g_nccl.handle = h;
+    return true;
+}
+
+struct oss_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    std::string err;
+    Geom g{};
+    bool has_geom = false;
+    int slots = 0;
+    size_t frame_bytes = 0;
+    std::vector<void *> allocs; // geometry-scoped device allocations
+    std::vector<void *> user_allocs;
+    float *master[4] = {nullptr, nullptr, nullptr, nullptr};
+    float *sum = nullptr, *ref_cal = nullptr, *result = nullptr;
+    bool has_ref = false, ref_in_sum = true;
+    int threshold = 20;
+    int *d_valid = nullptr;
+    int extra_valid = 0; // lights counted on other ranks (after oss_comm_reduce)
+    Workspace ws{};
+    ResizeTap *dx = nullptr, *dy = nullptr, *ux = nullptr, *uy = nullptr;
+    RefTriangles *d_ref = nullptr, *d_ref_tmp = nullptr;
+    int *d_xy = nullptr, *d_nxy = nullptr; // [slots + 1] star lists for alignment (last = reference)
+    int *d_dbg_matches = nullptr, *d_dbg_table = nullptr;
+    float *d_M = nullptr, *d_flat_ratio = nullptr;
+    double *d_flat_partial = nullptr;
+    unsigned char *raw_stage[2] = {nullptr, nullptr};
+    cudaEvent_t copy_done[2] = {nullptr, nullptr}, raw_free[2] = {nullptr, nullptr};
+    long long batch_counter = 0;
+    // host-side mirrors (pinned), one entry per light handed in so far
+    std::vector<DetectState *> h_ds_chunks;
+    std::vector<AlignOut *> h_al_chunks;
+    int nlights = 0;
+    std::vector<oss_star> ref_stars;
+    oss_detect_info ref_info{};
+    // instrumentation
+    bool profiling = false;
+    std::vector<ProfEntry> prof;
+    std::vector<ProfPending> prof_pending;
+    std::vector<cudaEvent_t> event_pool;
+    long long launches = 0;
+    // multi-GPU
+    ncclComm_t comm = nullptr;
+    int rank = 0, nranks = 1;
+};
+
+static const int kChunk = 1024;
+
+static int fail(oss_ctx *c, int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf;
+    return code;
+}
+
+#define CK(call)                                                                                      \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess)                                                                        \
+            return fail(c, OSS_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+#define NK(call)                                                                                      \
+    do {                                                                                              \
+        ncclResult_t r_ = (call);                                                                     \
+        if (r_ != ncclSuccess)                                                                        \
+            return fail(c, OSS_E_CUDA, "%s failed: %s", #call, g_nccl.GetErrorString(r_));           \
+    } while (0)
+
+// ---- profiling-aware launch ------------------------------------------------------------
+static int prof_entry(oss_ctx *c, const char *name)
+{
+    for (size_t i = 0; i < c->prof.size(); i++)
+        if (c->prof[i].name == name) return (int)i;
+    c->prof.push_back({name, 0.0, 0});
+    return (int)c->prof.size() - 1;
+}
+
+static cudaEvent_t get_event(oss_ctx *c)
+{
+    if (!c->event_pool.empty()) { cudaEvent_t e = c->event_pool.back(); c->event_pool.pop_back(); return e; }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+
+static void prof_flush(oss_ctx *c)
+{
+    for (auto &p : c->prof_pending) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) { c->prof[p.entry].ms += ms; c->prof[p.entry].launches++; }
+        c->event_pool.push_back(p.a);
+        c->event_pool.push_back(p.b);
+    }
+    c->prof_pending.clear();
+}
+
+#define LAUNCH(name, kern, grid, block, smem, ...)                                   \
+    do {                                                                             \
+        ProfPending pp_{-1, nullptr, nullptr};                                       \
+        if (c->profiling) {                                                          \
+            pp_.entry = prof_entry(c, name);                                         \
+            pp_.a = get_event(c); pp_.b = get_event(c);                              \
+            cudaEventRecord(pp_.a, c->stream);                                       \
+        }                                                                            \
+        kern<<<grid, block, smem, c->stream>>>(__VA_ARGS__);                         \
+        c->launches++;                                                               \
+        if (c->profiling) { cudaEventRecord(pp_.b, c->stream); c->prof_pending.push_back(pp_); } \
+        CK(cudaGetLastError());                                                      \
+    } while (0)
+
+template <typename T>
+static int dalloc(oss_ctx *c, T **p, size_t count, bool geom_scoped = true)
+{
+    void *q = nullptr;
+    cudaError_t e = cudaMalloc(&q, count * sizeof(T) + 256);
+    if (e != cudaSuccess) return fail(c, OSS_E_NOMEM, "cudaMalloc(%zu bytes) failed: %s", count * sizeof(T), cudaGetErrorString(e));
+    if (geom_scoped) c->allocs.push_back(q);
+    *p = (T *)q;
+    return OSS_OK;
+}
+#define DA(ptr, count) do { int r_ = dalloc(c, &(ptr), (size_t)(count)); if (r_) return r_; } while (0)
+
+static void free_geometry(oss_ctx *c)
+{
+    cudaDeviceSynchronize();
+    for (void *p : c->allocs) cudaFree(p);
+    c->allocs.clear();
+    for (int i = 0; i < 4; i++) c->master[i] = nullptr;
+    for (int i = 0; i < 2; i++) {
+        c->raw_stage[i] = nullptr;
+        if (c->copy_done[i]) { cudaEventDestroy(c->copy_done[i]); c->copy_done[i] = nullptr; }
+        if (c->raw_free[i]) { cudaEventDestroy(c->raw_free[i]); c->raw_free[i] = nullptr; }
+    }
+    c->has_geom = false;
+    c->has_ref = false;
+}
+
+// ---- exported: lifetime ----------------------------------------------------------------
+extern "C" {
+
+const char *oss_version(void) { return "oss-b200 0.1 (sm_100a)"; }
+
+const char *oss_status_string(int s)
+{
+    switch (s) {
+    case OSS_OK: return "ok";
+    case OSS_E_CUDA: return "CUDA/NCCL failure or no CUDA device (this library has no CPU path)";
+    case OSS_E_ARG: return "bad argument or call order";
+    case OSS_E_TYPE: return "Images must be the same type.";
+    case OSS_E_SIZE: return "Images must all be the same size.";
+    case OSS_E_THREADS: return "Number of threads must be at least 1.";
+    case OSS_E_NO_ALIGNED: return "No images could be aligned to the reference image. Try using a lower tolerance.";
+    case OSS_E_CAPACITY: return "detection workspace capacity exceeded";
+    case OSS_E_NOMEM: return "out of device memory";
+    }
+    return "unknown";
+}
+
+int oss_create(oss_ctx **out, int device)
+{
+    if (!out) return OSS_E_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return OSS_E_CUDA;
+    if (device < 0 || device >= ndev) return OSS_E_ARG;
+    oss_ctx *c = new oss_ctx();
+    c->device = device;
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete c;
+        return OSS_E_CUDA;
+    }
+    // constant tables
+    float taps[31];
+    for (int i = 0; i < 16; i++) { memcpy(&taps[i], &kGaussBits[i], 4); taps[30 - i] = taps[i]; }
+    std::vector<uint32_t> ijk;
+    for (int i = 0; i < OSS_NOBJS - 2; i++)
+        for (int j = i + 1; j < OSS_NOBJS - 1; j++)
+            for (int k = j + 1; k < OSS_NOBJS; k++) ijk.push_back((uint32_t)i | ((uint32_t)j << 8) | ((uint32_t)k << 16));
+    if (cudaMemcpyToSymbol(c_gauss, taps, sizeof taps) != cudaSuccess ||
+        cudaMemcpyToSymbol(d_tri_ijk, ijk.data(), ijk.size() * 4) != cudaSuccess ||
+        cudaFuncSetAttribute(k_sky_sub_stats, cudaFuncAttributeMaxDynamicSharedMemorySize, kSkySmemBytes) != cudaSuccess ||
+        cudaFuncSetAttribute(k_focas, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FocasSmem)) != cudaSuccess) {
+        cudaStreamDestroy(c->stream); cudaStreamDestroy(c->copy_stream);
+        delete c;
+        return OSS_E_CUDA;
+    }
+    *out = c;
+    return OSS_OK;
+}
+
+void oss_destroy(oss_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    free_geometry(c);
+    for (void *p : c->user_allocs) cudaFree(p);
+    for (auto p : c->h_ds_chunks) cudaFreeHost(p);
+    for (auto p : c->h_al_chunks) cudaFreeHost(p);
+    prof_flush(c);
+    for (auto e : c->event_pool) cudaEventDestroy(e);
+    cudaStreamDestroy(c->stream);
+    cudaStreamDestroy(c->copy_stream);
+    delete c;
+}
+
+const char *oss_last_error(const oss_ctx *c) { return c ? c->err.c_str() : "no context"; }
+
+void *oss_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    return cudaMallocHost(&p, bytes) == cudaSuccess ? p : nullptr;
+}
+void oss_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+void *oss_device_alloc(oss_ctx *c, size_t bytes)
+{
+    if (!c) return nullptr;
+    cudaSetDevice(c->device);
+    void *p = nullptr;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) { c->err = "cudaMalloc failed"; return nullptr; }
+    c->user_allocs.push_back(p);
+    return p;
+}
+void oss_device_free(oss_ctx *c, void *p)
+{
+    if (!c || !p) return;
+    for (size_t i = 0; i < c->user_allocs.size(); i++)
+        if (c->user_allocs[i] == p) { c->user_allocs.erase(c->user_allocs.begin() + i); break; }
+    cudaFree(p);
+}
+int oss_memcpy_h2d(oss_ctx *c, void *d, const void *s, size_t n)
+{
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpyAsync(d, s, n, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return OSS_OK;
+}
+int oss_memcpy_d2h(oss_ctx *c, void *d, const void *s, size_t n)
+{
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return OSS_OK;
+}
+
+// ---- geometry --------------------------------------------------------------------------
+int oss_set_geometry(oss_ctx *c, int W, int H, int C, int sample, int slots)
+{
+    if (!c) return OSS_E_ARG;
+    if (W < 8 || H < 8 || (C != 1 && C != 3) || sample < OSS_U8 || sample > OSS_F32)
+        return fail(c, OSS_E_ARG, "unsupported geometry %dx%dx%d sample %d", W, H, C, sample);
+    if ((long long)W * H >= (1ll << 31)) return fail(c, OSS_E_ARG, "frame too large");
+    if (slots < 1) slots = 1;
+    if (slots > OSS_MAX_BATCH) slots = OSS_MAX_BATCH;
+    CK(cudaSetDevice(c->device));
+    free_geometry(c);
+    Geom g{};
+    g.W = W; g.H = H; g.C = C; g.sample = sample;
+    g.lw = W / 8; g.lh = H / 8;
+    g.nseg = (W + OSS_SEG - 1) / OSS_SEG;
+    g.roi_x = W / 20; g.roi_y = H / 20;
+    g.roi_w = (int)(W * 0.9); g.roi_h = (int)(H * 0.9);
+    g.P = (long long)W * H;
+    long long div = 16;
+    if (const char *e = getenv("OSS_B200_CAP_DIV")) div = atoll(e) > 0 ? atoll(e) : 16;
+    long long cap = g.P / div;
+    if (cap < 4096) cap = g.P < 4096 ? g.P : 4096;
+    g.cap = (int)cap;
+    c->g = g;
+    c->slots = slots;
+    const size_t ssz = sample == OSS_U8 ? 1 : (sample == OSS_U16 ? 2 : 4);
+    c->frame_bytes = (size_t)g.P * C * ssz;
+    const long long PC = g.P * C, nsegs = (long long)H * g.nseg, lo = (long long)g.lw * g.lh;
+    Workspace &w = c->ws;
+    w = Workspace{};
+    w.strideP = g.P; w.stridePC = PC; w.strideLo = lo; w.strideSeg = nsegs;
+    w.stat_blocks = ((W + SKY_T - 1) / SKY_T) * ((H + SKY_T - 1) / SKY_T);
+    w.stridePart = 2ll * w.stat_blocks;
+    long long scan_max = nsegs + 1 > cap ? nsegs + 1 : cap;
+    w.strideScan = (scan_max + SCAN_ITEMS - 1) / SCAN_ITEMS + 1;
+    DA(w.cal, slots * PC);
+    if (C == 3) { DA(w.gray, slots * g.P); } else w.gray = w.cal;
+    DA(w.stars, slots * g.P);
+    DA(w.lo, slots * lo); DA(w.med, slots * lo);
+    DA(w.segmax, slots * nsegs); DA(w.segmask, slots * nsegs); DA(w.segoff, slots * (nsegs + 1));
+    DA(w.partials, slots * w.stridePart);
+    DA(w.ds, slots);
+    DA(w.cand_idx, slots * cap); DA(w.cand_val, slots * cap); DA(w.nbr, slots * cap); DA(w.parent, slots * cap);
+    DA(w.owner, slots * cap); DA(w.comp_size, slots * cap); DA(w.comp_peak, slots * cap);
+    DA(w.flag, slots * cap); DA(w.flagscan, slots * cap);
+    DA(w.comp_root, slots * cap); DA(w.comp_off, slots * cap); DA(w.comp_nstar, slots * cap);
+    DA(w.comp_staroff, slots * cap);
+    DA(w.scratch, 12ll * slots * cap);
+    DA(w.star_tmp, slots * cap); DA(w.star_out, slots * cap);
+    DA(w.blocksum, slots * w.strideScan);
+    DA(w.align, slots);
+    DA(c->dx, g.lw); DA(c->dy, g.lh); DA(c->ux, W); DA(c->uy, H);
+    DA(c->sum, PC); DA(c->ref_cal, PC); DA(c->result, PC);
+    DA(c->d_valid, 4);
+    DA(c->d_ref, 1); DA(c->d_ref_tmp, 1);
+    DA(c->d_xy, (slots + 1) * 2 * OSS_NOBJS); DA(c->d_nxy, slots + 1);
+    DA(c->d_dbg_matches, 3 * OSS_MAX_MATCH); DA(c->d_dbg_table, OSS_NOBJS * OSS_NOBJS);
+    DA(c->d_M, 8); DA(c->d_flat_ratio, 4); DA(c->d_flat_partial, 1024);
+    for (int i = 0; i < 2; i++) {
+        DA(c->raw_stage[i], (size_t)slots * c->frame_bytes);
+        CK(cudaEventCreateWithFlags(&c->copy_done[i], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&c->raw_free[i], cudaEventDisableTiming));
+    }
+    LAUNCH("resize_taps", k_resize_taps, (g.lw + 255) / 256, 256, 0, c->dx, W, g.lw, 1);
+    LAUNCH("resize_taps", k_resize_taps, (g.lh + 255) / 256, 256, 0, c->dy, H, g.lh, 0);
+    LAUNCH("resize_taps", k_resize_taps, (W + 255) / 256, 256, 0, c->ux, g.lw, W, 1);
+    LAUNCH("resize_taps", k_resize_taps, (H + 255) / 256, 256, 0, c->uy, g.lh, H, 0);
+    CK(cudaMemsetAsync(c->sum, 0, PC * sizeof(float), c->stream));
+    CK(cudaMemsetAsync(c->d_valid, 0, 16, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->has_geom = true;
+    c->nlights = 0;
+    c->extra_valid = 0;
+    c->batch_counter = 0;
+    return OSS_OK;
+}
+
+}  // extern "C"
+
+// ---- helpers ---------------------------------------------------------------------------
+static int run_scan(oss_ctx *c, const int *in, long long strideIn, int *out, long long strideOut, const int *n_dev,
+                    int n_dev_stride, int n_host_max, int nframes, int *total_out, int total_stride, int write_total_at_n = 0)
+{
+    Workspace &w = c->ws;
+    int nb = (n_host_max + SCAN_ITEMS - 1) / SCAN_ITEMS;
+    if (nb < 1) nb = 1;
+    int n_host = n_dev ? 0 : n_host_max;
+    LAUNCH("scan", k_scan_phase1, dim3(nb, nframes), 1024, 0, in, strideIn, out, strideOut, n_dev, n_dev_stride, n_host,
+           w.blocksum, w.strideScan);
+    LAUNCH("scan", k_scan_phase2, nframes, 1024, 0, w.blocksum, w.strideScan, n_dev, n_dev_stride, n_host, out, strideOut,
+           write_total_at_n, total_out, total_stride);
+    if (nb > 1)
+        LAUNCH("scan", k_scan_phase3, dim3(nb, nframes), 1024, 0, out, strideOut, n_dev, n_dev_stride, n_host, w.blocksum,
+               w.strideScan);
+    return OSS_OK;
+}
+
+template <typename T, int C>
+static int launch_calibrate(oss_ctx *c, const FramePtrs &fp, int n, const float *b, const float *d, const float *f)
+{
+    Workspace &w = c->ws;
+    const Geom &g = c->g;
+    dim3 grid((unsigned)((g.P + 256ll * Sample<T>::PX - 1) / (256ll * Sample<T>::PX)), n);
+#define CAL(HB, HD, HF) { auto kf = k_calibrate_gray<T, C, HB, HD, HF>; LAUNCH("calibrate_gray", kf, grid, 256, 0, fp, b, d, f, w.cal, w.stridePC, w.gray, w.strideP, g.P); }
+    int key = (b ? 4 : 0) | (d ? 2 : 0) | (f ? 1 : 0);
+    switch (key) {
+    case 0: CAL(false, false, false); break;
+    case 1: CAL(false, false, true); break;
+    case 2: CAL(false, true, false); break;
+    case 3: CAL(false, true, true); break;
+    case 4: CAL(true, false, false); break;
+    case 5: CAL(true, false, true); break;
+    case 6: CAL(true, true, false); break;
+    case 7: CAL(true, true, true); break;
+    }
+#undef CAL
+    return OSS_OK;
+}
+
+static int dispatch_calibrate(oss_ctx *c, const FramePtrs &fp, int n, bool use_masters)
+{
+    const float *b = use_masters ? c->master[OSS_MASTER_BIAS] : nullptr;
+    const float *d = use_masters ? c->master[OSS_MASTER_DARK] : nullptr;
+    const float *f = use_masters ? c->master[OSS_MASTER_FLAT] : nullptr;
+    const Geom &g = c->g;
+    if (g.sample == OSS_U16) return g.C == 3 ? launch_calibrate<uint16_t, 3>(c, fp, n, b, d, f) : launch_calibrate<uint16_t, 1>(c, fp, n, b, d, f);
+    if (g.sample == OSS_U8) return g.C == 3 ? launch_calibrate<uint8_t, 3>(c, fp, n, b, d, f) : launch_calibrate<uint8_t, 1>(c, fp, n, b, d, f);
+    return g.C == 3 ? launch_calibrate<float, 3>(c, fp, n, b, d, f) : launch_calibrate<float, 1>(c, fp, n, b, d, f);
+}
+
+// stage n host frames into raw_stage[set] (async on the copy stream) or pass device pointers through
+static int stage_frames(oss_ctx *c, const void *const *frames, int n, int mem, FramePtrs *fp, int *set_out)
+{
+    for (int i = 0; i < n; i++) {
+        if (!frames[i]) return fail(c, OSS_E_ARG, "null frame pointer");
+        if (((uintptr_t)frames[i] & 15) && mem == OSS_MEM_DEVICE) return fail(c, OSS_E_ARG, "device frames must be 16-byte aligned");
+    }
+    *set_out = -1;
+    if (mem == OSS_MEM_DEVICE) {
+        for (int i = 0; i < n; i++) fp->p[i] = frames[i];
+        return OSS_OK;
+    }
+    int set = (int)(c->batch_counter++ & 1);
+    CK(cudaStreamWaitEvent(c->copy_stream, c->raw_free[set], 0));
+    for (int i = 0; i < n; i++) {
+        unsigned char *dst = c->raw_stage[set] + (size_t)i * c->frame_bytes;
+        CK(cudaMemcpyAsync(dst, frames[i], c->frame_bytes, cudaMemcpyHostToDevice, c->copy_stream));
+        fp->p[i] = dst;
+    }
+    CK(cudaEventRecord(c->copy_done[set], c->copy_stream));
+    CK(cudaStreamWaitEvent(c->stream, c->copy_done[set], 0));
+    *set_out = set;
+    return OSS_OK;
+}
+
+// calibrate (optional) + full star detection for n frames sitting in fp; results in ws slots 0..n-1
+static int run_detect(oss_ctx *c, const FramePtrs &fp, int n, bool use_masters, int threshold, int stage_set)
+{
+    Workspace &w = c->ws;
+    const Geom &g = c->g;
+    int r = dispatch_calibrate(c, fp, n, use_masters);
+    if (r) return r;
+    if (stage_set >= 0) CK(cudaEventRecord(c->raw_free[stage_set], c->stream));
+    LAUNCH("resize_down", k_resize_down, dim3((g.lw + 31) / 32, (g.lh + 7) / 8, n), 256, 0, w.gray, g.C == 3 ? w.strideP : w.stridePC, g.W,
+           c->dx, c->dy, w.lo, w.strideLo, g.lw, g.lh);
+    LAUNCH("median5", k_median5, dim3((g.lw + 31) / 32, (g.lh + 7) / 8, n), 256, 0, w.lo, w.med, w.strideLo, g.lw, g.lh);
+    const long long strideGray = g.C == 3 ? w.strideP : w.stridePC;
+    LAUNCH("sky_sub_stats", k_sky_sub_stats, dim3((g.W + SKY_T - 1) / SKY_T, (g.H + SKY_T - 1) / SKY_T, n), 256, kSkySmemBytes,
+           w.gray, strideGray, w.med, w.strideLo, g.lw, c->ux, c->uy, w.stars, w.strideP, w.segmax, w.strideSeg, g.nseg,
+           w.partials, w.stridePart, g);
+    LAUNCH("finalize_stats", k_finalize_stats, n, 256, 0, w.partials, w.stridePart, w.stat_blocks, w.ds, threshold, g);
+    const long long nsegs = w.strideSeg;
+    const int segblocks = (int)((nsegs + 255) / 256);
+    LAUNCH("segment_masks", k_segment_masks, dim3(segblocks, n), 256, 0, w.stars, w.strideP, w.segmax, w.strideSeg, w.segmask,
+           w.segoff, w.ds, g);
+    r = run_scan(c, w.segoff, nsegs + 1, w.segoff, nsegs + 1, nullptr, 0, (int)nsegs, n, nullptr, 0, 1);
+    if (r) return r;
+    LAUNCH("compact_candidates", k_compact_candidates, dim3(segblocks, n), 256, 0, w.stars, w.strideP, w.segmask, w.strideSeg,
+           w.segoff, w.cand_idx, w.cand_val, w.owner, w.ds, g);
+    const int DS = (int)(sizeof(DetectState) / sizeof(int));
+    const int gs = 296;
+    LAUNCH("links", k_links, dim3(gs, n), 256, 0, w.cand_idx, w.segmask, w.strideSeg, w.segoff, w.nbr, w.parent, w.comp_size,
+           w.comp_peak, w.ds, g);
+    LAUNCH("ccl_union", k_ccl_union, dim3(gs, n), 256, 0, w.nbr, w.parent, w.ds, g);
+    LAUNCH("ccl_flatten", k_ccl_flatten, dim3(gs, n), 256, 0, w.parent, w.cand_val, w.comp_size, w.comp_peak, w.ds, g);
+    // flag = kept roots, comp_off (pre-scan) = their sizes
+    LAUNCH("root_flags", k_root_flags, dim3(gs, n), 256, 0, w.parent, w.comp_size, w.comp_peak, w.flag, w.comp_staroff, w.ds, g);
+    int *ncand = &w.ds[0].ncand, *ncomp = &w.ds[0].ncomp, *nstars = &w.ds[0].nstars;
+    r = run_scan(c, w.flag, g.cap, w.flagscan, g.cap, ncand, DS, g.cap, n, ncomp, DS);
+    if (r) return r;
+    r = run_scan(c, w.comp_staroff, g.cap, w.comp_staroff, g.cap, ncand, DS, g.cap, n, nullptr, 0);
+    if (r) return r;
+    LAUNCH("gather_roots", k_gather_roots, dim3(gs, n), 256, 0, w.flag, w.flagscan, w.comp_staroff, w.comp_root, w.comp_off, w.ds, g);
+    LAUNCH("components", k_components, dim3(592, n), 64, 0, w.cand_idx, w.cand_val, w.nbr, w.owner, w.comp_size, w.comp_root,
+           w.comp_off, w.comp_nstar, w.scratch, w.star_tmp, w.ds, g);
+    r = run_scan(c, w.comp_nstar, g.cap, w.comp_staroff, g.cap, ncomp, DS, g.cap, n, nstars, DS);
+    if (r) return r;
+    LAUNCH("gather_stars", k_gather_stars, dim3(gs, n), 256, 0, w.star_tmp, w.comp_off, w.comp_nstar, w.comp_staroff, w.star_out,
+           w.ds, g);
+    return OSS_OK;
+}
+
+static void fill_info(const DetectState &d, oss_detect_info *info)
+{
+    info->mean = d.mean; info->sigma = d.sigma; info->threshold = d.threshold; info->minpeak = d.minpeak;
+    info->ncandidates = d.ncand; info->ncomponents = d.ncomp; info->nstars = d.nstars; info->overflow = d.overflow;
+}
+
+static int need_geom(oss_ctx *c)
+{
+    if (!c) return OSS_E_ARG;
+    if (!c->has_geom) return fail(c, OSS_E_ARG, "oss_set_geometry has not been called");
+    cudaError_t e = cudaSetDevice(c->device);
+    if (e != cudaSuccess) return fail(c, OSS_E_CUDA, "cudaSetDevice failed: %s", cudaGetErrorString(e));
+    return OSS_OK;
+}
+#define NEED_GEOM() do { int r_ = need_geom(c); if (r_) return r_; } while (0)
+
+extern "C" {
+
+// ---- masters ---------------------------------------------------------------------------
+int oss_build_master(oss_ctx *c, int kind, const void *const *frames, int n, int mem)
+{
+    NEED_GEOM();
+    if (kind < 0 || kind > 3 || n < 1 || !frames) return fail(c, OSS_E_ARG, "bad master arguments");
+    const Geom &g = c->g;
+    const long long count = g.P * g.C;
+    if (!c->master[kind]) DA(c->master[kind], count);
+    float *acc = c->master[kind];
+    const float *sub1 = nullptr, *sub2 = nullptr;
+    if (kind != OSS_MASTER_BIAS) sub1 = c->master[OSS_MASTER_BIAS];     // util.cpp:593,627,662
+    if (kind == OSS_MASTER_FLAT) sub2 = c->master[OSS_MASTER_DARKFLAT]; // util.cpp:663
+    const float r = (float)(1.0 / (double)n);
+    const int per = c->slots;
+    for (int b0 = 0; b0 < n; b0 += per) {
+        int nb = n - b0 < per ? n - b0 : per;
+        FramePtrs fp{};
+        int set;
+        int rc = stage_frames(c, frames + b0, nb, mem, &fp, &set);
+        if (rc) return rc;
+        int first = b0 == 0, last = b0 + nb == n;
+#define ACC(T) { auto kf = k_master_accumulate<T>; LAUNCH("master_accumulate", kf, (unsigned)((count + 256ll * Sample<T>::PX - 1) / (256ll * Sample<T>::PX)), 256, 0, fp, nb, sub1, sub2, acc, first, last, r, count); }
+        if (g.sample == OSS_U16) ACC(uint16_t)
+        else if (g.sample == OSS_U8) ACC(uint8_t)
+        else ACC(float)
+#undef ACC
+        if (set >= 0) CK(cudaEventRecord(c->raw_free[set], c->stream));
+    }
+    if (kind == OSS_MASTER_FLAT) { // util.cpp:686-688
+        const int nblk = 592;
+        LAUNCH("flat_mean", k_channel0_partial, nblk, 256, 0, acc, g.P, g.C, c->d_flat_partial);
+        LAUNCH("flat_mean", k_flat_ratio, 1, 32, 0, c->d_flat_partial, nblk, g.P, c->d_flat_ratio);
+        LAUNCH("flat_scale", k_scale_by, (unsigned)((count + 1023) / 1024), 256, 0, acc, count, c->d_flat_ratio, 0.f);
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    return OSS_OK;
+}
+
+int oss_set_master(oss_ctx *c, int kind, const float *data, int mem)
+{
+    NEED_GEOM();
+    if (kind < 0 || kind > 3 || !data) return fail(c, OSS_E_ARG, "bad master arguments");
+    const long long count = c->g.P * c->g.C;
+    if (!c->master[kind]) DA(c->master[kind], count);
+    CK(cudaMemcpyAsync(c->master[kind], data, count * sizeof(float),
+                       mem == OSS_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return OSS_OK;
+}
+
+int oss_get_master(oss_ctx *c, int kind, float *out)
+{
+    NEED_GEOM();
+    if (kind < 0 || kind > 3 || !out) return fail(c, OSS_E_ARG, "bad master arguments");
+    if (!c->master[kind]) return fail(c, OSS_E_ARG, "master %d is absent", kind);
+    return oss_memcpy_d2h(c, out, c->master[kind], (size_t)c->g.P * c->g.C * sizeof(float));
+}
+
+int oss_clear_masters(oss_ctx *c)
+{
+    NEED_GEOM();
+    CK(cudaStreamSynchronize(c->stream));
+    for (int k = 0; k < 4; k++)
+        if (c->master[k]) {
+            for (size_t i = 0; i < c->allocs.size(); i++)
+                if (c->allocs[i] == c->master[k]) { c->allocs.erase(c->allocs.begin() + i); break; }
+            cudaFree(c->master[k]);
+            c->master[k] = nullptr;
+        }
+    return OSS_OK;
+}
+
+// ---- stacking --------------------------------------------------------------------------
+int oss_reset_stack(oss_ctx *c)
+{
+    NEED_GEOM();
+    CK(cudaMemsetAsync(c->sum, 0, (size_t)c->g.P * c->g.C * sizeof(float), c->stream));
+    CK(cudaMemsetAsync(c->d_valid, 0, 16, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->has_ref = false;
+    c->ref_in_sum = true;
+    c->nlights = 0;
+    c->extra_valid = 0;
+    c->ref_stars.clear();
+    return OSS_OK;
+}
+
+int oss_set_reference(oss_ctx *c, const void *frame, int mem, int threshold)
+{
+    NEED_GEOM();
+    if (!frame) return fail(c, OSS_E_ARG, "null reference frame");
+    int rc = oss_reset_stack(c);
+    if (rc) return rc;
+    const Geom &g = c->g;
+    Workspace &w = c->ws;
+    FramePtrs fp{};
+    int set;
+    rc = stage_frames(c, &frame, 1, mem, &fp, &set);
+    if (rc) return rc;
+    rc = run_detect(c, fp, 1, true, threshold, set);
+    if (rc) return rc;
+    const long long PC = g.P * g.C;
+    LAUNCH("copy_reference", k_copy_f32, (unsigned)((PC + 1023) / 1024), 256, 0, w.cal, c->ref_cal, PC);
+    int *xy_ref = c->d_xy + c->slots * 2 * OSS_NOBJS, *nxy_ref = c->d_nxy + c->slots;
+    LAUNCH("pack_xy", k_pack_xy, 1, OSS_NOBJS, 0, w.star_out, w.ds, g.cap, xy_ref, nxy_ref);
+    LAUNCH("build_ref_triangles", k_build_ref_triangles, 1, 256, 0, xy_ref, nxy_ref, c->d_ref);
+    DetectState d;
+    CK(cudaMemcpyAsync(&d, w.ds, sizeof d, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    fill_info(d, &c->ref_info);
+    if (d.overflow) return fail(c, OSS_E_CAPACITY, "reference frame: %d candidate pixels exceed the workspace (%d)", d.ncand, g.cap);
+    c->ref_stars.resize(d.nstars);
+    if (d.nstars) CK(cudaMemcpy(c->ref_stars.data(), w.star_out, (size_t)d.nstars * sizeof(oss_star), cudaMemcpyDeviceToHost));
+    c->threshold = threshold;
+    c->has_ref = true;
+    c->ref_in_sum = true;
+    return OSS_OK;
+}
+
+static int ensure_report_room(oss_ctx *c, int upto)
+{
+    while ((int)c->h_ds_chunks.size() * kChunk < upto) {
+        DetectState *a = nullptr;
+        AlignOut *b = nullptr;
+        CK(cudaMallocHost((void **)&a, sizeof(DetectState) * kChunk));
+        CK(cudaMallocHost((void **)&b, sizeof(AlignOut) * kChunk));
+        c->h_ds_chunks.push_back(a);
+        c->h_al_chunks.push_back(b);
+    }
+    return OSS_OK;
+}
+
+int oss_add_lights(oss_ctx *c, const void *const *frames, int n, int mem)
+{
+    NEED_GEOM();
+    if (!c->has_ref) return fail(c, OSS_E_ARG, "oss_set_reference (or oss_comm_broadcast_reference) must come first");
+    if (n < 0 || (n && !frames)) return fail(c, OSS_E_ARG, "bad light list");
+    const Geom &g = c->g;
+    Workspace &w = c->ws;
+    int rc = ensure_report_room(c, c->nlights + n);
+    if (rc) return rc;
+    for (int b0 = 0; b0 < n; b0 += c->slots) {
+        int nb = n - b0 < c->slots ? n - b0 : c->slots;
+        FramePtrs fp{};
+        int set;
+        rc = stage_frames(c, frames + b0, nb, mem, &fp, &set);
+        if (rc) return rc;
+        rc = run_detect(c, fp, nb, true, c->threshold, set);
+        if (rc) return rc;
+        LAUNCH("pack_xy", k_pack_xy, nb, OSS_NOBJS, 0, w.star_out, w.ds, g.cap, c->d_xy, c->d_nxy);
+        LAUNCH("focas_match_fit", k_focas, nb, 256, sizeof(FocasSmem), c->d_ref, c->d_xy, c->d_nxy, w.align, c->d_valid,
+               (int *)nullptr, (int *)nullptr);
+        if (g.C == 3) {
+            LAUNCH("warp_accumulate", k_warp_accumulate<3>, dim3((g.W + 31) / 32, (g.H + 7) / 8), dim3(32, 8), 0, w.cal, w.stridePC,
+                   w.align, nb, c->sum, g.W, g.H);
+        } else {
+            LAUNCH("warp_accumulate", k_warp_accumulate<1>, dim3((g.W + 31) / 32, (g.H + 7) / 8), dim3(32, 8), 0, w.cal, w.stridePC,
+                   w.align, nb, c->sum, g.W, g.H);
+        }
+        // reports back to pinned host memory, asynchronously; a batch never straddles a chunk
+        // boundary more than once
+        int done = 0;
+        while (done < nb) {
+            int gi = c->nlights + done, ch = gi / kChunk, off = gi % kChunk;
+            int m = nb - done < kChunk - off ? nb - done : kChunk - off;
+            CK(cudaMemcpyAsync(c->h_ds_chunks[ch] + off, w.ds + done, sizeof(DetectState) * m, cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaMemcpyAsync(c->h_al_chunks[ch] + off, w.align + done, sizeof(AlignOut) * m, cudaMemcpyDeviceToHost, c->stream));
+            done += m;
+        }
+        c->nlights += nb;
+    }
+    return OSS_OK;
+}
+
+int oss_sync(oss_ctx *c)
+{
+    NEED_GEOM();
+    CK(cudaStreamSynchronize(c->copy_stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return OSS_OK;
+}
+
+int oss_num_reports(oss_ctx *c) { return c ? c->nlights : 0; }
+
+int oss_get_frame_report(oss_ctx *c, int i, oss_frame_report *out)
+{
+    NEED_GEOM();
+    if (i < 0 || i >= c->nlights || !out) return fail(c, OSS_E_ARG, "report index out of range");
+    CK(cudaStreamSynchronize(c->stream));
+    const DetectState &d = c->h_ds_chunks[i / kChunk][i % kChunk];
+    const AlignOut &a = c->h_al_chunks[i / kChunk][i % kChunk];
+    out->nstars = d.nstars; out->k = a.k; out->err = a.err;
+    memcpy(out->M, a.M, sizeof a.M);
+    out->threshold = d.threshold; out->overflow = d.overflow;
+    return OSS_OK;
+}
+
+int oss_get_reference_stars(oss_ctx *c, oss_star *out, int cap, int *n, oss_detect_info *info)
+{
+    NEED_GEOM();
+    if (!c->has_ref) return fail(c, OSS_E_ARG, "no reference");
+    int m = (int)c->ref_stars.size();
+    if (n) *n = m;
+    if (out) memcpy(out, c->ref_stars.data(), sizeof(oss_star) * (size_t)(m < cap ? m : cap));
+    if (info) *info = c->ref_info;
+    return OSS_OK;
+}
+
+static int total_valid(oss_ctx *c, int *out)
+{
+    int v = 0;
+    CK(cudaMemcpyAsync(&v, c->d_valid, sizeof v, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    *out = v + (c->ref_in_sum ? 1 : 0); // imagestacker.cpp:304: the reference counts as one
+    return OSS_OK;
+}
+
+int oss_get_sum(oss_ctx *c, float *out, int *tv)
+{
+    NEED_GEOM();
+    if (tv) { int rc = total_valid(c, tv); if (rc) return rc; }
+    if (out) return oss_memcpy_d2h(c, out, c->sum, (size_t)c->g.P * c->g.C * sizeof(float));
+    return OSS_OK;
+}
+
+int oss_finish(oss_ctx *c, float *out, int *tv)
+{
+    NEED_GEOM();
+    if (!c->has_ref) return fail(c, OSS_E_ARG, "no reference");
+    CK(cudaStreamSynchronize(c->copy_stream));
+    int v;
+    int rc = total_valid(c, &v);
+    if (rc) return rc;
+    if (tv) *tv = v;
+    if (v < 2) return fail(c, OSS_E_NO_ALIGNED, "%s", oss_status_string(OSS_E_NO_ALIGNED));
+    const long long PC = c->g.P * c->g.C;
+    const float r = (float)(1.0 / (double)v);
+    LAUNCH("finalize", k_finalize, (unsigned)((PC + 1023) / 1024), 256, 0, c->sum, c->ref_in_sum ? c->ref_cal : (const float *)nullptr,
+           c->result, PC, r);
+    if (out) return oss_memcpy_d2h(c, out, c->result, (size_t)PC * sizeof(float));
+    CK(cudaStreamSynchronize(c->stream));
+    return OSS_OK;
+}
+
+const float *oss_result_device_ptr(oss_ctx *c) { return c ? c->result : nullptr; }
+
+// ---- detect only -----------------------------------------------------------------------
+int oss_detect_stars(oss_ctx *c, const void *frame, int mem, int threshold, oss_star *out, int cap, int *n, oss_detect_info *info)
+{
+    NEED_GEOM();
+    if (!frame) return fail(c, OSS_E_ARG, "null frame");
+    FramePtrs fp{};
+    int set;
+    int rc = stage_frames(c, &frame, 1, mem, &fp, &set);
+    if (rc) return rc;
+    rc = run_detect(c, fp, 1, false, threshold, set); // imagestacker.cpp:395: readImage only, no calibration
+    if (rc) return rc;
+    DetectState d;
+    CK(cudaMemcpyAsync(&d, c->ws.ds, sizeof d, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (info) fill_info(d, info);
+    if (n) *n = d.nstars;
+    if (d.overflow) return fail(c, OSS_E_CAPACITY, "%d candidate pixels exceed the workspace (%d)", d.ncand, c->g.cap);
+    int m = d.nstars < cap ? d.nstars : cap;
+    if (out && m > 0) CK(cudaMemcpy(out, c->ws.star_out, sizeof(oss_star) * (size_t)m, cudaMemcpyDeviceToHost));
+    return OSS_OK;
+}
+
+int oss_detect_stars_batch(oss_ctx *c, const void *const *frames, int n, int mem, int threshold, int32_t *counts)
+{
+    NEED_GEOM();
+    if (n < 0 || (n && (!frames || !counts))) return fail(c, OSS_E_ARG, "bad arguments");
+    std::vector<DetectState> d(c->slots);
+    for (int b0 = 0; b0 < n; b0 += c->slots) {
+        int nb = n - b0 < c->slots ? n - b0 : c->slots;
+        FramePtrs fp{};
+        int set;
+        int rc = stage_frames(c, frames + b0, nb, mem, &fp, &set);
+        if (rc) return rc;
+        rc = run_detect(c, fp, nb, false, threshold, set);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(d.data(), c->ws.ds, sizeof(DetectState) * nb, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        for (int i = 0; i < nb; i++) counts[b0 + i] = d[i].overflow ? -1 : d[i].nstars;
+    }
+    return OSS_OK;
+}
+
+// ---- alignment only --------------------------------------------------------------------
+int oss_align_lists(oss_ctx *c, const int32_t *xy1, int n1, const int32_t *xy2, int n2, int32_t *k, int32_t *err, float *M,
+                    int32_t *matches_out, int32_t *votes_out)
+{
+    NEED_GEOM();
+    if (n1 < 0 || n2 < 0 || (n1 && !xy1) || (n2 && !xy2)) return fail(c, OSS_E_ARG, "bad star lists");
+    int m1 = n1 < OSS_NOBJS ? n1 : OSS_NOBJS, m2 = n2 < OSS_NOBJS ? n2 : OSS_NOBJS;
+    int *xy_ref = c->d_xy + c->slots * 2 * OSS_NOBJS, *nxy_ref = c->d_nxy + c->slots;
+    // the reference slot of d_xy is shared with the stack's reference list: restore it afterwards
+    std::vector<int> keep(2 * OSS_NOBJS + 1);
+    CK(cudaMemcpyAsync(keep.data(), xy_ref, sizeof(int) * 2 * OSS_NOBJS, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(keep.data() + 2 * OSS_NOBJS, nxy_ref, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (m1) CK(cudaMemcpyAsync(xy_ref, xy1, sizeof(int) * 2 * m1, cudaMemcpyHostToDevice, c->stream));
+    if (m2) CK(cudaMemcpyAsync(c->d_xy, xy2, sizeof(int) * 2 * m2, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(nxy_ref, &m1, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->d_nxy, &m2, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    LAUNCH("build_ref_triangles", k_build_ref_triangles, 1, 256, 0, xy_ref, nxy_ref, c->d_ref_tmp);
+    LAUNCH("focas_match_fit", k_focas, 1, 256, sizeof(FocasSmem), c->d_ref_tmp, c->d_xy, c->d_nxy, c->ws.align, (int *)nullptr,
+           c->d_dbg_matches, c->d_dbg_table);
+    AlignOut o;
+    CK(cudaMemcpyAsync(&o, c->ws.align, sizeof o, cudaMemcpyDeviceToHost, c->stream));
+    if (matches_out) CK(cudaMemcpyAsync(matches_out, c->d_dbg_matches, sizeof(int) * 3 * OSS_MAX_MATCH, cudaMemcpyDeviceToHost, c->stream));
+    if (votes_out) CK(cudaMemcpyAsync(votes_out, c->d_dbg_table, sizeof(int) * OSS_NOBJS * OSS_NOBJS, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(xy_ref, keep.data(), sizeof(int) * 2 * OSS_NOBJS, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(nxy_ref, keep.data() + 2 * OSS_NOBJS, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (k) *k = o.k;
+    if (err) *err = o.err;
+    if (M) memcpy(M, o.M, sizeof o.M);
+    return OSS_OK;
+}
+
+// ---- warp only -------------------------------------------------------------------------
+int oss_warp_affine(oss_ctx *c, const float *src, float *dst, const float *M)
+{
+    NEED_GEOM();
+    if (!src || !dst || !M) return fail(c, OSS_E_ARG, "null argument");
+    const Geom &g = c->g;
+    const size_t bytes = (size_t)g.P * g.C * sizeof(float);
+    CK(cudaMemcpyAsync(c->ws.cal, src, bytes, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->d_M, M, 6 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    if (g.C == 3) {
+        LAUNCH("warp_only", k_warp_only<3>, dim3((g.W + 31) / 32, (g.H + 7) / 8), dim3(32, 8), 0, c->ws.cal, c->result, c->d_M, g.W, g.H);
+    } else {
+        LAUNCH("warp_only", k_warp_only<1>, dim3((g.W + 31) / 32, (g.H + 7) / 8), dim3(32, 8), 0, c->ws.cal, c->result, c->d_M, g.W, g.H);
+    }
+    CK(cudaMemcpyAsync(dst, c->result, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return OSS_OK;
+}
+
+// ---- multi-GPU -------------------------------------------------------------------------
+int oss_comm_unique_id(void *id128)
+{
+    std::string why;
+    if (!id128 || !nccl_load(&why)) return OSS_E_CUDA;
+    ncclUniqueId id;
+    if (g_nccl.GetUniqueId(&id) != ncclSuccess) return OSS_E_CUDA;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    memcpy(id128, &id, 128);
+    return OSS_OK;
+}
+
+int oss_comm_init(oss_ctx *c, const void *id128, int rank, int nranks)
+{
+    if (!c || !id128 || rank < 0 || rank >= nranks) return fail(c, OSS_E_ARG, "bad communicator arguments");
+    std::string why;
+    if (!nccl_load(&why)) return fail(c, OSS_E_CUDA, "%s", why.c_str());
+    CK(cudaSetDevice(c->device));
+    ncclUniqueId id;
+    memcpy(&id, id128, 128);
+    NK(g_nccl.CommInitRank(&c->comm, nranks, id, rank));
+    c->rank = rank;
+    c->nranks = nranks;
+    return OSS_OK;
+}
+
+int oss_comm_broadcast_masters(oss_ctx *c, int root)
+{
+    NEED_GEOM();
+    if (!c->comm) return fail(c, OSS_E_ARG, "oss_comm_init has not been called");
+    const long long count = c->g.P * c->g.C;
+    int present[4];
+    for (int k = 0; k < 4; k++) present[k] = c->master[k] != nullptr;
+    int *d_present = nullptr;
+    { int r_ = dalloc(c, &d_present, 4); if (r_) return r_; }
+    CK(cudaMemcpyAsync(d_present, present, sizeof present, cudaMemcpyHostToDevice, c->stream));
+    NK(g_nccl.Broadcast(d_present, d_present, 4, ncclInt32, root, c->comm, c->stream));
+    CK(cudaMemcpyAsync(present, d_present, sizeof present, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    for (int k = 0; k < 4; k++) {
+        if (!present[k]) continue;
+        if (!c->master[k]) DA(c->master[k], count);
+        NK(g_nccl.Broadcast(c->master[k], c->master[k], (size_t)count, ncclFloat32, root, c->comm, c->stream));
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    return OSS_OK;
+}
+
+int oss_comm_broadcast_reference(oss_ctx *c, int root)
+{
+    NEED_GEOM();
+    if (!c->comm) return fail(c, OSS_E_ARG, "oss_comm_init has not been called");
+    if (c->rank == root && !c->has_ref) return fail(c, OSS_E_ARG, "root has no reference");
+    if (c->rank != root) { int rc = oss_reset_stack(c); if (rc) return rc; }
+    int *xy_ref = c->d_xy + c->slots * 2 * OSS_NOBJS, *nxy_ref = c->d_nxy + c->slots;
+    NK(g_nccl.Broadcast(c->d_ref, c->d_ref, sizeof(RefTriangles), ncclUint8, root, c->comm, c->stream));
+    NK(g_nccl.Broadcast(xy_ref, xy_ref, 2 * OSS_NOBJS, ncclInt32, root, c->comm, c->stream));
+    NK(g_nccl.Broadcast(nxy_ref, nxy_ref, 1, ncclInt32, root, c->comm, c->stream));
+    int *d_th = c->d_valid + 2;
+    if (c->rank == root) CK(cudaMemcpyAsync(d_th, &c->threshold, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    NK(g_nccl.Broadcast(d_th, d_th, 1, ncclInt32, root, c->comm, c->stream));
+    CK(cudaMemcpyAsync(&c->threshold, d_th, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->has_ref = true;
+    c->ref_in_sum = c->rank == root; // imagestacker.cpp:287,304: the reference is counted once
+    return OSS_OK;
+}
+
+int oss_comm_reduce(oss_ctx *c, int root)
+{
+    NEED_GEOM();
+    if (!c->comm) return fail(c, OSS_E_ARG, "oss_comm_init has not been called");
+    const long long count = c->g.P * c->g.C;
+    CK(cudaStreamSynchronize(c->copy_stream));
+    NK(g_nccl.Reduce(c->sum, c->sum, (size_t)count, ncclFloat32, ncclSum, root, c->comm, c->stream));
+    NK(g_nccl.Reduce(c->d_valid, c->d_valid, 1, ncclInt32, ncclSum, root, c->comm, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return OSS_OK;
+}
+
+// ---- instrumentation -------------------------------------------------------------------
+int oss_profile_enable(oss_ctx *c, int on)
+{
+    if (!c) return OSS_E_ARG;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    prof_flush(c);
+    c->profiling = on != 0;
+    return OSS_OK;
+}
+int oss_profile_reset(oss_ctx *c)
+{
+    if (!c) return OSS_E_ARG;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    prof_flush(c);
+    c->prof.clear();
+    return OSS_OK;
+}
+int oss_profile_count(oss_ctx *c)
+{
+    if (!c) return 0;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    prof_flush(c);
+    return (int)c->prof.size();
+}
+int oss_profile_get(oss_ctx *c, int i, const char **name, double *ms, int *launches)
+{
+    if (!c || i < 0 || i >= (int)c->prof.size()) return OSS_E_ARG;
+    if (name) *name = c->prof[i].name.c_str();
+    if (ms) *ms = c->prof[i].ms;
+    if (launches) *launches = c->prof[i].launches;
+    return OSS_OK;
+}
+long long oss_launch_count(oss_ctx *c) { return c ? c->launches : 0; }
+
+int oss_debug_copy(oss_ctx *c, int what, int slot, float *out)
+{
+    NEED_GEOM();
+    if (slot < 0 || slot >= c->slots || !out) return fail(c, OSS_E_ARG, "bad slot");
+    const Geom &g = c->g;
+    const Workspace &w = c->ws;
+    const float *src = nullptr;
+    size_t count = 0;
+    switch (what) {
+    case 0: src = w.cal + slot * w.stridePC; count = (size_t)g.P * g.C; break;
+    case 1: src = g.C == 3 ? w.gray + slot * w.strideP : w.cal + slot * w.stridePC; count = (size_t)g.P; break;
+    case 2: src = w.stars + slot * w.strideP; count = (size_t)g.P; break;
+    case 3: src = w.lo + slot * w.strideLo; count = (size_t)g.lw * g.lh; break;
+    case 4: src = w.med + slot * w.strideLo; count = (size_t)g.lw * g.lh; break;
+    default: return fail(c, OSS_E_ARG, "unknown plane %d", what);
+    }
+    return oss_memcpy_d2h(c, out, src, count * sizeof(float));
+}
+
+}  // extern "C"

@@ -1,0 +1,287 @@
+"""GPU parity: every stage of the CUDA path, called through the C ABI, against the CPU
+oracle on the same seeded inputs.  Integer / index results and all fp32 images are compared
+BIT-EXACT; the only tolerance is on sigma (fp64 reduction order): rel <= 1e-12."""
+import numpy as np
+import pytest
+
+import oracle
+import openskystacker_b200 as ob
+from openskystacker_b200 import binding as B
+from openskystacker_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    e = ob.Engine(0)
+    yield e
+    e.close()
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def same_stars(a, b):
+    assert len(a) == len(b), (len(a), len(b))
+    for f in ("x", "y", "area"):
+        assert np.array_equal(a[f], b[f]), f
+    assert np.array_equal(bits(a["peak"]), bits(b["peak"]))
+    assert np.array_equal(bits(a["value"]), bits(b["value"]))
+
+
+def blob_image(w, h, n, seed, noise=0.002):
+    r = np.random.default_rng(seed)
+    img = r.normal(0, noise, (h, w)) + 0.05
+    yy, xx = np.mgrid[0:h, 0:w]
+    for _ in range(n):
+        x, y = r.uniform(0, w), r.uniform(0, h)
+        a = np.exp(r.uniform(np.log(0.01), np.log(0.9)))
+        s = r.uniform(1.2, 3.5)
+        for k in range(int(r.integers(1, 4))):
+            img += a * r.uniform(0.3, 1) * np.exp(-0.5 * ((xx + 0.5 - x - k * r.uniform(-6, 6)) ** 2 +
+                                                         (yy + 0.5 - y - k * r.uniform(-6, 6)) ** 2) / s ** 2)
+    return img.astype(np.float32)
+
+
+# ------------------------------------------------------------------------------- K0 / K1
+@pytest.mark.parametrize("w,h,c,dt", [(203, 165, 3, np.uint16), (640, 480, 1, np.uint16), (333, 200, 3, np.uint8),
+                                      (96, 72, 3, np.float32)])
+def test_masters_and_calibration(eng, w, h, c, dt):
+    rng = np.random.default_rng(w + h)
+    eng.set_geometry(w, h, c, dt, 4)
+    shape = (h, w) if c == 1 else (h, w, c)
+
+    def frames(n, lo, hi):
+        if dt == np.float32:
+            return [rng.uniform(lo / 65535, hi / 65535, shape).astype(np.float32) for _ in range(n)]
+        top = 255 if dt == np.uint8 else 65535
+        return [rng.integers(int(lo * top / 65535), max(int(hi * top / 65535), 2), shape).astype(dt) for _ in range(n)]
+
+    conv = {np.uint16: oracle.u16_to_f32, np.uint8: lambda a: a.astype(np.float32) * np.float32(1 / 255.0),
+            np.float32: lambda a: a}[dt]
+    bias, dark, dflat, flat = frames(3, 300, 900), frames(6, 900, 3000), frames(2, 500, 1200), frames(5, 20000, 40000)
+    o_bias = oracle.stack_mean([conv(f) for f in bias])
+    o_dark = oracle.stack_mean([conv(f) for f in dark], o_bias)
+    o_dflat = oracle.stack_mean([conv(f) for f in dflat], o_bias)
+    o_flat = oracle.flat_normalize(oracle.stack_mean([conv(f) for f in flat], o_bias, o_dflat))
+    eng.build_master(B.BIAS, bias)
+    eng.build_master(B.DARK, dark)   # 6 frames > 4 in flight: two accumulation passes
+    eng.build_master(B.DARKFLAT, dflat)
+    eng.build_master(B.FLAT, flat)
+    assert np.array_equal(bits(eng.get_master(B.BIAS)), bits(o_bias))
+    assert np.array_equal(bits(eng.get_master(B.DARK)), bits(o_dark))
+    assert np.array_equal(bits(eng.get_master(B.DARKFLAT)), bits(o_dflat))
+    assert np.array_equal(bits(eng.get_master(B.FLAT)), bits(o_flat))
+    light = frames(1, 3000, 60000)[0]
+    eng.set_reference(light, 20)
+    cal = eng.debug_plane(0)
+    o_cal = oracle.calibrate(conv(light), o_bias, o_dark, o_flat)
+    assert np.array_equal(bits(cal), bits(o_cal))
+    assert np.array_equal(bits(eng.debug_plane(1)), bits(oracle.gray(o_cal)))
+    eng.clear_masters()
+    eng.set_reference(light, 20)
+    assert np.array_equal(bits(eng.debug_plane(0)), bits(conv(light)))
+
+
+# ------------------------------------------------------------------------------- K2 / K3
+@pytest.mark.parametrize("w,h", [(203, 165), (640, 480), (1197, 799), (333, 1064), (64, 64)])
+def test_sky_subtraction_and_threshold(eng, w, h):
+    eng.set_geometry(w, h, 1, np.float32, 2)
+    g = blob_image(w, h, 20, seed=w * 3 + h)
+    stars, info = eng.detect_stars(g, 20)
+    lo = oracle.resize_linear(g, w // 8, h // 8)
+    assert np.array_equal(bits(eng.debug_plane(3)), bits(lo))
+    assert np.array_equal(bits(eng.debug_plane(4)), bits(oracle.median5(lo)))
+    o_st = g - oracle.sky_background(g)
+    assert np.array_equal(bits(eng.debug_plane(2)), bits(o_st))
+    m, s = oracle.roi_stats(o_st)
+    assert abs(info.sigma - s) <= 1e-12 * s and abs(info.mean - m) <= 1e-12 * max(abs(m), s)
+    assert np.float32(info.threshold) == np.float32(s * 20 * 1.5)
+    assert np.float32(info.minpeak) == np.float32(s * 20 * 2.0)
+
+
+# ------------------------------------------------------------------------------- K4..K6
+@pytest.mark.parametrize("seed,t", [(0, 2), (1, 5), (2, 20), (3, 1), (4, 50)])
+def test_star_lists_identical(eng, seed, t):
+    w, h = 400, 300
+    eng.set_geometry(w, h, 1, np.float32, 2)
+    g = blob_image(w, h, 60, seed)
+    got, info = eng.detect_stars(g, t)
+    want, oinfo = oracle.get_stars(g, t)
+    assert info.ncomponents == oinfo.ncomponents
+    same_stars(got, want)
+    assert info.nstars == len(want)
+
+
+def test_star_lists_edge_cases(eng):
+    w, h = 160, 120
+    eng.set_geometry(w, h, 1, np.float32, 2)
+    # empty: pure noise at a high threshold
+    g = np.random.default_rng(5).normal(0.05, 0.002, (h, w)).astype(np.float32)
+    got, info = eng.detect_stars(g, 100)
+    assert len(got) == 0 and info.nstars == 0 and len(oracle.get_stars(g, 100)[0]) == 0
+    # very low threshold: thousands of noise components, many of them touching the borders
+    got, info = eng.detect_stars(g, 1)
+    want, _ = oracle.get_stars(g, 1)
+    assert len(want) > 300
+    same_stars(got, want)
+    # one huge blob (>= 10000 px: the deblender is bypassed, adjoiningpixel.cpp:45)
+    yy, xx = np.mgrid[0:h, 0:w]
+    big = (0.05 + 0.5 * np.exp(-0.5 * ((xx - 80) ** 2 + (yy - 60) ** 2) / 40.0 ** 2)).astype(np.float32)
+    big += np.random.default_rng(6).normal(0, 0.0005, (h, w)).astype(np.float32)
+    got, info = eng.detect_stars(big, 3)
+    want, oinfo = oracle.get_stars(big, 3)
+    same_stars(got, want)
+    assert max(want["area"], default=0) >= 10000
+
+
+def test_detect_rgb_u16_matches_cli_star_count(eng):
+    w, h = 1200, 800
+    f = synth.Field(w, h, 120, seed=7)
+    frame = synth.light(f, 0, 3)
+    eng.set_geometry(w, h, 3, np.uint16, 2)
+    got, info = eng.detect_stars(frame, 20)
+    want, _ = oracle.get_stars(oracle.u16_to_f32(frame), 20)
+    assert len(want) > 20
+    same_stars(got, want)
+    counts = eng.detect_stars_batch([frame, synth.light(f, 1, 3), frame], 20)
+    assert counts[0] == counts[2] == len(want)
+    assert counts[1] == len(oracle.get_stars(oracle.u16_to_f32(synth.light(f, 1, 3)), 20)[0])
+
+
+# ------------------------------------------------------------------------------- K7
+def test_alignment_matches_oracle(eng):
+    eng.set_geometry(64, 64, 1, np.float32, 1)
+    rng = np.random.default_rng(21)
+    failed = 0
+    for t in range(60):
+        n1 = int(rng.integers(3, 60))
+        xy1 = np.stack([rng.integers(0, 6000, n1), rng.integers(0, 800, n1)], 1).astype(np.int32)
+        th = rng.uniform(-0.003, 0.003)
+        c, s = np.cos(th), np.sin(th)
+        sh = rng.uniform(-8, 8, 2)
+        xy2 = np.stack([c * xy1[:, 0] - s * xy1[:, 1] + sh[0], s * xy1[:, 0] + c * xy1[:, 1] + sh[1]], 1)
+        xy2 = np.floor(xy2 + rng.normal(0, 0.4, (n1, 2))).astype(np.int32)
+        if t % 2:
+            keep = rng.random(n1) > 0.15
+            extra = np.stack([rng.integers(0, 6000, 5), rng.integers(0, 800, 5)], 1).astype(np.int32)
+            xy2 = np.concatenate([xy2[keep], extra])[rng.permutation(int(keep.sum()) + 5)]
+        got, want = eng.align_lists(xy1, xy2), oracle.align(xy1, xy2)
+        assert np.array_equal(got["table"], want["table"])
+        assert got["k"] == want["k"] and got["err"] == want["err"]
+        assert np.array_equal(got["matches"][:, :got["k"]], want["matches"][:, :want["k"]])
+        assert np.array_equal(bits(got["M"]), bits(want["M"]))
+        failed += want["err"] != 0
+    assert 0 < failed < 60
+    # degenerate inputs: empty lists, fewer than 3 stars, duplicates
+    for a, b in [(np.zeros((0, 2)), np.zeros((0, 2))), ([[1, 2], [3, 4]], [[1, 2], [3, 4]]),
+                 ([[5, 5]] * 10, [[5, 5]] * 10)]:
+        got, want = eng.align_lists(np.array(a), np.array(b)), oracle.align(np.array(a), np.array(b))
+        assert got["err"] == want["err"] == -1 and got["k"] == want["k"]
+
+
+# ------------------------------------------------------------------------------- K8
+@pytest.mark.parametrize("c", [1, 3])
+def test_warp_bit_exact(eng, c):
+    w, h = 131, 97
+    eng.set_geometry(w, h, c, np.float32, 1)
+    rng = np.random.default_rng(30 + c)
+    src = rng.random((h, w, c), dtype=np.float32) if c == 3 else rng.random((h, w), dtype=np.float32)
+    for _ in range(6):
+        ang, s = rng.uniform(-0.2, 0.2), rng.uniform(0.8, 1.2)
+        M = np.array([[s * np.cos(ang), -s * np.sin(ang), rng.uniform(-30, 30)],
+                      [s * np.sin(ang), s * np.cos(ang), rng.uniform(-30, 30)]], np.float32)
+        assert np.array_equal(bits(eng.warp_affine(src, M)), bits(oracle.warp_affine(src, M)))
+    M = np.array([[1, 0, 1000], [0, 1, 1000]], np.float32)  # fully outside: constant-0 border
+    assert not eng.warp_affine(src, M).any()
+
+
+# ------------------------------------------------------------------------------- whole path
+def run_stack(eng, ds, w, h, c, t, slots):
+    eng.set_geometry(w, h, c, np.uint16, slots)
+    if ds["bias"]:
+        eng.build_master(B.BIAS, ds["bias"])
+    if ds["darks"]:
+        eng.build_master(B.DARK, ds["darks"])
+    if ds["darkflats"]:
+        eng.build_master(B.DARKFLAT, ds["darkflats"])
+    if ds["flats"]:
+        eng.build_master(B.FLAT, ds["flats"])
+    eng.set_reference(ds["ref"], t)
+    eng.add_lights(ds["lights"])
+    return eng.finish(), eng.reports()
+
+
+def check_stack(eng, ds, w, h, c, t, slots):
+    (img, tv), reps = run_stack(eng, ds, w, h, c, t, slots)
+    want = oracle.stack(ds["ref"], ds["lights"], t, ds["bias"] or None, ds["darks"] or None,
+                        ds["darkflats"] or None, ds["flats"] or None)
+    ref_stars, _ = eng.reference_stars()
+    same_stars(ref_stars, want["ref_stars"])
+    assert tv == want["total_valid"]
+    for r, o in zip(reps, want["reports"]):
+        assert (r.nstars, r.k, r.err) == (o.nstars, o.k, o.err)
+        assert np.array_equal(bits(np.array(r.M[:])), bits(np.array(o.M[:])))  # tolerance allowed: 1e-4; observed: 0
+    assert np.array_equal(bits(img), bits(want["image"]))  # tolerance allowed: 1e-4 rel; observed: bit-equal
+    return want
+
+
+def test_stack_full_calibration_rgb(eng):
+    w, h = 1200, 800
+    ds = synth.dataset(w, h, 5, 3, nstars=150, ndarks=3, nflats=3, nbias=3, ndarkflats=2)
+    want = check_stack(eng, ds, w, h, 3, 20, slots=2)   # 5 lights over 2 slots: 3 batches, ragged last one
+    assert want["total_valid"] >= 5
+
+
+def test_stack_mono_darks_only_with_a_failing_light(eng):
+    w, h = 1000, 700
+    ds = synth.dataset(w, h, 4, 1, nstars=120, ndarks=2)
+    ds["lights"][2] = synth.dark(w, h, 77, 1)          # no stars at all: alignment fails, frame skipped
+    want = check_stack(eng, ds, w, h, 1, 20, slots=4)
+    assert want["reports"][2].err == -1 and want["total_valid"] == 4
+
+
+def test_no_light_aligns_is_the_reference_error(eng):
+    w, h = 320, 240
+    ds = synth.dataset(w, h, 2, 1, nstars=30)
+    ds["lights"] = [synth.dark(w, h, i, 1) for i in range(2)]
+    eng.set_geometry(w, h, 1, np.uint16, 2)
+    eng.set_reference(ds["ref"], 20)
+    eng.add_lights(ds["lights"])
+    with pytest.raises(ob.OssError) as e:
+        eng.finish()
+    assert e.value.status == -6 and "No images could be aligned" in str(e.value)
+
+
+def test_device_resident_frames_give_the_same_stack(eng):
+    w, h = 640, 480
+    ds = synth.dataset(w, h, 3, 3, nstars=80, ndarks=2)
+    (img, tv), _ = run_stack(eng, ds, w, h, 3, 20, 4)
+    ptrs = [eng.to_device(f) for f in ds["lights"]]
+    rp = eng.to_device(ds["ref"])
+    eng.set_reference(rp, 20, mem=B.DEVICE)
+    eng.add_lights(ptrs, mem=B.DEVICE)
+    img2, tv2 = eng.finish()
+    for p in ptrs + [rp]:
+        eng.device_free(p)
+    assert tv == tv2 and np.array_equal(bits(img), bits(img2))
+
+
+def test_stack_is_linear_in_repeated_frames(eng):
+    """size-independent property: stacking the reference with k copies of itself returns the reference
+    (identity transform, every copy aligned), up to (1+k) * x * float(1/(1+k)) rounding."""
+    w, h = 800, 600
+    f = synth.Field(w, h, 100, seed=3)
+    ref = synth.light(f, 0, 1)
+    eng.set_geometry(w, h, 1, np.uint16, 4)
+    eng.set_reference(ref, 20)
+    eng.add_lights([ref] * 3)
+    img, tv = eng.finish()
+    assert tv == 4
+    for r in eng.reports():
+        assert r.err == 0 and np.allclose(np.array(r.M[:]), [1, 0, 0, 0, 1, 0], atol=1e-4)
+    x = oracle.u16_to_f32(ref)
+    inner = img[2:-2, 2:-2]
+    assert np.max(np.abs(inner - x[2:-2, 2:-2])) <= 2e-7
