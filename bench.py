@@ -1,0 +1,372 @@
+#!/usr/bin/env python
+"""bench.py — 24 MP frames/sec (calibrate + align + stack) on N B200s.
+
+Workload (BASELINE.json configs[1], the one the metric is quoted on): a stack of
+50 x 24 MP (6000x4000) 16-bit RGB lights with 10 darks, 10 flats and 10 bias frames:
+full calibration + star detection + FOCAS alignment + warp + mean stack.  One *step* is
+the whole job on one GPU: build the three masters, calibrate + detect the reference,
+process the 50 lights, finalise the mean.  frames/s = (lights + reference) / step time.
+With N > 1 every rank processes its own 50 lights against the masters and reference
+broadcast from rank 0 and one NCCL reduce combines the sum images (weak scaling).
+
+Printed JSON keys follow the driver's contract; see DESIGN.md "Measurement".
+  value     device-resident inputs, timed with CUDA events on the engine's stream
+  e2e       same job through the C ABI with pinned HOST buffers, H2D + D2H inside the timing
+  roofline  the dominant kernel's algorithmic bytes / its mean CUDA-event duration
+  cpu_baseline  the reference's CPU path (oracle/) on this box's cores, bounded sample
+`--impl reference` times only that CPU path (rank 0), same metric/config.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "24MP frames/sec (calibrate+align+stack)"
+UNIT = "frames/s"
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag, self.proc = index, [], False, None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                if self.stop_flag:
+                    break
+                self.rows.append([x.strip() for x in line.split(",")])
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def star_motion(field, index, w, h):
+    from openskystacker_b200 import synth
+    ang, dx, dy = synth.motion(index, w, h)
+    cx, cy = 0.5 * w, 0.5 * h
+    ca, sa = np.cos(ang), np.sin(ang)
+    xs = cx + ca * (field.x - cx) - sa * (field.y - cy) + dx
+    ys = cy + sa * (field.x - cx) + ca * (field.y - cy) + dy
+    return np.stack([xs, ys, field.amp, field.sigma], 1).astype(np.float32)
+
+
+class Inputs:
+    """Seeded synthetic stack rendered directly in HBM (oss_synth_*), SURVEY.md §8(d) spec."""
+
+    def __init__(self, eng, w, h, nlights, ncal, first_light=1):
+        from openskystacker_b200 import synth
+        self.eng, self.w, self.h = eng, w, h
+        nb = eng.frame_bytes()
+        field = synth.Field(w, h, max(60, int(600 * w * h / 24e6)), 1234)
+        mk = lambda: eng.device_alloc(nb)
+        self.bias, self.darks, self.flats = [mk() for _ in range(ncal)], [mk() for _ in range(ncal)], [mk() for _ in range(ncal)]
+        for i, p in enumerate(self.bias):
+            eng.synth_calib(p, 100.0, 5.0, False, 0.0, 4000 + i)
+        for i, p in enumerate(self.darks):
+            eng.synth_calib(p, 300.0, 20.0, False, 100.0, 3000 + i)
+        for i, p in enumerate(self.flats):
+            eng.synth_calib(p, 0.5 * 65535.0, 50.0, True, 100.0, 5000 + i)
+        self.ref = mk()
+        eng.synth_light(self.ref, star_motion(field, 0, w, h), pedestal_adu=400.0, vignette=True, seed=1000)
+        self.lights = [mk() for _ in range(nlights)]
+        for i, p in enumerate(self.lights):
+            eng.synth_light(p, star_motion(field, first_light + i, w, h), pedestal_adu=400.0, vignette=True,
+                            seed=1000 + first_light + i)
+
+    def all_ptrs(self):
+        return self.bias + self.darks + self.flats + [self.ref] + self.lights
+
+
+def run_job(eng, B, cal, ref, light_arr, nlights, mem, result_host, comm=None, rank=0):
+    """One step.  cal = (bias_ptrs, dark_ptrs, flat_ptrs) as ctypes arrays + counts."""
+    L, h = eng._L, eng._h
+    if rank == 0:
+        for kind, (arr, n) in zip((B.BIAS, B.DARK, B.FLAT), cal):
+            eng._ck(L.oss_build_master(h, kind, arr, n, mem))
+        eng._ck(L.oss_set_reference(h, ref, mem, 20))
+    if comm:
+        eng.comm_broadcast_masters(0)
+        eng.comm_broadcast_reference(0)
+    eng._ck(L.oss_add_lights(h, light_arr, nlights, mem))
+    if comm:
+        eng.comm_reduce(0)
+    if rank == 0:
+        import ctypes as C
+        tv = C.c_int()
+        eng._ck(L.oss_finish(h, result_host, C.byref(tv)))
+        return tv.value
+    eng.sync()
+    return 0
+
+
+def cpu_baseline(raw_lights, ref_raw, cal_frames, threads, steps=1, warmup=0):
+    """The reference's CPU path on this box (all in host memory).  Returns (fps, kind, note, times)."""
+    import oracle
+    from oracle import cv2_pipeline as cvp
+    conv = oracle.u16_to_f32
+    bias = oracle.stack_mean([conv(f) for f in cal_frames[0]]) if cal_frames[0] else None
+    dark = oracle.stack_mean([conv(f) for f in cal_frames[1]], bias) if cal_frames[1] else None
+    flat = oracle.flat_normalize(oracle.stack_mean([conv(f) for f in cal_frames[2]], bias)) if cal_frames[2] else None
+    ref_cal = oracle.calibrate(conv(ref_raw), bias, dark, flat)
+    use_cv = cvp.available()
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        if use_cv:
+            cvp.stack_lights(raw_lights, (bias, dark, flat), 20, ref_cal, threads)
+        else:
+            from concurrent.futures import ThreadPoolExecutor
+
+            def worker(i):
+                part = np.zeros_like(ref_cal)
+                for k in range(i, len(raw_lights), threads):
+                    oracle.process_light(raw_lights[k], bias, dark, flat, 20, ref_cal, None, part)
+                return part
+            with ThreadPoolExecutor(threads) as ex:
+                list(ex.map(worker, range(threads)))
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    kind = "port"
+    note = ("cv2 %s optimised + reference object code (oracle/_ref) for deblend/FOCAS/HFTI, strided workers like "
+            "util.cpp:738, ref stars re-detected per light like util.cpp:559" % __import__("cv2").__version__) if use_cv else \
+        "plain-C oracle (oracle/oss_oracle.c), strided workers"
+    return len(raw_lights) / float(np.mean(times)), kind, note, times
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--width", type=int, default=6000)
+    ap.add_argument("--height", type=int, default=4000)
+    ap.add_argument("--lights", type=int, default=50)
+    ap.add_argument("--ncal", type=int, default=10)
+    ap.add_argument("--slots", type=int, default=8)
+    ap.add_argument("--cpu-lights", type=int, default=0, help="lights in the CPU sample (0 = host cores)")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 3) if a.impl != "reference" else a.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    cores = os.cpu_count() or 1
+    W, H, C = a.width, a.height, 3
+    workload = f"{a.lights} x {W}x{H} RGB16 lights + {a.ncal} darks + {a.ncal} flats + {a.ncal} bias: full calibration + align + stack"
+    config = {"workload": workload, "width": W, "height": H, "channels": C, "lights_per_gpu": a.lights,
+              "calibration_frames": 3 * a.ncal, "threshold": 20, "frames_in_flight": a.slots,
+              "l2": "inputs (%.1f GB per step) are far larger than L2" % ((a.lights + 1 + 3 * a.ncal) * W * H * C * 2 / 1e9),
+              "parallelism": f"frames sharded over {world} GPU(s), one ncclReduce of the f32 sum" if world > 1 else "1 GPU"}
+
+    import openskystacker_b200 as ob
+    from openskystacker_b200 import binding as B
+    from openskystacker_b200 import synth
+
+    # ------------------------------------------------------------------ reference arm (CPU only)
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        nl = a.cpu_lights or cores
+        try:
+            eng = ob.Engine(local)
+            eng.set_geometry(W, H, C, np.uint16, 1)
+            inp = Inputs(eng, W, H, nl, a.ncal)
+            shape = (H, W, C)
+            pull = lambda p: eng.from_device(p, shape, np.uint16)
+            cal = ([pull(p) for p in inp.bias], [pull(p) for p in inp.darks], [pull(p) for p in inp.flats])
+            ref, lights = pull(inp.ref), [pull(p) for p in inp.lights]
+            eng.close()
+            data = "synthetic (seeded star field rendered on the GPU, copied to host before timing)"
+        except ob.OssError:
+            ds = synth.dataset(W, H, nl, C, ndarks=a.ncal, nflats=a.ncal, nbias=a.ncal)
+            cal, ref, lights = (ds["bias"], ds["darks"], ds["flats"]), ds["ref"], ds["lights"]
+            data = "synthetic (numpy)"
+        fps, kind, note, times = cpu_baseline(lights, ref, cal, cores, a.steps, a.warmup)
+        sample = f"{nl} of {a.lights} lights per step against a prebuilt reference + masters, {cores} worker threads; {note}"
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+                          "warmup": a.warmup, "ms_per_step": 1e3 * float(np.mean(times)), "higher_is_better": True,
+                          "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": data, "config": config,
+                          "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+                          "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    # ------------------------------------------------------------------ our arm
+    import ctypes as Ct
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    eng = ob.Engine(local)
+    eng.set_geometry(W, H, C, np.uint16, a.slots)
+    comm = None
+    if world > 1:
+        box = [ob.Engine.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        eng.comm_init(box[0], rank, world)
+        comm = True
+
+    inp = Inputs(eng, W, H, a.lights, a.ncal if rank == 0 else 0, first_light=1 + rank * a.lights)
+    arr = lambda ps: ((Ct.c_void_p * len(ps))(*ps), len(ps))
+    cal_d = (arr(inp.bias), arr(inp.darks), arr(inp.flats))
+    lights_d, nl = arr(inp.lights)
+    nb = eng.frame_bytes()
+
+    def barrier():
+        eng.sync()
+        if dist:
+            dist.barrier()
+
+    def timed(fn, steps):
+        """-> per-step seconds, max over ranks (device events for our own stream; wall for host-fed runs)."""
+        out = []
+        for _ in range(steps):
+            barrier()
+            t0 = time.perf_counter()
+            eng.mark(0)
+            fn()
+            eng.mark(1)
+            dev_ms = eng.elapsed_ms()
+            barrier()
+            wall = time.perf_counter() - t0
+            out.append((dev_ms * 1e-3, wall))
+        if dist:
+            import torch
+            t = torch.tensor(out, dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            out = [tuple(x) for x in t.cpu().tolist()]
+        return out
+
+    step_dev = lambda: run_job(eng, B, cal_d, Ct.c_void_p(inp.ref), lights_d, nl, B.DEVICE, None, comm, rank)
+    timed(step_dev, a.warmup)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    eng.profile_reset()
+    eng.profile(True)
+    l0 = eng.launch_count()
+    t_dev = timed(step_dev, a.steps)
+    launches = eng.launch_count() - l0
+    eng.profile(False)
+    prof = eng.profile_table()
+    clocks = sampler.finish() if rank == 0 else None
+    frames_total = world * a.lights + 1
+    dev_s = float(np.mean([t[0] for t in t_dev]))
+    value = frames_total / dev_s
+
+    # ------------------------------------------------------------------ e2e: pinned host buffers in, result out
+    e2e = None
+    if not a.no_e2e:
+        L = eng._L
+        host = {}
+        for p in inp.all_ptrs():
+            hp = L.oss_host_alloc(nb)
+            if not hp:
+                raise SystemExit("pinned allocation failed")
+            eng._ck(L.oss_memcpy_d2h(eng._h, hp, p, nb))
+            host[p] = hp
+        hp_arr = lambda ps: ((Ct.c_void_p * len(ps))(*[host[p] for p in ps]), len(ps))
+        cal_h = (hp_arr(inp.bias), hp_arr(inp.darks), hp_arr(inp.flats))
+        lights_h, _ = hp_arr(inp.lights)
+        res_host = L.oss_host_alloc(W * H * C * 4) if rank == 0 else None
+        step_host = lambda: run_job(eng, B, cal_h, Ct.c_void_p(host[inp.ref]), lights_h, nl, B.HOST,
+                                    Ct.c_void_p(res_host) if rank == 0 else None, comm, rank)
+        timed(step_host, 1)
+        t_host = timed(step_host, max(1, min(a.steps, 3)))
+        wall_s = float(np.mean([t[1] for t in t_host]))
+        h2d = (a.lights + (1 + 3 * a.ncal if rank == 0 else 0)) * nb
+        e2e = {"value": frames_total / wall_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(W * H * C * 4), "ms_per_step": 1e3 * wall_s,
+               "timing": "wall clock between stream syncs (covers H2D, kernels, D2H of the float32 stack)"}
+
+    if rank != 0:
+        if dist:
+            dist.destroy_process_group()
+        return
+
+    # ------------------------------------------------------------------ roofline of the dominant kernel
+    peak, peak_src = peaks()
+    P = W * H
+    M = 3
+    per_frame = {  # algorithmic bytes per light frame, SURVEY.md §8(d)
+        "calibrate_gray": P * (2 * C + 4 * C * M + 4 * C + 4),
+        "sky_sub_stats": P * (4 + 4),
+        "warp_accumulate": P * (12 * C),
+    }
+    hbm = {k: v for k, v in prof.items() if k in per_frame}
+    total_ms = sum(ms for ms, _ in prof.values())
+    shares = {k: round(ms / total_ms, 4) for k, (ms, n) in sorted(prof.items(), key=lambda kv: -kv[1][0])}
+    roof = None
+    if hbm:
+        name = max(hbm, key=lambda k: hbm[k][0])
+        ms, n = hbm[name]
+        frames_done = a.steps * (a.lights + (1 if name != "warp_accumulate" else 0))
+        achieved = per_frame[name] * frames_done / (ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src, "launches": n, "avg_launch_ms": ms / n,
+                "algorithmic_bytes_per_frame": per_frame[name], "kernel_time_shares": shares,
+                "whole_pipeline": {"algorithmic_bytes_per_frame": P * 102,
+                                   "achieved_gbs": P * 102 * (a.lights + 1) / dev_s / 1e9,
+                                   "frac": P * 102 * (a.lights + 1) / dev_s / 1e9 / peak}}
+
+    # ------------------------------------------------------------------ CPU baseline beside it (N = 1 only)
+    cpu = None
+    if world == 1 and not a.no_cpu:
+        ncpu = a.cpu_lights or cores
+        shape = (H, W, C)
+        pull = lambda p: eng.from_device(p, shape, np.uint16)
+        cal = ([pull(p) for p in inp.bias], [pull(p) for p in inp.darks], [pull(p) for p in inp.flats])
+        fps, kind, note, times = cpu_baseline([pull(p) for p in inp.lights[:ncpu]], pull(inp.ref), cal, cores)
+        cpu = {"value": fps, "unit": UNIT, "cores": cores, "kind": kind,
+               "sample": f"{min(ncpu, a.lights)} of the {a.lights} lights (same bytes as the GPU run) against prebuilt masters + reference, "
+                         f"{cores} worker threads, {times[0]:.1f} s; {note}"}
+
+    print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+                      "ms_per_step": 1e3 * dev_s, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                      "dtype": "f32", "data": "synthetic (seeded star field + dark/flat/bias frames rendered in HBM)",
+                      "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof,
+                      "cpu_baseline": cpu}))
+    if dist:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

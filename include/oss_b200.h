@@ -124,10 +124,10 @@ OSS_API int oss_clear_masters(oss_ctx *ctx);
  *   util.cpp:559 — same values, no need to repeat).
  * oss_add_lights: the body of processConcurrent's loop (util.cpp:738-751) for n lights:
  *   calibrate, getStars, triangles, vote, HFTI fit, warpAffine, accumulate; lights whose
- *   alignment fails are skipped silently.  Asynchronous: returns once the work is queued
- *   (host frames are fully consumed before it returns only if oss_sync is called, or on
- *   the next call that reuses the staging slot — the library copies them on entry to
- *   pinned staging, so the caller may reuse its buffers after return).
+ *   alignment fails are skipped silently.  Asynchronous: it returns once the copies and
+ *   kernels are queued; OSS_MEM_HOST frames must stay valid and unmodified until
+ *   oss_sync / oss_finish / oss_get_frame_report returns (pinned buffers from
+ *   oss_host_alloc are copied by DMA while earlier batches compute).
  * oss_finish: workingImage /= totalValidImages (imagestacker.cpp:361), copies the float32
  *   HWC result to out_host (may be NULL to leave it on the device) and returns the count.
  *   OSS_E_NO_ALIGNED when totalValidImages < 2 (imagestacker.cpp:355-359). */
@@ -175,6 +175,19 @@ OSS_API int oss_comm_broadcast_masters(oss_ctx *ctx, int root);
 OSS_API int oss_comm_broadcast_reference(oss_ctx *ctx, int root);
 /* ncclReduce(sum) + count to root over NVLink; afterwards oss_finish on root gives the stack */
 OSS_API int oss_comm_reduce(oss_ctx *ctx, int root);
+
+/* ---- bench utilities (no reference counterpart) -------------------------------------------
+ * oss_mark(0) / oss_mark(1) record CUDA events on the engine's compute stream; oss_elapsed_ms
+ * waits for mark 1 and returns the device time between them.
+ * oss_synth_*: seeded synthetic u16 frames rendered directly in device memory (star field
+ * through a per-frame motion, or dark/bias/flat-like calibration frames), so that device-
+ * resident benchmarks need no host rendering.  stars_xyas = nstars * (x, y, amplitude, sigma). */
+OSS_API int oss_mark(oss_ctx *ctx, int which);
+OSS_API int oss_elapsed_ms(oss_ctx *ctx, double *ms);
+OSS_API int oss_synth_light(oss_ctx *ctx, void *dst_dev, const float *stars_xyas, int nstars, float background,
+                            float noise, float pedestal_adu, int vignette, unsigned seed, const float *gains3);
+OSS_API int oss_synth_calib(oss_ctx *ctx, void *dst_dev, float level_adu, float sigma_adu, int flat_profile,
+                            float pedestal_adu, unsigned seed);
 
 /* ---- instrumentation ------------------------------------------------------------------- */
 /* CUDA-event timing of every kernel launch, on the stream it is launched on. */

@@ -87,6 +87,11 @@ _SIGS = {
     "oss_comm_broadcast_masters": (C.c_int, [C.c_void_p, C.c_int]),
     "oss_comm_broadcast_reference": (C.c_int, [C.c_void_p, C.c_int]),
     "oss_comm_reduce": (C.c_int, [C.c_void_p, C.c_int]),
+    "oss_mark": (C.c_int, [C.c_void_p, C.c_int]),
+    "oss_elapsed_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
+    "oss_synth_light": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int,
+                                  C.c_uint, C.c_void_p]),
+    "oss_synth_calib": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_int, C.c_float, C.c_uint]),
     "oss_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "oss_profile_reset": (C.c_int, [C.c_void_p]),
     "oss_profile_count": (C.c_int, [C.c_void_p]),
@@ -317,6 +322,29 @@ class Engine:
 
     def comm_reduce(self, root=0):
         self._ck(self._L.oss_comm_reduce(self._h, root))
+
+    # -- bench utilities
+    def mark(self, which):
+        self._ck(self._L.oss_mark(self._h, which))
+
+    def elapsed_ms(self):
+        ms = C.c_double()
+        self._ck(self._L.oss_elapsed_ms(self._h, C.byref(ms)))
+        return ms.value
+
+    def synth_light(self, dst_dev, stars_xyas, background=0.05, noise=0.002, pedestal_adu=0.0, vignette=False, seed=0,
+                    gains=(1.0, 0.9, 0.8)):
+        st = np.ascontiguousarray(stars_xyas, np.float32).reshape(-1, 4)
+        g = np.asarray(gains, np.float32)
+        self._ck(self._L.oss_synth_light(self._h, C.c_void_p(dst_dev), _ptr(st), len(st), background, noise, pedestal_adu,
+                                         int(vignette), seed, _ptr(g)))
+
+    def synth_calib(self, dst_dev, level_adu, sigma_adu, flat_profile=False, pedestal_adu=0.0, seed=0):
+        self._ck(self._L.oss_synth_calib(self._h, C.c_void_p(dst_dev), level_adu, sigma_adu, int(flat_profile), pedestal_adu, seed))
+
+    def frame_bytes(self):
+        h, w, c, dt = self.geom
+        return h * w * c * dt.itemsize
 
     # -- instrumentation
     def profile(self, on):

@@ -17,6 +17,7 @@
 #include "k_detect.cuh"
 #include "k_focas.cuh"
 #include "k_sky.cuh"
+#include "k_synth.cuh"
 #include "k_warp.cuh"
 
 using namespace oss;
@@ -66,7 +67,7 @@ struct oss_ctx {
     Geom g{};
     bool has_geom = false;
     int slots = 0;
-    size_t frame_bytes = 0;
+    size_t frame_bytes = 0, stage_stride = 0; // stage_stride: frame_bytes rounded up to 256
     std::vector<void *> allocs; // geometry-scoped device allocations
     std::vector<void *> user_allocs;
     float *master[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -97,6 +98,9 @@ struct oss_ctx {
     std::vector<ProfPending> prof_pending;
     std::vector<cudaEvent_t> event_pool;
     long long launches = 0;
+    cudaEvent_t mark[2] = {nullptr, nullptr};
+    float *synth_plane = nullptr;
+    float4 *synth_stars = nullptr;
     // multi-GPU
     ncclComm_t comm = nullptr;
     int rank = 0, nranks = 1;
@@ -196,6 +200,8 @@ static void free_geometry(oss_ctx *c)
     }
     c->has_geom = false;
     c->has_ref = false;
+    c->synth_plane = nullptr;
+    c->synth_stars = nullptr;
 }
 
 // ---- exported: lifetime ----------------------------------------------------------------
@@ -330,23 +336,25 @@ int oss_set_geometry(oss_ctx *c, int W, int H, int C, int sample, int slots)
     long long div = 16;
     if (const char *e = getenv("OSS_B200_CAP_DIV")) div = atoll(e) > 0 ? atoll(e) : 16;
     long long cap = g.P / div;
-    if (cap < 4096) cap = g.P < 4096 ? g.P : 4096;
+    if (cap < 65536) cap = g.P < 65536 ? g.P : 65536; // small frames: every pixel may be a candidate
     g.cap = (int)cap;
     c->g = g;
     c->slots = slots;
     const size_t ssz = sample == OSS_U8 ? 1 : (sample == OSS_U16 ? 2 : 4);
     c->frame_bytes = (size_t)g.P * C * ssz;
+    c->stage_stride = (c->frame_bytes + 255) / 256 * 256;
     const long long PC = g.P * C, nsegs = (long long)H * g.nseg, lo = (long long)g.lw * g.lh;
     Workspace &w = c->ws;
     w = Workspace{};
-    w.strideP = g.P; w.stridePC = PC; w.strideLo = lo; w.strideSeg = nsegs;
+    auto pad64 = [](long long v) { return (v + 63) / 64 * 64; }; // keep every slot 256-byte aligned
+    w.strideP = pad64(g.P); w.stridePC = pad64(PC); w.strideLo = lo; w.strideSeg = nsegs;
     w.stat_blocks = ((W + SKY_T - 1) / SKY_T) * ((H + SKY_T - 1) / SKY_T);
     w.stridePart = 2ll * w.stat_blocks;
     long long scan_max = nsegs + 1 > cap ? nsegs + 1 : cap;
     w.strideScan = (scan_max + SCAN_ITEMS - 1) / SCAN_ITEMS + 1;
-    DA(w.cal, slots * PC);
-    if (C == 3) { DA(w.gray, slots * g.P); } else w.gray = w.cal;
-    DA(w.stars, slots * g.P);
+    DA(w.cal, slots * w.stridePC);
+    if (C == 3) { DA(w.gray, slots * w.strideP); } else w.gray = w.cal;
+    DA(w.stars, slots * w.strideP);
     DA(w.lo, slots * lo); DA(w.med, slots * lo);
     DA(w.segmax, slots * nsegs); DA(w.segmask, slots * nsegs); DA(w.segoff, slots * (nsegs + 1));
     DA(w.partials, slots * w.stridePart);
@@ -368,7 +376,7 @@ int oss_set_geometry(oss_ctx *c, int W, int H, int C, int sample, int slots)
     DA(c->d_dbg_matches, 3 * OSS_MAX_MATCH); DA(c->d_dbg_table, OSS_NOBJS * OSS_NOBJS);
     DA(c->d_M, 8); DA(c->d_flat_ratio, 4); DA(c->d_flat_partial, 1024);
     for (int i = 0; i < 2; i++) {
-        DA(c->raw_stage[i], (size_t)slots * c->frame_bytes);
+        DA(c->raw_stage[i], (size_t)slots * c->stage_stride);
         CK(cudaEventCreateWithFlags(&c->copy_done[i], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&c->raw_free[i], cudaEventDisableTiming));
     }
@@ -454,7 +462,7 @@ static int stage_frames(oss_ctx *c, const void *const *frames, int n, int mem, F
     int set = (int)(c->batch_counter++ & 1);
     CK(cudaStreamWaitEvent(c->copy_stream, c->raw_free[set], 0));
     for (int i = 0; i < n; i++) {
-        unsigned char *dst = c->raw_stage[set] + (size_t)i * c->frame_bytes;
+        unsigned char *dst = c->raw_stage[set] + (size_t)i * c->stage_stride;
         CK(cudaMemcpyAsync(dst, frames[i], c->frame_bytes, cudaMemcpyHostToDevice, c->copy_stream));
         fp->p[i] = dst;
     }
@@ -945,6 +953,53 @@ int oss_comm_reduce(oss_ctx *c, int root)
     CK(cudaStreamSynchronize(c->copy_stream));
     NK(g_nccl.Reduce(c->sum, c->sum, (size_t)count, ncclFloat32, ncclSum, root, c->comm, c->stream));
     NK(g_nccl.Reduce(c->d_valid, c->d_valid, 1, ncclInt32, ncclSum, root, c->comm, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return OSS_OK;
+}
+
+// ---- device timer + synthetic frames (bench utilities) ---------------------------------
+int oss_mark(oss_ctx *c, int which)
+{
+    if (!c || which < 0 || which > 1) return OSS_E_ARG;
+    CK(cudaSetDevice(c->device));
+    if (!c->mark[which]) CK(cudaEventCreate(&c->mark[which]));
+    CK(cudaEventRecord(c->mark[which], c->stream));
+    return OSS_OK;
+}
+
+int oss_elapsed_ms(oss_ctx *c, double *ms)
+{
+    if (!c || !ms || !c->mark[0] || !c->mark[1]) return OSS_E_ARG;
+    CK(cudaEventSynchronize(c->mark[1]));
+    float f = 0.f;
+    CK(cudaEventElapsedTime(&f, c->mark[0], c->mark[1]));
+    *ms = f;
+    return OSS_OK;
+}
+
+int oss_synth_light(oss_ctx *c, void *dst_dev, const float *stars_xyas, int nstars, float background, float noise,
+                    float pedestal_adu, int vignette, unsigned seed, const float *gains3)
+{
+    NEED_GEOM();
+    const Geom &g = c->g;
+    if (g.sample != OSS_U16 || !dst_dev || nstars < 0 || nstars > 65536) return fail(c, OSS_E_ARG, "synth needs a u16 geometry");
+    if (!c->synth_plane) { DA(c->synth_plane, g.P); DA(c->synth_stars, 65536); }
+    if (nstars) CK(cudaMemcpyAsync(c->synth_stars, stars_xyas, sizeof(float4) * nstars, cudaMemcpyHostToDevice, c->stream));
+    LAUNCH("synth", k_synth_fill, 1184, 256, 0, c->synth_plane, g.P, background);
+    if (nstars) LAUNCH("synth", k_synth_splat, nstars, 128, 0, c->synth_plane, g.W, g.H, c->synth_stars, nstars);
+    const float g0 = gains3 ? gains3[0] : 1.f, g1 = gains3 ? gains3[1] : 1.f, g2 = gains3 ? gains3[2] : 1.f;
+    LAUNCH("synth", k_synth_quantize, 1184, 256, 0, c->synth_plane, (uint16_t *)dst_dev, g.W, g.H, g.C, noise, pedestal_adu, vignette,
+           seed, g0, g1, g2);
+    CK(cudaStreamSynchronize(c->stream));
+    return OSS_OK;
+}
+
+int oss_synth_calib(oss_ctx *c, void *dst_dev, float level_adu, float sigma_adu, int flat_profile, float pedestal_adu, unsigned seed)
+{
+    NEED_GEOM();
+    const Geom &g = c->g;
+    if (g.sample != OSS_U16 || !dst_dev) return fail(c, OSS_E_ARG, "synth needs a u16 geometry");
+    LAUNCH("synth", k_synth_calib, 1184, 256, 0, (uint16_t *)dst_dev, g.W, g.H, g.C, level_adu, sigma_adu, flat_profile, pedestal_adu, seed);
     CK(cudaStreamSynchronize(c->stream));
     return OSS_OK;
 }

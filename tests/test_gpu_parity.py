@@ -127,14 +127,18 @@ def test_star_lists_edge_cases(eng):
     want, _ = oracle.get_stars(g, 1)
     assert len(want) > 300
     same_stars(got, want)
-    # one huge blob (>= 10000 px: the deblender is bypassed, adjoiningpixel.cpp:45)
-    yy, xx = np.mgrid[0:h, 0:w]
-    big = (0.05 + 0.5 * np.exp(-0.5 * ((xx - 80) ** 2 + (yy - 60) ** 2) / 40.0 ** 2)).astype(np.float32)
-    big += np.random.default_rng(6).normal(0, 0.0005, (h, w)).astype(np.float32)
-    got, info = eng.detect_stars(big, 3)
-    want, oinfo = oracle.get_stars(big, 3)
+    # one huge component (>= 10000 px: the deblender is bypassed, adjoiningpixel.cpp:45): a 1-px lattice
+    # on an 8-px pitch that the low-res sky grid (samples at 8d+3, 8d+4) never sees
+    w, h = 240, 200
+    eng.set_geometry(w, h, 1, np.float32, 2)
+    lat = np.full((h, w), 0.05, np.float32)
+    lat[::8, :] = 1.0
+    lat[:, ::8] = 1.0
+    lat += np.random.default_rng(6).normal(0, 0.001, (h, w)).astype(np.float32)
+    got, info = eng.detect_stars(lat, 1)
+    want, oinfo = oracle.get_stars(lat, 1)
+    assert len(want) >= 1 and max(want["area"]) >= 10000
     same_stars(got, want)
-    assert max(want["area"], default=0) >= 10000
 
 
 def test_detect_rgb_u16_matches_cli_star_count(eng):
@@ -144,7 +148,7 @@ def test_detect_rgb_u16_matches_cli_star_count(eng):
     eng.set_geometry(w, h, 3, np.uint16, 2)
     got, info = eng.detect_stars(frame, 20)
     want, _ = oracle.get_stars(oracle.u16_to_f32(frame), 20)
-    assert len(want) > 20
+    assert len(want) >= 10
     same_stars(got, want)
     counts = eng.detect_stars_batch([frame, synth.light(f, 1, 3), frame], 20)
     assert counts[0] == counts[2] == len(want)
@@ -269,19 +273,39 @@ def test_device_resident_frames_give_the_same_stack(eng):
     assert tv == tv2 and np.array_equal(bits(img), bits(img2))
 
 
-def test_stack_is_linear_in_repeated_frames(eng):
-    """size-independent property: stacking the reference with k copies of itself returns the reference
-    (identity transform, every copy aligned), up to (1+k) * x * float(1/(1+k)) rounding."""
-    w, h = 800, 600
-    f = synth.Field(w, h, 100, seed=3)
-    ref = synth.light(f, 0, 1)
-    eng.set_geometry(w, h, 1, np.uint16, 4)
-    eng.set_reference(ref, 20)
-    eng.add_lights([ref] * 3)
-    img, tv = eng.finish()
-    assert tv == 4
-    for r in eng.reports():
-        assert r.err == 0 and np.allclose(np.array(r.M[:]), [1, 0, 0, 0, 1, 0], atol=1e-4)
-    x = oracle.u16_to_f32(ref)
-    inner = img[2:-2, 2:-2]
-    assert np.max(np.abs(inner - x[2:-2, 2:-2])) <= 2e-7
+def test_batch_size_invariance_and_identical_frames(eng):
+    """Size-independent properties: (1) the stack does not depend on how many frames share a launch
+    (the accumulation order is the frame order either way): bit-equal image and reports for 1 vs 4
+    frames in flight; (2) lights identical to the reference (the degenerate all-zero-residual case of
+    focas.cpp:338-369) behave exactly like the oracle says, whatever that is."""
+    w, h = 1000, 700
+    ds = synth.dataset(w, h, 5, 1, nstars=120, seed=1234)
+    (img1, tv1), rep1 = run_stack(eng, ds, w, h, 1, 20, 1)
+    (img4, tv4), rep4 = run_stack(eng, ds, w, h, 1, 20, 4)
+    assert tv1 == tv4 == 6 and np.array_equal(bits(img1), bits(img4))
+    for a, b in zip(rep1, rep4):
+        assert (a.nstars, a.k, a.err) == (b.nstars, b.k, b.err) and list(a.M) == list(b.M)
+    # identical frames: every residual is 0 -> lim = 0 rejects all pairs -> every light is skipped, in the
+    # reference (oracle) and here alike; the stack then ends with the reference's own error
+    same = [ds["ref"]] * 3
+    want = oracle.stack(ds["ref"], same, 20)
+    eng.set_reference(ds["ref"], 20)
+    eng.add_lights(same)
+    for r, o in zip(eng.reports(), want["reports"]):
+        assert (r.nstars, r.k, r.err) == (o.nstars, o.k, o.err)
+        assert np.array_equal(bits(np.array(r.M[:])), bits(np.array(o.M[:])))
+    if want["total_valid"] < 2:
+        with pytest.raises(ob.OssError) as e:
+            eng.finish()
+        assert e.value.status == -6
+    else:
+        assert eng.finish()[1] == want["total_valid"]
+
+
+def test_full_size_24mp_rgb_parity(eng):
+    """Config-1 geometry (6000x4000 RGB16 + darks) on two lights: star lists, transforms and the stacked
+    image against the oracle at full size."""
+    w, h = 6000, 4000
+    ds = synth.dataset(w, h, 2, 3, nstars=600, ndarks=2)
+    want = check_stack(eng, ds, w, h, 3, 20, 2)
+    assert want["total_valid"] == 3 and len(want["ref_stars"]) > 100
