@@ -77,11 +77,13 @@ __device__ __forceinline__ bool make_triangle(const int *xy, int n, uint32_t ijk
     return true;
 }
 
-// Ordered triangle list for one star list, by the whole CTA (blockDim.x == 256).
-// Thread t owns triples [t*39, t*39+39); kept ones are written in enumeration order.
+// Ordered triangle list for one star list, by the whole CTA (blockDim.x == FOCAS_NT).
+// Thread t owns PER consecutive triples; kept ones are written in enumeration order.
+#define FOCAS_NT 1024
+#define FOCAS_NW (FOCAS_NT / 32)
 __device__ int build_triangle_list(const int *xy, int n, float *tx, float *ty, uint32_t *ts, int *scan_tmp)
 {
-    constexpr int PER = (OSS_MAX_TRI + 255) / 256; // 39
+    constexpr int PER = (OSS_MAX_TRI + FOCAS_NT - 1) / FOCAS_NT; // 10
     const int t0 = threadIdx.x * PER;
     unsigned long long keep = 0;
     int cnt = 0;
@@ -90,7 +92,7 @@ __device__ int build_triangle_list(const int *xy, int n, float *tx, float *ty, u
         float x, y; uint32_t s;
         if (t < OSS_MAX_TRI && make_triangle(xy, n, d_tri_ijk[t], &x, &y, &s)) { keep |= 1ull << q; cnt++; }
     }
-    // exclusive scan of cnt over 256 threads
+    // exclusive scan of cnt over the block
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     int inc = cnt;
 #pragma unroll
@@ -102,28 +104,29 @@ __device__ int build_triangle_list(const int *xy, int n, float *tx, float *ty, u
     __syncthreads();
     if (threadIdx.x == 0) {
         int run = 0;
-        for (int i = 0; i < 8; i++) { int v = scan_tmp[i]; scan_tmp[i] = run; run += v; }
-        scan_tmp[8] = run;
+        for (int i = 0; i < FOCAS_NW; i++) { int v = scan_tmp[i]; scan_tmp[i] = run; run += v; }
+        scan_tmp[FOCAS_NW] = run;
     }
     __syncthreads();
     int pos = scan_tmp[w] + inc - cnt;
-    const int total = scan_tmp[8];
+    const int total = scan_tmp[FOCAS_NW];
     for (int q = 0; q < PER; q++) {
         if (!((keep >> q) & 1ull)) continue;
         float x, y; uint32_t s;
         make_triangle(xy, n, d_tri_ijk[t0 + q], &x, &y, &s);
-        tx[pos] = x; ty[pos] = y; ts[pos] = s;
+        tx[pos] = x;
+        if (ty) { ty[pos] = y; ts[pos] = s; }
         pos++;
     }
     __syncthreads();
     return total;
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(FOCAS_NT)
 k_build_ref_triangles(const int *__restrict__ xy, const int *__restrict__ nxy, RefTriangles *__restrict__ ref)
 {
     __shared__ int sxy[2 * OSS_NOBJS];
-    __shared__ int tmp[9];
+    __shared__ int tmp[FOCAS_NW + 1];
     const int n = nxy[0];
     if (threadIdx.x < 2 * OSS_NOBJS) {
         int v = threadIdx.x < 2 * n ? xy[threadIdx.x] : 0;
@@ -311,103 +314,226 @@ __device__ int dev_find_transform(int *mi, int *mj, int m, const int *xy1, const
 }
 
 // ---- K7  one CTA per light -------------------------------------------------------------
+// sortTriangles emulation.  The reference's quicksort (focas.cpp:146-210) guards its down-scan
+// with (j > 1) instead of (j > l).  Consequences (verified against the reference's object
+// code on thousands of inputs, see tests/): partitions with l >= 2 sort correctly; the chain
+// of partitions with l == 0 can strand one element at slot 0; every other slot ends sorted.
+// So the final array is  [e*] + sorted(all other elements)  where e* is whatever the l == 0
+// chain leaves in slot 0.  We therefore
+//   (1) replay ONLY the l == 0 chain, each Hoare partition evaluated in parallel from the
+//       ordered lists of up-scan stops (x >= pivot) and down-scan stops (x <= pivot, slot 1
+//       being a forced stop, slot 0 never visited), keeping just the left part it leaves;
+//   (2) sort everything with a bitonic network;
+//   (3) address the result through a view that moves e* to slot 0.
+#define FOCAS_SORT_MAX 16384
 struct FocasSmem {
-    float bx[OSS_MAX_TRI];      // sort keys (x), permuted by the quicksort
-    float by[OSS_MAX_TRI];      // generation order
-    uint32_t bs[OSS_MAX_TRI];   // generation order
-    unsigned short bid[OSS_MAX_TRI]; // payload riding with bx: index into by/bs
+    float kx[FOCAS_SORT_MAX];          // keys
+    unsigned short kid[FOCAS_SORT_MAX]; // payload: generation index of the triangle
+    float by[OSS_MAX_TRI];             // generation order   (aliased by the chain's stop lists)
+    uint32_t bs[OSS_MAX_TRI];          // generation order
     int table[OSS_NOBJS * OSS_NOBJS];
     int matches[3][OSS_MAX_MATCH + 1];
     float a[3 * OSS_MAX_MATCH], b[2 * OSS_MAX_MATCH];
     int xy1[2 * OSS_NOBJS], xy2[2 * OSS_NOBJS];
-    int range[64][2];
-    int tmp[9];
-    int nB;
+    int tmp[FOCAS_NW + 1];
+    int scan[FOCAS_NW + 2];
+    int s, ifinal, e_id, e_pos;
+    int sel[2];
+    int rank[OSS_NOBJS];
+    unsigned short above[OSS_NOBJS];
+    unsigned short afirst[OSS_MAX_TRI], alast[OSS_MAX_TRI]; // vote window per A triangle
 };
 
-__global__ void __launch_bounds__(256)
+__device__ __forceinline__ int block_scan_packed(int v, int *wsum, int *total)
+{
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) wsum[w] = inc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int i = 0; i < FOCAS_NW; i++) { int t = wsum[i]; wsum[i] = run; run += t; }
+        *total = run;
+    }
+    __syncthreads();
+    int r = wsum[w] + inc - v;
+    __syncthreads();
+    return r;
+}
+
+// (1) replay the l == 0 partition chain; returns (in sm.e_id) the triangle stranded at slot 0
+__device__ void focas_left_chain(FocasSmem &sm, int nB)
+{
+    const int tid = threadIdx.x;
+    unsigned short *gpos = reinterpret_cast<unsigned short *>(sm.by); // up-scan stops, ascending
+    unsigned short *hpos = reinterpret_cast<unsigned short *>(sm.bs); // down-scan stops, ascending (read backwards)
+    int r = nB - 1;
+    while (r > 0) {
+        const float v = sm.kx[r];
+        if (r == 1) { // the down-scan cannot move at all: j stays on the pivot
+            if (tid == 0 && sm.kx[0] >= v) {
+                float tx = sm.kx[0]; sm.kx[0] = sm.kx[1]; sm.kx[1] = tx;
+                unsigned short ti = sm.kid[0]; sm.kid[0] = sm.kid[1]; sm.kid[1] = ti;
+            }
+            break;
+        }
+        const int per = (r + FOCAS_NT - 1) / FOCAS_NT, p0 = tid * per, p1 = min(r, p0 + per);
+        int cg = 0, ch = 0;
+        for (int p = p0; p < p1; p++) {
+            float x = sm.kx[p];
+            cg += x >= v;
+            ch += p >= 1 && (x <= v || p == 1);
+        }
+        int total;
+        int ex = block_scan_packed(cg | (ch << 16), sm.scan, &sm.scan[FOCAS_NW + 1]);
+        total = sm.scan[FOCAS_NW + 1];
+        const int nG = total & 0xffff, nH = total >> 16;
+        int g = ex & 0xffff, h = ex >> 16;
+        for (int p = p0; p < p1; p++) {
+            float x = sm.kx[p];
+            if (x >= v) gpos[g++] = (unsigned short)p;
+            if (p >= 1 && (x <= v || p == 1)) hpos[h++] = (unsigned short)p;
+        }
+        __syncthreads();
+        if (tid == 0) { // number of swaps: pairs (k-th up stop, k-th down stop) with g_k < h_k, monotone in k
+            int lo = 0, hi = min(nG, nH);
+            while (lo < hi) {
+                int mid = (lo + hi) >> 1;
+                if (gpos[mid] < hpos[nH - 1 - mid]) lo = mid + 1; else hi = mid;
+            }
+            int ifin = lo < nG ? gpos[lo] : r;            // next up-scan stop in the untouched array ...
+            if (lo >= 1) ifin = min(ifin, (int)hpos[nH - lo]); // ... or the last swapped-in big element
+            sm.s = lo;
+            sm.ifinal = ifin;
+        }
+        __syncthreads();
+        const int s = sm.s;
+        for (int k = tid; k < s; k += FOCAS_NT) { // what the swaps leave in the LEFT part (sources lie right of it)
+            int gp = gpos[k], hp = hpos[nH - 1 - k];
+            sm.kx[gp] = sm.kx[hp];
+            sm.kid[gp] = sm.kid[hp];
+        }
+        r = sm.ifinal - 1;
+        __syncthreads();
+    }
+    __syncthreads();
+    if (tid == 0) sm.e_id = nB > 0 ? sm.kid[0] : -1;
+    __syncthreads();
+}
+
+// (2) bitonic sort of (kx, kid)[0..N), N a power of two, ascending by key
+__device__ void focas_bitonic(FocasSmem &sm, int N)
+{
+    for (int k = 2; k <= N; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = threadIdx.x; t < (N >> 1); t += FOCAS_NT) {
+                int i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), l = i | j;
+                float a = sm.kx[i], b = sm.kx[l];
+                bool asc = (i & k) == 0;
+                if ((a > b) == asc && a != b) {
+                    sm.kx[i] = b; sm.kx[l] = a;
+                    unsigned short t2 = sm.kid[i]; sm.kid[i] = sm.kid[l]; sm.kid[l] = t2;
+                }
+            }
+            __syncthreads();
+        }
+}
+
+__global__ void __launch_bounds__(FOCAS_NT)
 k_focas(const RefTriangles *__restrict__ ref, const int *__restrict__ xy_tgt, const int *__restrict__ nxy_tgt,
-        AlignOut *__restrict__ out, int *__restrict__ valid_total, int *__restrict__ dbg_matches, int *__restrict__ dbg_table)
+        AlignOut *__restrict__ out, int *__restrict__ valid_total, int *__restrict__ dbg_matches, int *__restrict__ dbg_table,
+        long long *__restrict__ dbg_clk)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FocasSmem &sm = *reinterpret_cast<FocasSmem *>(smem_raw);
     const int f = blockIdx.x, tid = threadIdx.x;
     const int n2 = nxy_tgt[f];
+    long long c0 = clock64();
     if (tid < 2 * OSS_NOBJS) {
         sm.xy1[tid] = ref->xy[tid];
         sm.xy2[tid] = tid < 2 * n2 ? xy_tgt[f * 2 * OSS_NOBJS + tid] : 0;
     }
-    for (int i = tid; i < OSS_NOBJS * OSS_NOBJS; i += 256) sm.table[i] = 0;
-    for (int i = tid; i < 3 * (OSS_MAX_MATCH + 1); i += 256) (&sm.matches[0][0])[i] = 0;
+    for (int i = tid; i < OSS_NOBJS * OSS_NOBJS; i += FOCAS_NT) sm.table[i] = 0;
+    for (int i = tid; i < 3 * (OSS_MAX_MATCH + 1); i += FOCAS_NT) (&sm.matches[0][0])[i] = 0;
     __syncthreads();
-    const int nB = build_triangle_list(sm.xy2, n2, sm.bx, sm.by, sm.bs, sm.tmp);
-    for (int i = tid; i < nB; i += 256) sm.bid[i] = (unsigned short)i;
+    // keys only, for the chain replay (by/bs are the chain's scratch)
+    const int nB = build_triangle_list(sm.xy2, n2, sm.kx, nullptr, nullptr, sm.tmp);
+    for (int i = tid; i < nB; i += FOCAS_NT) sm.kid[i] = (unsigned short)i;
     __syncthreads();
-
-    // sortTriangles: literal emulation (one thread; sub-ranges are independent, so the
-    // order in which they are processed does not change the result)
-    if (tid == 0) {
-        float *x = sm.bx;
-        unsigned short *id = sm.bid;
-        int sp = 0;
-        sm.range[sp][0] = 0; sm.range[sp][1] = nB - 1; sp++;
-        while (sp > 0) {
-            sp--;
-            int l = sm.range[sp][0], r = sm.range[sp][1];
-            while (r > l) {
-                float v = x[r];
-                int i = l - 1, j = r;
-                for (;;) {
-                    while (x[++i] < v) {}
-                    while (j > 1 && x[--j] > v) {}
-                    if (i >= j) break;
-                    float tx = x[i]; x[i] = x[j]; x[j] = tx;
-                    unsigned short ti = id[i]; id[i] = id[j]; id[j] = ti;
-                }
-                float tx = x[i]; x[i] = x[r]; x[r] = tx;
-                unsigned short ti = id[i]; id[i] = id[r]; id[r] = ti;
-                // continue with the smaller part, defer the larger one
-                int ll = l, lr = i - 1, rl = i + 1, rr = r;
-                if (lr - ll > rr - rl) {
-                    if (lr > ll) { sm.range[sp][0] = ll; sm.range[sp][1] = lr; sp++; }
-                    l = rl; r = rr;
-                } else {
-                    if (rr > rl) { sm.range[sp][0] = rl; sm.range[sp][1] = rr; sp++; }
-                    l = ll; r = lr;
-                }
-            }
-        }
+    long long c1 = clock64();
+    focas_left_chain(sm, nB);
+    long long c2 = clock64();
+    // full triangle list again (keys were permuted by the replay), then the real sort
+    build_triangle_list(sm.xy2, n2, sm.kx, sm.by, sm.bs, sm.tmp);
+    int N = 2;
+    while (N < nB) N <<= 1;
+    for (int i = tid; i < N; i += FOCAS_NT) {
+        sm.kid[i] = (unsigned short)i;
+        if (i >= nB) sm.kx[i] = INFINITY;
     }
     __syncthreads();
+    if (nB > 1) focas_bitonic(sm, N);
+    // (3) view: F[0] = e*, F[i] = S[i-1] for 1 <= i <= e_pos, F[i] = S[i] beyond
+    if (tid == 0) sm.e_pos = 0;
+    __syncthreads();
+    for (int i = tid; i < nB; i += FOCAS_NT)
+        if (sm.kid[i] == sm.e_id) sm.e_pos = i;
+    __syncthreads();
+    const int e_pos = sm.e_pos;
+    auto F = [&](int i) { return i == 0 ? e_pos : (i <= e_pos ? i - 1 : i); };
+    long long c3 = clock64();
 
-    // vote: one A triangle per thread step (binSearchTriangles + checkTolerance)
+    // ---- vote (binSearchTriangles + checkTolerance, focas.cpp:212-279) ----------------------
+    // phase 1, one A triangle per thread: the reference's bisection decides WHETHER a B triangle
+    // within tolerance is found (its probes never test slots 0 and n-1, so small runs can be
+    // missed) and is replayed literally; the [first,last] window it then widens by linear scans
+    // is the in-tolerance run around `mid` plus one element each side (or slot 0 / n-1 when the
+    // scan runs off the end), which two more bisections over the sorted part give directly.
     const double tol = 0.002, tol2 = 0.002 * 0.002;
     const int nA = ref->n;
-    for (int t = tid; t < nA; t += 256) {
-        const float ax = ref->x[t], ay = ref->y[t];
+    auto in_tol = [&](int i, float ax) { return !(fabs((double)__fsub_rn(sm.kx[F(i)], ax)) > tol); };
+    for (int t = tid; t < nA; t += FOCAS_NT) {
+        const float ax = ref->x[t];
         int lo = 0, hi = nB - 1, mid = 0, guard = 0;
         bool found = false;
         while (!found && hi - lo > 1 && guard++ < 64) {
             mid = (lo + hi) / 2;
-            float bx = sm.bx[mid];
+            float bx = sm.kx[F(mid)];
             if (fabs((double)__fsub_rn(bx, ax)) < tol) found = true;
             else if ((double)ax < (double)bx - tol) hi = mid;
             else if ((double)ax > (double)bx + tol) lo = mid;
         }
-        if (!found) continue;
-        int first, last, i;
-        for (i = mid; i > 0; i--)
-            if (fabs((double)__fsub_rn(sm.bx[i], ax)) > tol) break;
-        first = i;
-        for (i = mid; i < nB - 1; i++)
-            if (fabs((double)__fsub_rn(sm.bx[i], ax)) > tol) break;
-        last = i;
+        int first = 2, last = 1;
+        if (found) {
+            int a = 1, b = mid; // smallest in-tolerance slot p in [1, mid]; first = p - 1
+            while (a < b) { int m = (a + b) >> 1; if (in_tol(m, ax)) b = m; else a = m + 1; }
+            first = a - 1;
+            a = mid; b = nB - 2; // largest in-tolerance slot q in [mid, n-2]; last = q + 1
+            if (b < a) b = a;
+            while (a < b) { int m = (a + b + 1) >> 1; if (in_tol(m, ax)) a = m; else b = m - 1; }
+            last = mid >= nB - 1 ? mid : a + 1;
+        }
+        sm.afirst[t] = (unsigned short)first;
+        sm.alast[t] = (unsigned short)last;
+    }
+    __syncthreads();
+    // phase 2, one A triangle per warp, lanes across its window
+    for (int t = tid >> 5; t < nA; t += FOCAS_NW) {
+        const int first = sm.afirst[t], last = sm.alast[t];
+        if (first > last) continue;
+        const float ax = ref->x[t], ay = ref->y[t];
         const uint32_t as = ref->s[t];
-        for (i = first; i <= last; i++) {
-            int id = sm.bid[i];
+        for (int i = first + (tid & 31); i <= last; i += 32) {
+            const int fi = F(i);
+            int id = sm.kid[fi];
             float dy = __fsub_rn(ay, sm.by[id]);
-            if ((double)dy < tol) {
-                float dx = __fsub_rn(ax, sm.bx[i]);
+            if ((double)dy < tol) { // signed test, focas.cpp:261
+                float dx = __fsub_rn(ax, sm.kx[fi]);
                 float d2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
                 if ((double)d2 < tol2) {
                     uint32_t bs = sm.bs[id];
@@ -419,39 +545,96 @@ k_focas(const RefTriangles *__restrict__ ref, const int *__restrict__ xy_tgt, co
         }
     }
     __syncthreads();
+    long long c4 = clock64();
+
+    // ---- selection (focas.cpp:107-139) --------------------------------------------------------
+    // The reference's running insertion keeps, of all voted pairs in row-major scan order, the
+    // list sorted by votes (descending, stable), cut after the 40th entry plus its ties, never
+    // longer than 120.  Same list, computed by ranking: T = 40th largest vote count; pairs above
+    // T are ranked by counting, pairs equal to T by their scan-order prefix.
+    {
+        constexpr int NT = OSS_NOBJS * OSS_NOBJS, PER = (NT + FOCAS_NT - 1) / FOCAS_NT; // table slots per thread
+        const int e0 = tid * PER, e1 = min(NT, e0 + PER);
+        int nz = 0, mx = 0;
+        for (int e = e0; e < e1; e++) { int n = sm.table[e]; nz += n > 0; mx = max(mx, n); }
+        int tot;
+        block_scan_packed(nz, sm.scan, &sm.scan[FOCAS_NW + 1]);
+        tot = sm.scan[FOCAS_NW + 1];
+        if (tid == 0) sm.sel[0] = 0;
+        __syncthreads();
+        atomicMax(&sm.sel[0], mx);
+        __syncthreads();
+        const int maxn = sm.sel[0];
+        int T = 0; // all voted pairs qualify when there are at most 40 of them
+        if (tot > OSS_NOBJS) { // largest v with count(n >= v) >= 40
+            int lo = 1, hi = maxn;
+            while (lo < hi) {
+                int mid = (lo + hi + 1) >> 1, c = 0;
+                for (int e = e0; e < e1; e++) c += sm.table[e] >= mid;
+                block_scan_packed(c, sm.scan, &sm.scan[FOCAS_NW + 1]);
+                if (sm.scan[FOCAS_NW + 1] >= OSS_NOBJS) lo = mid; else hi = mid - 1;
+                __syncthreads();
+            }
+            T = lo;
+        }
+        int cAbove = 0, cTie = 0;
+        for (int e = e0; e < e1; e++) { int n = sm.table[e]; cAbove += n > T; cTie += (T > 0 && n == T); }
+        int ex = block_scan_packed(cAbove | (cTie << 16), sm.scan, &sm.scan[FOCAS_NW + 1]);
+        const int c1 = sm.scan[FOCAS_NW + 1] & 0xffff, cT = sm.scan[FOCAS_NW + 1] >> 16;
+        const int k = min(c1 + cT, OSS_MAX_MATCH);
+        // pairs above T: compact (any order), then rank each by counting over the whole table
+        int ia = ex & 0xffff, it = ex >> 16;
+        for (int e = e0; e < e1; e++) {
+            int n = sm.table[e];
+            if (n > T) sm.above[ia++] = (unsigned short)e;
+            else if (T > 0 && n == T) {
+                int rank = c1 + it++;
+                if (rank < k) { sm.matches[0][rank] = e / OSS_NOBJS; sm.matches[1][rank] = e % OSS_NOBJS; sm.matches[2][rank] = n; }
+            }
+        }
+        if (tid < OSS_NOBJS) sm.rank[tid] = 0;
+        __syncthreads();
+        { // thread -> (pair a, slice sl of the table): 6 slices of 267 slots for up to 40 pairs
+            const int a = tid / 6, sl = tid % 6;
+            if (a < c1 && tid < 240) {
+                const int e = sm.above[a], n = sm.table[e];
+                int r = 0;
+                for (int q = sl * 267; q < min(NT, sl * 267 + 267); q++) {
+                    int m = sm.table[q];
+                    r += (m > n) || (m == n && q < e);
+                }
+                atomicAdd(&sm.rank[a], r);
+            }
+        }
+        __syncthreads();
+        if (tid < c1) {
+            const int e = sm.above[tid], r = sm.rank[tid];
+            sm.matches[0][r] = e / OSS_NOBJS; sm.matches[1][r] = e % OSS_NOBJS; sm.matches[2][r] = sm.table[e];
+        }
+        if (tid == 0) sm.sel[1] = k;
+        __syncthreads();
+    }
 
     if (tid == 0) {
-        // focas.cpp:107-139: the 40 best-voted pairs plus ties with the 40th (stable, row-major scan)
-        const int N = OSS_NOBJS;
-        int *mi = sm.matches[0], *mj = sm.matches[1], *mn = sm.matches[2];
-        int k = 0;
-        for (int i = 0; i < N; i++)
-            for (int j = 0; j < N; j++) {
-                int n = sm.table[i * N + j];
-                if (n <= 0) continue;
-                bool grow = k < N;
-                if (!grow && n < mn[N - 1]) continue;
-                int l;
-                for (l = k; l > 0 && n > mn[l - 1]; l--) { mi[l] = mi[l - 1]; mj[l] = mj[l - 1]; mn[l] = mn[l - 1]; }
-                mi[l] = i; mj[l] = j; mn[l] = n;
-                if (grow) k++;
-                else {
-                    int lim = k < OSS_MAX_MATCH ? k + 1 : k;
-                    int nth = mn[N - 1];
-                    for (k = N; k < lim && nth == mn[k]; k++) {}
-                }
-            }
+        const int k = sm.sel[1];
+        int *mi = sm.matches[0], *mj = sm.matches[1];
         if (dbg_matches)
             for (int r = 0; r < 3; r++)
                 for (int i = 0; i < OSS_MAX_MATCH; i++) dbg_matches[(f * 3 + r) * OSS_MAX_MATCH + i] = sm.matches[r][i];
+        long long c5 = clock64();
         AlignOut o;
         o.k = k;
         o.err = dev_find_transform(mi, mj, k, sm.xy1, sm.xy2, sm.a, sm.b, o.M);
         out[f] = o;
         if (valid_total && o.err == 0) atomicAdd(valid_total, 1);
+        if (dbg_clk) {
+            long long c6 = clock64();
+            dbg_clk[0] = c1 - c0; dbg_clk[1] = c2 - c1; dbg_clk[2] = c3 - c2; dbg_clk[3] = c4 - c3; dbg_clk[4] = c5 - c4;
+            dbg_clk[5] = c6 - c5; dbg_clk[6] = nB; dbg_clk[7] = e_pos;
+        }
     }
     if (dbg_table)
-        for (int i = tid; i < OSS_NOBJS * OSS_NOBJS; i += 256) dbg_table[f * OSS_NOBJS * OSS_NOBJS + i] = sm.table[i];
+        for (int i = tid; i < OSS_NOBJS * OSS_NOBJS; i += FOCAS_NT) dbg_table[f * OSS_NOBJS * OSS_NOBJS + i] = sm.table[i];
 }
 
 }  // namespace oss

@@ -81,6 +81,7 @@ struct oss_ctx {
     RefTriangles *d_ref = nullptr, *d_ref_tmp = nullptr;
     int *d_xy = nullptr, *d_nxy = nullptr; // [slots + 1] star lists for alignment (last = reference)
     int *d_dbg_matches = nullptr, *d_dbg_table = nullptr;
+    long long *d_dbg_clk = nullptr;
     float *d_M = nullptr, *d_flat_ratio = nullptr;
     double *d_flat_partial = nullptr;
     unsigned char *raw_stage[2] = {nullptr, nullptr};
@@ -373,7 +374,7 @@ int oss_set_geometry(oss_ctx *c, int W, int H, int C, int sample, int slots)
     DA(c->d_valid, 4);
     DA(c->d_ref, 1); DA(c->d_ref_tmp, 1);
     DA(c->d_xy, (slots + 1) * 2 * OSS_NOBJS); DA(c->d_nxy, slots + 1);
-    DA(c->d_dbg_matches, 3 * OSS_MAX_MATCH); DA(c->d_dbg_table, OSS_NOBJS * OSS_NOBJS);
+    DA(c->d_dbg_matches, 3 * OSS_MAX_MATCH); DA(c->d_dbg_table, OSS_NOBJS * OSS_NOBJS); DA(c->d_dbg_clk, 8);
     DA(c->d_M, 8); DA(c->d_flat_ratio, 4); DA(c->d_flat_partial, 1024);
     for (int i = 0; i < 2; i++) {
         DA(c->raw_stage[i], (size_t)slots * c->stage_stride);
@@ -642,7 +643,7 @@ int oss_set_reference(oss_ctx *c, const void *frame, int mem, int threshold)
     LAUNCH("copy_reference", k_copy_f32, (unsigned)((PC + 1023) / 1024), 256, 0, w.cal, c->ref_cal, PC);
     int *xy_ref = c->d_xy + c->slots * 2 * OSS_NOBJS, *nxy_ref = c->d_nxy + c->slots;
     LAUNCH("pack_xy", k_pack_xy, 1, OSS_NOBJS, 0, w.star_out, w.ds, g.cap, xy_ref, nxy_ref);
-    LAUNCH("build_ref_triangles", k_build_ref_triangles, 1, 256, 0, xy_ref, nxy_ref, c->d_ref);
+    LAUNCH("build_ref_triangles", k_build_ref_triangles, 1, FOCAS_NT, 0, xy_ref, nxy_ref, c->d_ref);
     DetectState d;
     CK(cudaMemcpyAsync(&d, w.ds, sizeof d, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
@@ -687,8 +688,8 @@ int oss_add_lights(oss_ctx *c, const void *const *frames, int n, int mem)
         rc = run_detect(c, fp, nb, true, c->threshold, set);
         if (rc) return rc;
         LAUNCH("pack_xy", k_pack_xy, nb, OSS_NOBJS, 0, w.star_out, w.ds, g.cap, c->d_xy, c->d_nxy);
-        LAUNCH("focas_match_fit", k_focas, nb, 256, sizeof(FocasSmem), c->d_ref, c->d_xy, c->d_nxy, w.align, c->d_valid,
-               (int *)nullptr, (int *)nullptr);
+        LAUNCH("focas_match_fit", k_focas, nb, FOCAS_NT, sizeof(FocasSmem), c->d_ref, c->d_xy, c->d_nxy, w.align, c->d_valid,
+               (int *)nullptr, (int *)nullptr, (long long *)nullptr);
         if (g.C == 3) {
             LAUNCH("warp_accumulate", k_warp_accumulate<3>, dim3((g.W + 31) / 32, (g.H + 7) / 8), dim3(32, 8), 0, w.cal, w.stridePC,
                    w.align, nb, c->sum, g.W, g.H);
@@ -842,9 +843,9 @@ int oss_align_lists(oss_ctx *c, const int32_t *xy1, int n1, const int32_t *xy2, 
     if (m2) CK(cudaMemcpyAsync(c->d_xy, xy2, sizeof(int) * 2 * m2, cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(nxy_ref, &m1, sizeof(int), cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(c->d_nxy, &m2, sizeof(int), cudaMemcpyHostToDevice, c->stream));
-    LAUNCH("build_ref_triangles", k_build_ref_triangles, 1, 256, 0, xy_ref, nxy_ref, c->d_ref_tmp);
-    LAUNCH("focas_match_fit", k_focas, 1, 256, sizeof(FocasSmem), c->d_ref_tmp, c->d_xy, c->d_nxy, c->ws.align, (int *)nullptr,
-           c->d_dbg_matches, c->d_dbg_table);
+    LAUNCH("build_ref_triangles", k_build_ref_triangles, 1, FOCAS_NT, 0, xy_ref, nxy_ref, c->d_ref_tmp);
+    LAUNCH("focas_match_fit", k_focas, 1, FOCAS_NT, sizeof(FocasSmem), c->d_ref_tmp, c->d_xy, c->d_nxy, c->ws.align, (int *)nullptr,
+           c->d_dbg_matches, c->d_dbg_table, c->d_dbg_clk);
     AlignOut o;
     CK(cudaMemcpyAsync(&o, c->ws.align, sizeof o, cudaMemcpyDeviceToHost, c->stream));
     if (matches_out) CK(cudaMemcpyAsync(matches_out, c->d_dbg_matches, sizeof(int) * 3 * OSS_MAX_MATCH, cudaMemcpyDeviceToHost, c->stream));
@@ -852,6 +853,12 @@ int oss_align_lists(oss_ctx *c, const int32_t *xy1, int n1, const int32_t *xy2, 
     CK(cudaMemcpyAsync(xy_ref, keep.data(), sizeof(int) * 2 * OSS_NOBJS, cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(nxy_ref, keep.data() + 2 * OSS_NOBJS, sizeof(int), cudaMemcpyHostToDevice, c->stream));
     CK(cudaStreamSynchronize(c->stream));
+    if (getenv("OSS_B200_FOCAS_CLK")) {
+        long long clk[8];
+        cudaMemcpy(clk, c->d_dbg_clk, sizeof clk, cudaMemcpyDeviceToHost);
+        fprintf(stderr, "focas clocks: tri %lld chain %lld rebuild+sort %lld vote %lld select %lld fit %lld (nB %lld e_pos %lld)\n",
+                clk[0], clk[1], clk[2], clk[3], clk[4], clk[5], clk[6], clk[7]);
+    }
     if (k) *k = o.k;
     if (err) *err = o.err;
     if (M) memcpy(M, o.M, sizeof o.M);
