@@ -94,93 +94,148 @@ static const uint32_t kGaussBits[16] = {
     0x3d88bfb5u, 0x3d972180u, 0x3da079edu, 0x3da3b7d6u};
 
 // ---------------------------------------------------------------------------------------
-// K3  sky_sub_stats.  One CTA produces a 64x64 tile of stars = gray - sky:
-//   phase 1  upsample the median grid (resize taps) over the tile + 15 px apron, with the
-//            Gaussian's BORDER_REFLECT_101 applied to the FULL-RES coordinates;
-//   phase 2  31-tap row filter, taps accumulated k = 0..30 in order;
-//   phase 3  column filter as centre + 15 symmetric pairs; subtract from gray; write;
-//            fp64 sum / sum-of-squares over the statistics ROI; per-32-px-segment maximum
-//            (lets the thresholding pass skip empty segments).
-// HBM traffic: gray read once (4 B/px), stars written once (4 B/px).  The arithmetic
-// (about 110 non-fusable fp32 ops per pixel) makes this kernel ALU-bound, not HBM-bound.
-#define SKY_T 64
+// K3  sky_sub_stats.  One CTA produces a 64 x 128 tile of stars = gray - sky:
+//   phase 1  upsample the median grid over the tile + 15 px apron (horizontal lerp of the few
+//            low-res rows the tile touches, then vertical lerp), with the Gaussian's
+//            BORDER_REFLECT_101 applied to the FULL-RES coordinates;
+//   phase 2  31-tap row filter, taps accumulated k = 0..30 in order; each thread makes 4
+//            neighbouring outputs from one 36-float register window (9 LDS.128);
+//   phase 3  column filter as centre + 15 symmetric pairs, 4 vertically adjacent outputs per
+//            thread from a 34-float window; subtract from gray; write; fp64 sum / sum of
+//            squares over the statistics ROI; per-32-px-segment maximum (lets the
+//            thresholding pass skip empty segments).
+// HBM traffic: gray read once (4 B/px), stars written once (4 B/px).  About 120 non-fusable
+// fp32 operations per pixel make this kernel FP32-pipe bound, not HBM bound; the register
+// windows keep shared-memory traffic (22 words/px) below the FP32 time.
+#define SKY_TX 64
+#define SKY_TY 128
 #define SKY_R 15
-#define SKY_A (SKY_T + 2 * SKY_R) // 94
-#define SKY_UP_LD 96
-constexpr int kSkySmemBytes = (SKY_A * SKY_UP_LD + SKY_A * SKY_T) * 4 + 2 * SKY_A * (int)sizeof(ResizeTap);
+#define SKY_AX (SKY_TX + 2 * SKY_R) // 94 columns of apron
+#define SKY_AY (SKY_TY + 2 * SKY_R) // 158 rows of apron
+#define SKY_UP_LD 100               // 36-float windows starting at 4*gx stay inside the row
+#define SKY_HROWS 40                // low-res rows a tile may touch (158/8 + reflections)
+constexpr int kSkySmemBytes = (SKY_AY * SKY_UP_LD + SKY_AY * SKY_TX) * 4 + (SKY_AX + SKY_AY) * (int)sizeof(ResizeTap);
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 k_sky_sub_stats(const float *__restrict__ gray, long long strideGray, const float *__restrict__ med,
                 long long strideLo, int lw, const ResizeTap *__restrict__ ux, const ResizeTap *__restrict__ uy,
                 float *__restrict__ stars, long long strideStars, float *__restrict__ segmax, long long strideSeg,
                 int nseg, double *__restrict__ partials, long long stridePart, Geom g)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float *up = (float *)smem_raw;              // [SKY_A][SKY_UP_LD]
-    float *rf = up + SKY_A * SKY_UP_LD;         // [SKY_A][SKY_T]
-    ResizeTap *tcol = (ResizeTap *)(rf + SKY_A * SKY_T); // [SKY_A]
-    ResizeTap *trow = tcol + SKY_A;             // [SKY_A]
+    float *up = (float *)smem_raw;                  // [SKY_AY][SKY_UP_LD]
+    float *rf = up + SKY_AY * SKY_UP_LD;            // [SKY_AY][SKY_TX]
+    float *hrow = rf;                               // [SKY_HROWS][SKY_UP_LD], dead before phase 2 writes rf
+    ResizeTap *tcol = (ResizeTap *)(rf + SKY_AY * SKY_TX); // [SKY_AX]
+    ResizeTap *trow = tcol + SKY_AX;                // [SKY_AY]
+    __shared__ int lr_min, lr_max;
 
     const int tid = threadIdx.x;
-    const int x0 = blockIdx.x * SKY_T, y0 = blockIdx.y * SKY_T, f = blockIdx.z;
+    const int x0 = blockIdx.x * SKY_TX, y0 = blockIdx.y * SKY_TY, f = blockIdx.z;
     const float *L = med + f * strideLo;
 
-    for (int i = tid; i < 2 * SKY_A; i += 256) {
-        if (i < SKY_A) tcol[i] = ux[reflect101(x0 - SKY_R + i, g.W)];
-        else trow[i - SKY_A] = uy[reflect101(y0 - SKY_R + (i - SKY_A), g.H)];
+    if (tid == 0) { lr_min = 1 << 30; lr_max = -1; }
+    __syncthreads();
+    for (int i = tid; i < SKY_AX + SKY_AY; i += 256) {
+        if (i < SKY_AX) tcol[i] = ux[reflect101(x0 - SKY_R + i, g.W)];
+        else {
+            ResizeTap t = uy[reflect101(y0 - SKY_R + (i - SKY_AX), g.H)];
+            trow[i - SKY_AX] = t;
+            atomicMin(&lr_min, t.i0);
+            atomicMax(&lr_max, t.i1);
+        }
+    }
+    __syncthreads();
+    const int r_lo = lr_min, nlr = lr_max - lr_min + 1;
+
+    // phase 1
+    if (nlr <= SKY_HROWS) {
+        for (int i = tid; i < nlr * SKY_AX; i += 256) {
+            int lr = i / SKY_AX, c = i - lr * SKY_AX;
+            ResizeTap a = tcol[c];
+            const float *row = L + (long long)(r_lo + lr) * lw;
+            hrow[lr * SKY_UP_LD + c] = lerp2(__ldg(row + a.i0), a.w0, __ldg(row + a.i1), a.w1);
+        }
+        __syncthreads();
+        for (int i = tid; i < SKY_AY * SKY_AX; i += 256) {
+            int r = i / SKY_AX, c = i - r * SKY_AX;
+            ResizeTap b = trow[r];
+            up[r * SKY_UP_LD + c] = lerp2(hrow[(b.i0 - r_lo) * SKY_UP_LD + c], b.w0, hrow[(b.i1 - r_lo) * SKY_UP_LD + c], b.w1);
+        }
+    } else { // pathological geometry (tiny low-res grid folded many times): direct evaluation
+        for (int i = tid; i < SKY_AY * SKY_AX; i += 256) {
+            int r = i / SKY_AX, c = i - r * SKY_AX;
+            ResizeTap a = tcol[c], b = trow[r];
+            const float *r0 = L + (long long)b.i0 * lw, *r1 = L + (long long)b.i1 * lw;
+            float h0 = lerp2(__ldg(r0 + a.i0), a.w0, __ldg(r0 + a.i1), a.w1);
+            float h1 = lerp2(__ldg(r1 + a.i0), a.w0, __ldg(r1 + a.i1), a.w1);
+            up[r * SKY_UP_LD + c] = lerp2(h0, b.w0, h1, b.w1);
+        }
     }
     __syncthreads();
 
-    // phase 1: up[r][c] = resize(med)(reflect(y0-15+r), reflect(x0-15+c))
-    for (int i = tid; i < SKY_A * SKY_A; i += 256) {
-        int r = i / SKY_A, c = i - r * SKY_A;
-        ResizeTap a = tcol[c], b = trow[r];
-        const float *r0 = L + (long long)b.i0 * lw, *r1 = L + (long long)b.i1 * lw;
-        float h0 = lerp2(__ldg(r0 + a.i0), a.w0, __ldg(r0 + a.i1), a.w1);
-        float h1 = lerp2(__ldg(r1 + a.i0), a.w0, __ldg(r1 + a.i1), a.w1);
-        up[r * SKY_UP_LD + c] = lerp2(h0, b.w0, h1, b.w1);
-    }
-    __syncthreads();
-
-    // phase 2: row filter
-    for (int i = tid; i < SKY_A * SKY_T; i += 256) {
-        int r = i >> 6, c = i & 63;
-        const float *u = up + r * SKY_UP_LD + c;
-        float s = __fmul_rn(c_gauss[0], u[0]);
+    // phase 2: rf[r][4gx .. 4gx+3] from up[r][4gx .. 4gx+33]
+    for (int i = tid; i < SKY_AY * (SKY_TX / 4); i += 256) {
+        const int r = i >> 4, gx = i & 15;
+        const float4 *src = (const float4 *)(up + r * SKY_UP_LD + 4 * gx);
+        float w[36];
 #pragma unroll
-        for (int j = 1; j < 31; j++) s = __fadd_rn(s, __fmul_rn(c_gauss[j], u[j]));
-        rf[i] = s;
+        for (int q = 0; q < 9; q++) { float4 v = src[q]; w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w; }
+        float o[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            float s = __fmul_rn(c_gauss[0], w[e]);
+#pragma unroll
+            for (int j = 1; j < 31; j++) s = __fadd_rn(s, __fmul_rn(c_gauss[j], w[e + j]));
+            o[e] = s;
+        }
+        ((float4 *)(rf + r * SKY_TX + 4 * gx))[0] = make_float4(o[0], o[1], o[2], o[3]);
     }
     __syncthreads();
 
-    // phase 3: column filter, subtract, statistics
+    // phase 3: out[4gy .. 4gy+3][c] from rf[4gy .. 4gy+33][c]
     double sum = 0.0, sq = 0.0;
     const float *G = gray + f * strideGray;
     float *S = stars + f * strideStars;
-    for (int i = tid; i < SKY_T * SKY_T; i += 256) {
-        int r = i >> 6, c = i & 63;
-        const float *q = rf + (r + SKY_R) * SKY_T + c;
-        float s = __fmul_rn(c_gauss[15], q[0]);
+    for (int i = tid; i < (SKY_TY / 4) * SKY_TX; i += 256) {
+        const int gy = i >> 6, c = i & 63;
+        const int x = x0 + c;
+        // gray first: its HBM latency hides behind the window loads and ~190 fp32 operations
+        float gv[4];
 #pragma unroll
-        for (int j = 1; j <= 15; j++)
-            s = __fadd_rn(s, __fmul_rn(c_gauss[15 + j], __fadd_rn(q[j * SKY_T], q[-j * SKY_T])));
-        int x = x0 + c, y = y0 + r;
-        float v = -INFINITY;
-        if (x < g.W && y < g.H) {
-            long long p = (long long)y * g.W + x;
-            v = __fsub_rn(__ldg(G + p), s);
-            S[p] = v;
-            if (x >= g.roi_x && x < g.roi_x + g.roi_w && y >= g.roi_y && y < g.roi_y + g.roi_h) {
-                double d = (double)v;
-                sum += d;
-                sq += d * d;
+        for (int e = 0; e < 4; e++) {
+            const int y = y0 + 4 * gy + e;
+            gv[e] = (x < g.W && y < g.H) ? __ldg(G + (long long)y * g.W + x) : 0.f;
+        }
+        const float *q = rf + (4 * gy) * SKY_TX + c;
+        float w[34];
+#pragma unroll
+        for (int j = 0; j < 34; j++) w[j] = q[j * SKY_TX];
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            float s = __fmul_rn(c_gauss[15], w[e + 15]);
+#pragma unroll
+            for (int j = 1; j <= 15; j++) s = __fadd_rn(s, __fmul_rn(c_gauss[15 + j], __fadd_rn(w[e + 15 + j], w[e + 15 - j])));
+            const int y = y0 + 4 * gy + e;
+            float v = -INFINITY;
+            if (x < g.W && y < g.H) {
+                v = __fsub_rn(gv[e], s);
+                S[(long long)y * g.W + x] = v;
+                if (x >= g.roi_x && x < g.roi_x + g.roi_w && y >= g.roi_y && y < g.roi_y + g.roi_h) {
+                    double d = (double)v;
+                    sum += d;
+                    sq += d * d;
+                }
+            }
+            // warp maximum through one REDUX on an order-preserving integer image of the float
+            unsigned key = __float_as_uint(v);
+            key ^= (unsigned)((int)key >> 31) | 0x80000000u;
+            key = __reduce_max_sync(0xffffffffu, key);
+            if ((tid & 31) == 0 && y < g.H && (x >> 5) < nseg) {
+                key ^= (key & 0x80000000u) ? 0x80000000u : 0xffffffffu;
+                segmax[f * strideSeg + (long long)y * nseg + (x >> 5)] = __uint_as_float(key);
             }
         }
-        float m = v;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-        if ((tid & 31) == 0 && y < g.H && (x >> 5) < nseg)
-            segmax[f * strideSeg + (long long)y * nseg + (x >> 5)] = m;
     }
     // block reduction of the fp64 partial sums, fixed order
     __shared__ double sh[2][8];

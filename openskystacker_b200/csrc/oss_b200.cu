@@ -349,7 +349,7 @@ int oss_set_geometry(oss_ctx *c, int W, int H, int C, int sample, int slots)
     w = Workspace{};
     auto pad64 = [](long long v) { return (v + 63) / 64 * 64; }; // keep every slot 256-byte aligned
     w.strideP = pad64(g.P); w.stridePC = pad64(PC); w.strideLo = lo; w.strideSeg = nsegs;
-    w.stat_blocks = ((W + SKY_T - 1) / SKY_T) * ((H + SKY_T - 1) / SKY_T);
+    w.stat_blocks = ((W + SKY_TX - 1) / SKY_TX) * ((H + SKY_TY - 1) / SKY_TY);
     w.stridePart = 2ll * w.stat_blocks;
     long long scan_max = nsegs + 1 > cap ? nsegs + 1 : cap;
     w.strideScan = (scan_max + SCAN_ITEMS - 1) / SCAN_ITEMS + 1;
@@ -485,7 +485,7 @@ static int run_detect(oss_ctx *c, const FramePtrs &fp, int n, bool use_masters, 
            c->dx, c->dy, w.lo, w.strideLo, g.lw, g.lh);
     LAUNCH("median5", k_median5, dim3((g.lw + 31) / 32, (g.lh + 7) / 8, n), 256, 0, w.lo, w.med, w.strideLo, g.lw, g.lh);
     const long long strideGray = g.C == 3 ? w.strideP : w.stridePC;
-    LAUNCH("sky_sub_stats", k_sky_sub_stats, dim3((g.W + SKY_T - 1) / SKY_T, (g.H + SKY_T - 1) / SKY_T, n), 256, kSkySmemBytes,
+    LAUNCH("sky_sub_stats", k_sky_sub_stats, dim3((g.W + SKY_TX - 1) / SKY_TX, (g.H + SKY_TY - 1) / SKY_TY, n), 256, kSkySmemBytes,
            w.gray, strideGray, w.med, w.strideLo, g.lw, c->ux, c->uy, w.stars, w.strideP, w.segmax, w.strideSeg, g.nseg,
            w.partials, w.stridePart, g);
     LAUNCH("finalize_stats", k_finalize_stats, n, 256, 0, w.partials, w.stridePart, w.stat_blocks, w.ds, threshold, g);
