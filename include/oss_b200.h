@@ -106,6 +106,10 @@ OSS_API int oss_memcpy_d2h(oss_ctx *ctx, void *dst_host, const void *src_dev, si
  * frames_in_flight (>= 1) sizes the batch the engine processes per kernel launch. */
 OSS_API int oss_set_geometry(oss_ctx *ctx, int width, int height, int channels, int sample,
                              int frames_in_flight);
+/* Number of independent pipelines (streams + work spaces) that batches of lights alternate
+ * between, so FP32-bound and HBM-bound kernels of different batches overlap; 1..4, default 2.
+ * The accumulation order stays the frame order.  Takes effect at the next oss_set_geometry. */
+OSS_API int oss_set_pipelines(oss_ctx *ctx, int n);
 
 /* ---- master frames: stackBias / stackDarks / stackDarkFlats / stackFlats, util.cpp:584-722
  * Build order follows ImageStackerPrivate::process (imagestacker.cpp:262-281): bias first,

@@ -63,6 +63,7 @@ _SIGS = {
     "oss_memcpy_h2d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "oss_memcpy_d2h": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "oss_set_geometry": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "oss_set_pipelines": (C.c_int, [C.c_void_p, C.c_int]),
     "oss_build_master": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.c_int, C.c_int]),
     "oss_set_master": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
     "oss_get_master": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
@@ -152,6 +153,9 @@ class Engine:
     def set_geometry(self, width, height, channels, dtype=np.uint16, frames_in_flight=4):
         self._ck(self._L.oss_set_geometry(self._h, width, height, channels, _SAMPLE[np.dtype(dtype)], frames_in_flight))
         self.geom = (height, width, channels, np.dtype(dtype))
+
+    def set_pipelines(self, n):
+        self._ck(self._L.oss_set_pipelines(self._h, n))
 
     def _shape(self):
         h, w, c, _ = self.geom

@@ -60,9 +60,30 @@ static bool nccl_load(std::string *why)
     return true;
 }
 
+// One processing pipeline: its own stream, staging buffers and detection work space.
+// Batches of lights alternate between pipelines so that the FP32-bound kernels of one batch
+// (sky estimation, component walk, alignment) overlap the HBM-bound kernels of another
+// (calibration, warp + accumulate).  Only the accumulator is shared; the warp kernels are
+// chained by events in batch order, which keeps the summation order = frame order.
+#define OSS_MAX_PIPES 4
+struct Pipe {
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    Workspace ws{};
+    int *d_xy = nullptr, *d_nxy = nullptr;
+    unsigned char *raw_stage[2] = {nullptr, nullptr};
+    cudaEvent_t copy_done[2] = {nullptr, nullptr}, raw_free[2] = {nullptr, nullptr};
+    cudaEvent_t warp_done = nullptr;
+    long long batch_counter = 0;
+};
+
 struct oss_ctx {
     int device = 0;
+    // the fields below alias the CURRENT pipeline (select_pipe); all launch helpers use them
     cudaStream_t stream = nullptr, copy_stream = nullptr;
+    Pipe pipes[OSS_MAX_PIPES];
+    int npipes = 3, want_pipes = 3, cur = 0;
+    cudaEvent_t last_warp = nullptr; // warp_done of the most recently queued batch
+    long long light_batches = 0;
     std::string err;
     Geom g{};
     bool has_geom = false;
@@ -118,6 +139,28 @@ static int fail(oss_ctx *c, int code, const char *fmt, ...)
     va_end(ap);
     if (c) c->err = buf;
     return code;
+}
+
+static void select_pipe(oss_ctx *c, int p)
+{
+    Pipe &o = c->pipes[c->cur];
+    o.batch_counter = c->batch_counter;
+    Pipe &n = c->pipes[p];
+    c->cur = p;
+    c->stream = n.stream; c->copy_stream = n.copy_stream;
+    c->ws = n.ws; c->d_xy = n.d_xy; c->d_nxy = n.d_nxy;
+    for (int i = 0; i < 2; i++) { c->raw_stage[i] = n.raw_stage[i]; c->copy_done[i] = n.copy_done[i]; c->raw_free[i] = n.raw_free[i]; }
+    c->batch_counter = n.batch_counter;
+}
+
+static cudaError_t sync_all(oss_ctx *c)
+{
+    cudaError_t e = cudaSuccess;
+    for (int p = 0; p < OSS_MAX_PIPES; p++) {
+        if (c->pipes[p].copy_stream) { cudaError_t r = cudaStreamSynchronize(c->pipes[p].copy_stream); if (r != cudaSuccess) e = r; }
+        if (c->pipes[p].stream) { cudaError_t r = cudaStreamSynchronize(c->pipes[p].stream); if (r != cudaSuccess) e = r; }
+    }
+    return e;
 }
 
 #define CK(call)                                                                                      \
@@ -194,11 +237,20 @@ static void free_geometry(oss_ctx *c)
     for (void *p : c->allocs) cudaFree(p);
     c->allocs.clear();
     for (int i = 0; i < 4; i++) c->master[i] = nullptr;
-    for (int i = 0; i < 2; i++) {
-        c->raw_stage[i] = nullptr;
-        if (c->copy_done[i]) { cudaEventDestroy(c->copy_done[i]); c->copy_done[i] = nullptr; }
-        if (c->raw_free[i]) { cudaEventDestroy(c->raw_free[i]); c->raw_free[i] = nullptr; }
+    for (int p = 0; p < OSS_MAX_PIPES; p++) {
+        Pipe &pp = c->pipes[p];
+        for (int i = 0; i < 2; i++) {
+            pp.raw_stage[i] = nullptr;
+            if (pp.copy_done[i]) { cudaEventDestroy(pp.copy_done[i]); pp.copy_done[i] = nullptr; }
+            if (pp.raw_free[i]) { cudaEventDestroy(pp.raw_free[i]); pp.raw_free[i] = nullptr; }
+        }
+        if (pp.warp_done) { cudaEventDestroy(pp.warp_done); pp.warp_done = nullptr; }
+        pp.ws = Workspace{};
+        pp.d_xy = pp.d_nxy = nullptr;
+        pp.batch_counter = 0;
     }
+    c->last_warp = nullptr;
+    c->light_batches = 0;
     c->has_geom = false;
     c->has_ref = false;
     c->synth_plane = nullptr;
@@ -235,11 +287,17 @@ int oss_create(oss_ctx **out, int device)
     if (device < 0 || device >= ndev) return OSS_E_ARG;
     oss_ctx *c = new oss_ctx();
     c->device = device;
-    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    bool ok = cudaSetDevice(device) == cudaSuccess;
+    for (int p = 0; ok && p < OSS_MAX_PIPES; p++)
+        ok = cudaStreamCreateWithFlags(&c->pipes[p].stream, cudaStreamNonBlocking) == cudaSuccess &&
+             cudaStreamCreateWithFlags(&c->pipes[p].copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+    if (!ok) {
         delete c;
         return OSS_E_CUDA;
     }
+    if (const char *e = getenv("OSS_B200_PIPES")) c->want_pipes = atoi(e);
+    c->stream = c->pipes[0].stream;
+    c->copy_stream = c->pipes[0].copy_stream;
     // constant tables
     float taps[31];
     for (int i = 0; i < 16; i++) { memcpy(&taps[i], &kGaussBits[i], 4); taps[30 - i] = taps[i]; }
@@ -251,7 +309,7 @@ int oss_create(oss_ctx **out, int device)
         cudaMemcpyToSymbol(d_tri_ijk, ijk.data(), ijk.size() * 4) != cudaSuccess ||
         cudaFuncSetAttribute(k_sky_sub_stats, cudaFuncAttributeMaxDynamicSharedMemorySize, kSkySmemBytes) != cudaSuccess ||
         cudaFuncSetAttribute(k_focas, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FocasSmem)) != cudaSuccess) {
-        cudaStreamDestroy(c->stream); cudaStreamDestroy(c->copy_stream);
+        for (int p = 0; p < OSS_MAX_PIPES; p++) { cudaStreamDestroy(c->pipes[p].stream); cudaStreamDestroy(c->pipes[p].copy_stream); }
         delete c;
         return OSS_E_CUDA;
     }
@@ -271,8 +329,7 @@ void oss_destroy(oss_ctx *c)
     for (auto p : c->h_al_chunks) cudaFreeHost(p);
     prof_flush(c);
     for (auto e : c->event_pool) cudaEventDestroy(e);
-    cudaStreamDestroy(c->stream);
-    cudaStreamDestroy(c->copy_stream);
+    for (int p = 0; p < OSS_MAX_PIPES; p++) { cudaStreamDestroy(c->pipes[p].stream); cudaStreamDestroy(c->pipes[p].copy_stream); }
     delete c;
 }
 
@@ -345,42 +402,51 @@ int oss_set_geometry(oss_ctx *c, int W, int H, int C, int sample, int slots)
     c->frame_bytes = (size_t)g.P * C * ssz;
     c->stage_stride = (c->frame_bytes + 255) / 256 * 256;
     const long long PC = g.P * C, nsegs = (long long)H * g.nseg, lo = (long long)g.lw * g.lh;
-    Workspace &w = c->ws;
-    w = Workspace{};
+    c->npipes = c->want_pipes < 1 ? 1 : (c->want_pipes > OSS_MAX_PIPES ? OSS_MAX_PIPES : c->want_pipes);
     auto pad64 = [](long long v) { return (v + 63) / 64 * 64; }; // keep every slot 256-byte aligned
-    w.strideP = pad64(g.P); w.stridePC = pad64(PC); w.strideLo = lo; w.strideSeg = nsegs;
-    w.stat_blocks = ((W + SKY_TX - 1) / SKY_TX) * ((H + SKY_TY - 1) / SKY_TY);
-    w.stridePart = 2ll * w.stat_blocks;
-    long long scan_max = nsegs + 1 > cap ? nsegs + 1 : cap;
-    w.strideScan = (scan_max + SCAN_ITEMS - 1) / SCAN_ITEMS + 1;
-    DA(w.cal, slots * w.stridePC);
-    if (C == 3) { DA(w.gray, slots * w.strideP); } else w.gray = w.cal;
-    DA(w.stars, slots * w.strideP);
-    DA(w.lo, slots * lo); DA(w.med, slots * lo);
-    DA(w.segmax, slots * nsegs); DA(w.segmask, slots * nsegs); DA(w.segoff, slots * (nsegs + 1));
-    DA(w.partials, slots * w.stridePart);
-    DA(w.ds, slots);
-    DA(w.cand_idx, slots * cap); DA(w.cand_val, slots * cap); DA(w.nbr, slots * cap); DA(w.parent, slots * cap);
-    DA(w.owner, slots * cap); DA(w.comp_size, slots * cap); DA(w.comp_peak, slots * cap);
-    DA(w.flag, slots * cap); DA(w.flagscan, slots * cap);
-    DA(w.comp_root, slots * cap); DA(w.comp_off, slots * cap); DA(w.comp_nstar, slots * cap);
-    DA(w.comp_staroff, slots * cap);
-    DA(w.scratch, 12ll * slots * cap);
-    DA(w.star_tmp, slots * cap); DA(w.star_out, slots * cap);
-    DA(w.blocksum, slots * w.strideScan);
-    DA(w.align, slots);
+    for (int pi = 0; pi < c->npipes; pi++) {
+        Pipe &pp = c->pipes[pi];
+        Workspace &w = pp.ws;
+        w = Workspace{};
+        w.strideP = pad64(g.P); w.stridePC = pad64(PC); w.strideLo = lo; w.strideSeg = nsegs;
+        w.stat_blocks = ((W + SKY_TX - 1) / SKY_TX) * ((H + SKY_TY - 1) / SKY_TY);
+        w.stridePart = 2ll * w.stat_blocks;
+        long long scan_max = nsegs + 1 > cap ? nsegs + 1 : cap;
+        w.strideScan = (scan_max + SCAN_ITEMS - 1) / SCAN_ITEMS + 1;
+        DA(w.cal, slots * w.stridePC);
+        if (C == 3) { DA(w.gray, slots * w.strideP); } else w.gray = w.cal;
+        DA(w.stars, slots * w.strideP);
+        DA(w.lo, slots * lo); DA(w.med, slots * lo);
+        DA(w.segmax, slots * nsegs); DA(w.segmask, slots * nsegs); DA(w.segoff, slots * (nsegs + 1));
+        DA(w.partials, slots * w.stridePart);
+        DA(w.ds, slots);
+        DA(w.cand_idx, slots * cap); DA(w.cand_val, slots * cap); DA(w.nbr, slots * cap); DA(w.parent, slots * cap);
+        DA(w.owner, slots * cap); DA(w.comp_size, slots * cap); DA(w.comp_peak, slots * cap);
+        DA(w.flag, slots * cap); DA(w.flagscan, slots * cap);
+        DA(w.comp_root, slots * cap); DA(w.comp_off, slots * cap); DA(w.comp_nstar, slots * cap);
+        DA(w.comp_staroff, slots * cap);
+        DA(w.scratch, 12ll * slots * cap);
+        DA(w.star_tmp, slots * cap); DA(w.star_out, slots * cap);
+        DA(w.blocksum, slots * w.strideScan);
+        DA(w.align, slots);
+        DA(pp.d_xy, (slots + 1) * 2 * OSS_NOBJS); DA(pp.d_nxy, slots + 1);
+        for (int i = 0; i < 2; i++) {
+            DA(pp.raw_stage[i], (size_t)slots * c->stage_stride);
+            CK(cudaEventCreateWithFlags(&pp.copy_done[i], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&pp.raw_free[i], cudaEventDisableTiming));
+        }
+        CK(cudaEventCreateWithFlags(&pp.warp_done, cudaEventDisableTiming));
+        pp.batch_counter = 0;
+    }
+    c->cur = 0;
+    c->batch_counter = 0;
+    select_pipe(c, 0);
     DA(c->dx, g.lw); DA(c->dy, g.lh); DA(c->ux, W); DA(c->uy, H);
     DA(c->sum, PC); DA(c->ref_cal, PC); DA(c->result, PC);
     DA(c->d_valid, 4);
     DA(c->d_ref, 1); DA(c->d_ref_tmp, 1);
-    DA(c->d_xy, (slots + 1) * 2 * OSS_NOBJS); DA(c->d_nxy, slots + 1);
     DA(c->d_dbg_matches, 3 * OSS_MAX_MATCH); DA(c->d_dbg_table, OSS_NOBJS * OSS_NOBJS); DA(c->d_dbg_clk, 8);
     DA(c->d_M, 8); DA(c->d_flat_ratio, 4); DA(c->d_flat_partial, 1024);
-    for (int i = 0; i < 2; i++) {
-        DA(c->raw_stage[i], (size_t)slots * c->stage_stride);
-        CK(cudaEventCreateWithFlags(&c->copy_done[i], cudaEventDisableTiming));
-        CK(cudaEventCreateWithFlags(&c->raw_free[i], cudaEventDisableTiming));
-    }
     LAUNCH("resize_taps", k_resize_taps, (g.lw + 255) / 256, 256, 0, c->dx, W, g.lw, 1);
     LAUNCH("resize_taps", k_resize_taps, (g.lh + 255) / 256, 256, 0, c->dy, H, g.lh, 0);
     LAUNCH("resize_taps", k_resize_taps, (W + 255) / 256, 256, 0, c->ux, g.lw, W, 1);
@@ -535,13 +601,22 @@ static int need_geom(oss_ctx *c)
     return OSS_OK;
 }
 #define NEED_GEOM() do { int r_ = need_geom(c); if (r_) return r_; } while (0)
+// single-frame / bookkeeping entry points: drain every pipeline, then work on pipeline 0
+#define USE_PIPE0()                                                                            \
+    do {                                                                                       \
+        int r_ = need_geom(c);                                                                 \
+        if (r_) return r_;                                                                     \
+        cudaError_t e_ = sync_all(c);                                                          \
+        if (e_ != cudaSuccess) return fail(c, OSS_E_CUDA, "stream sync failed: %s", cudaGetErrorString(e_)); \
+        select_pipe(c, 0);                                                                     \
+    } while (0)
 
 extern "C" {
 
 // ---- masters ---------------------------------------------------------------------------
 int oss_build_master(oss_ctx *c, int kind, const void *const *frames, int n, int mem)
 {
-    NEED_GEOM();
+    USE_PIPE0();
     if (kind < 0 || kind > 3 || n < 1 || !frames) return fail(c, OSS_E_ARG, "bad master arguments");
     const Geom &g = c->g;
     const long long count = g.P * g.C;
@@ -578,7 +653,7 @@ int oss_build_master(oss_ctx *c, int kind, const void *const *frames, int n, int
 
 int oss_set_master(oss_ctx *c, int kind, const float *data, int mem)
 {
-    NEED_GEOM();
+    USE_PIPE0();
     if (kind < 0 || kind > 3 || !data) return fail(c, OSS_E_ARG, "bad master arguments");
     const long long count = c->g.P * c->g.C;
     if (!c->master[kind]) DA(c->master[kind], count);
@@ -590,7 +665,7 @@ int oss_set_master(oss_ctx *c, int kind, const float *data, int mem)
 
 int oss_get_master(oss_ctx *c, int kind, float *out)
 {
-    NEED_GEOM();
+    USE_PIPE0();
     if (kind < 0 || kind > 3 || !out) return fail(c, OSS_E_ARG, "bad master arguments");
     if (!c->master[kind]) return fail(c, OSS_E_ARG, "master %d is absent", kind);
     return oss_memcpy_d2h(c, out, c->master[kind], (size_t)c->g.P * c->g.C * sizeof(float));
@@ -598,7 +673,7 @@ int oss_get_master(oss_ctx *c, int kind, float *out)
 
 int oss_clear_masters(oss_ctx *c)
 {
-    NEED_GEOM();
+    USE_PIPE0();
     CK(cudaStreamSynchronize(c->stream));
     for (int k = 0; k < 4; k++)
         if (c->master[k]) {
@@ -613,7 +688,7 @@ int oss_clear_masters(oss_ctx *c)
 // ---- stacking --------------------------------------------------------------------------
 int oss_reset_stack(oss_ctx *c)
 {
-    NEED_GEOM();
+    USE_PIPE0();
     CK(cudaMemsetAsync(c->sum, 0, (size_t)c->g.P * c->g.C * sizeof(float), c->stream));
     CK(cudaMemsetAsync(c->d_valid, 0, 16, c->stream));
     CK(cudaStreamSynchronize(c->stream));
@@ -627,7 +702,7 @@ int oss_reset_stack(oss_ctx *c)
 
 int oss_set_reference(oss_ctx *c, const void *frame, int mem, int threshold)
 {
-    NEED_GEOM();
+    USE_PIPE0();
     if (!frame) return fail(c, OSS_E_ARG, "null reference frame");
     int rc = oss_reset_stack(c);
     if (rc) return rc;
@@ -676,11 +751,12 @@ int oss_add_lights(oss_ctx *c, const void *const *frames, int n, int mem)
     if (!c->has_ref) return fail(c, OSS_E_ARG, "oss_set_reference (or oss_comm_broadcast_reference) must come first");
     if (n < 0 || (n && !frames)) return fail(c, OSS_E_ARG, "bad light list");
     const Geom &g = c->g;
-    Workspace &w = c->ws;
     int rc = ensure_report_room(c, c->nlights + n);
     if (rc) return rc;
     for (int b0 = 0; b0 < n; b0 += c->slots) {
         int nb = n - b0 < c->slots ? n - b0 : c->slots;
+        select_pipe(c, (int)(c->light_batches++ % c->npipes));
+        Workspace &w = c->ws;
         FramePtrs fp{};
         int set;
         rc = stage_frames(c, frames + b0, nb, mem, &fp, &set);
@@ -690,6 +766,8 @@ int oss_add_lights(oss_ctx *c, const void *const *frames, int n, int mem)
         LAUNCH("pack_xy", k_pack_xy, nb, OSS_NOBJS, 0, w.star_out, w.ds, g.cap, c->d_xy, c->d_nxy);
         LAUNCH("focas_match_fit", k_focas, nb, FOCAS_NT, sizeof(FocasSmem), c->d_ref, c->d_xy, c->d_nxy, w.align, c->d_valid,
                (int *)nullptr, (int *)nullptr, (long long *)nullptr);
+        // accumulate in batch order: wait for the previous batch's warp (it ran on another pipeline)
+        if (c->last_warp && c->npipes > 1) CK(cudaStreamWaitEvent(c->stream, c->last_warp, 0));
         if (g.C == 3) {
             LAUNCH("warp_accumulate", k_warp_accumulate<3>, dim3((g.W + 31) / 32, (g.H + 7) / 8), dim3(32, 8), 0, w.cal, w.stridePC,
                    w.align, nb, c->sum, g.W, g.H);
@@ -697,6 +775,8 @@ int oss_add_lights(oss_ctx *c, const void *const *frames, int n, int mem)
             LAUNCH("warp_accumulate", k_warp_accumulate<1>, dim3((g.W + 31) / 32, (g.H + 7) / 8), dim3(32, 8), 0, w.cal, w.stridePC,
                    w.align, nb, c->sum, g.W, g.H);
         }
+        CK(cudaEventRecord(c->pipes[c->cur].warp_done, c->stream));
+        c->last_warp = c->pipes[c->cur].warp_done;
         // reports back to pinned host memory, asynchronously; a batch never straddles a chunk
         // boundary more than once
         int done = 0;
@@ -714,9 +794,8 @@ int oss_add_lights(oss_ctx *c, const void *const *frames, int n, int mem)
 
 int oss_sync(oss_ctx *c)
 {
-    NEED_GEOM();
-    CK(cudaStreamSynchronize(c->copy_stream));
-    CK(cudaStreamSynchronize(c->stream));
+    USE_PIPE0();
+    CK(sync_all(c));
     return OSS_OK;
 }
 
@@ -724,7 +803,7 @@ int oss_num_reports(oss_ctx *c) { return c ? c->nlights : 0; }
 
 int oss_get_frame_report(oss_ctx *c, int i, oss_frame_report *out)
 {
-    NEED_GEOM();
+    USE_PIPE0();
     if (i < 0 || i >= c->nlights || !out) return fail(c, OSS_E_ARG, "report index out of range");
     CK(cudaStreamSynchronize(c->stream));
     const DetectState &d = c->h_ds_chunks[i / kChunk][i % kChunk];
@@ -737,7 +816,7 @@ int oss_get_frame_report(oss_ctx *c, int i, oss_frame_report *out)
 
 int oss_get_reference_stars(oss_ctx *c, oss_star *out, int cap, int *n, oss_detect_info *info)
 {
-    NEED_GEOM();
+    USE_PIPE0();
     if (!c->has_ref) return fail(c, OSS_E_ARG, "no reference");
     int m = (int)c->ref_stars.size();
     if (n) *n = m;
@@ -757,7 +836,7 @@ static int total_valid(oss_ctx *c, int *out)
 
 int oss_get_sum(oss_ctx *c, float *out, int *tv)
 {
-    NEED_GEOM();
+    USE_PIPE0();
     if (tv) { int rc = total_valid(c, tv); if (rc) return rc; }
     if (out) return oss_memcpy_d2h(c, out, c->sum, (size_t)c->g.P * c->g.C * sizeof(float));
     return OSS_OK;
@@ -765,7 +844,7 @@ int oss_get_sum(oss_ctx *c, float *out, int *tv)
 
 int oss_finish(oss_ctx *c, float *out, int *tv)
 {
-    NEED_GEOM();
+    USE_PIPE0();
     if (!c->has_ref) return fail(c, OSS_E_ARG, "no reference");
     CK(cudaStreamSynchronize(c->copy_stream));
     int v;
@@ -787,7 +866,7 @@ const float *oss_result_device_ptr(oss_ctx *c) { return c ? c->result : nullptr;
 // ---- detect only -----------------------------------------------------------------------
 int oss_detect_stars(oss_ctx *c, const void *frame, int mem, int threshold, oss_star *out, int cap, int *n, oss_detect_info *info)
 {
-    NEED_GEOM();
+    USE_PIPE0();
     if (!frame) return fail(c, OSS_E_ARG, "null frame");
     FramePtrs fp{};
     int set;
@@ -808,7 +887,7 @@ int oss_detect_stars(oss_ctx *c, const void *frame, int mem, int threshold, oss_
 
 int oss_detect_stars_batch(oss_ctx *c, const void *const *frames, int n, int mem, int threshold, int32_t *counts)
 {
-    NEED_GEOM();
+    USE_PIPE0();
     if (n < 0 || (n && (!frames || !counts))) return fail(c, OSS_E_ARG, "bad arguments");
     std::vector<DetectState> d(c->slots);
     for (int b0 = 0; b0 < n; b0 += c->slots) {
@@ -830,7 +909,7 @@ int oss_detect_stars_batch(oss_ctx *c, const void *const *frames, int n, int mem
 int oss_align_lists(oss_ctx *c, const int32_t *xy1, int n1, const int32_t *xy2, int n2, int32_t *k, int32_t *err, float *M,
                     int32_t *matches_out, int32_t *votes_out)
 {
-    NEED_GEOM();
+    USE_PIPE0();
     if (n1 < 0 || n2 < 0 || (n1 && !xy1) || (n2 && !xy2)) return fail(c, OSS_E_ARG, "bad star lists");
     int m1 = n1 < OSS_NOBJS ? n1 : OSS_NOBJS, m2 = n2 < OSS_NOBJS ? n2 : OSS_NOBJS;
     int *xy_ref = c->d_xy + c->slots * 2 * OSS_NOBJS, *nxy_ref = c->d_nxy + c->slots;
@@ -868,7 +947,7 @@ int oss_align_lists(oss_ctx *c, const int32_t *xy1, int n1, const int32_t *xy2, 
 // ---- warp only -------------------------------------------------------------------------
 int oss_warp_affine(oss_ctx *c, const float *src, float *dst, const float *M)
 {
-    NEED_GEOM();
+    USE_PIPE0();
     if (!src || !dst || !M) return fail(c, OSS_E_ARG, "null argument");
     const Geom &g = c->g;
     const size_t bytes = (size_t)g.P * g.C * sizeof(float);
@@ -912,7 +991,7 @@ int oss_comm_init(oss_ctx *c, const void *id128, int rank, int nranks)
 
 int oss_comm_broadcast_masters(oss_ctx *c, int root)
 {
-    NEED_GEOM();
+    USE_PIPE0();
     if (!c->comm) return fail(c, OSS_E_ARG, "oss_comm_init has not been called");
     const long long count = c->g.P * c->g.C;
     int present[4];
@@ -934,7 +1013,7 @@ int oss_comm_broadcast_masters(oss_ctx *c, int root)
 
 int oss_comm_broadcast_reference(oss_ctx *c, int root)
 {
-    NEED_GEOM();
+    USE_PIPE0();
     if (!c->comm) return fail(c, OSS_E_ARG, "oss_comm_init has not been called");
     if (c->rank == root && !c->has_ref) return fail(c, OSS_E_ARG, "root has no reference");
     if (c->rank != root) { int rc = oss_reset_stack(c); if (rc) return rc; }
@@ -954,7 +1033,7 @@ int oss_comm_broadcast_reference(oss_ctx *c, int root)
 
 int oss_comm_reduce(oss_ctx *c, int root)
 {
-    NEED_GEOM();
+    USE_PIPE0();
     if (!c->comm) return fail(c, OSS_E_ARG, "oss_comm_init has not been called");
     const long long count = c->g.P * c->g.C;
     CK(cudaStreamSynchronize(c->copy_stream));
@@ -965,10 +1044,19 @@ int oss_comm_reduce(oss_ctx *c, int root)
 }
 
 // ---- device timer + synthetic frames (bench utilities) ---------------------------------
+int oss_set_pipelines(oss_ctx *c, int n)
+{
+    if (!c || n < 1 || n > OSS_MAX_PIPES) return fail(c, OSS_E_ARG, "pipelines must be 1..%d", OSS_MAX_PIPES);
+    c->want_pipes = n; // takes effect at the next oss_set_geometry
+    return OSS_OK;
+}
+
 int oss_mark(oss_ctx *c, int which)
 {
     if (!c || which < 0 || which > 1) return OSS_E_ARG;
     CK(cudaSetDevice(c->device));
+    CK(sync_all(c));
+    if (c->has_geom) select_pipe(c, 0);
     if (!c->mark[which]) CK(cudaEventCreate(&c->mark[which]));
     CK(cudaEventRecord(c->mark[which], c->stream));
     return OSS_OK;
@@ -987,7 +1075,7 @@ int oss_elapsed_ms(oss_ctx *c, double *ms)
 int oss_synth_light(oss_ctx *c, void *dst_dev, const float *stars_xyas, int nstars, float background, float noise,
                     float pedestal_adu, int vignette, unsigned seed, const float *gains3)
 {
-    NEED_GEOM();
+    USE_PIPE0();
     const Geom &g = c->g;
     if (g.sample != OSS_U16 || !dst_dev || nstars < 0 || nstars > 65536) return fail(c, OSS_E_ARG, "synth needs a u16 geometry");
     if (!c->synth_plane) { DA(c->synth_plane, g.P); DA(c->synth_stars, 65536); }
@@ -1003,7 +1091,7 @@ int oss_synth_light(oss_ctx *c, void *dst_dev, const float *stars_xyas, int nsta
 
 int oss_synth_calib(oss_ctx *c, void *dst_dev, float level_adu, float sigma_adu, int flat_profile, float pedestal_adu, unsigned seed)
 {
-    NEED_GEOM();
+    USE_PIPE0();
     const Geom &g = c->g;
     if (g.sample != OSS_U16 || !dst_dev) return fail(c, OSS_E_ARG, "synth needs a u16 geometry");
     LAUNCH("synth", k_synth_calib, 1184, 256, 0, (uint16_t *)dst_dev, g.W, g.H, g.C, level_adu, sigma_adu, flat_profile, pedestal_adu, seed);
@@ -1016,7 +1104,7 @@ int oss_profile_enable(oss_ctx *c, int on)
 {
     if (!c) return OSS_E_ARG;
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
+    sync_all(c);
     prof_flush(c);
     c->profiling = on != 0;
     return OSS_OK;
@@ -1025,7 +1113,7 @@ int oss_profile_reset(oss_ctx *c)
 {
     if (!c) return OSS_E_ARG;
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
+    sync_all(c);
     prof_flush(c);
     c->prof.clear();
     return OSS_OK;
@@ -1034,7 +1122,7 @@ int oss_profile_count(oss_ctx *c)
 {
     if (!c) return 0;
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
+    sync_all(c);
     prof_flush(c);
     return (int)c->prof.size();
 }
@@ -1050,7 +1138,7 @@ long long oss_launch_count(oss_ctx *c) { return c ? c->launches : 0; }
 
 int oss_debug_copy(oss_ctx *c, int what, int slot, float *out)
 {
-    NEED_GEOM();
+    USE_PIPE0();
     if (slot < 0 || slot >= c->slots || !out) return fail(c, OSS_E_ARG, "bad slot");
     const Geom &g = c->g;
     const Workspace &w = c->ws;

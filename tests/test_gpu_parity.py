@@ -285,6 +285,14 @@ def test_batch_size_invariance_and_identical_frames(eng):
     assert tv1 == tv4 == 6 and np.array_equal(bits(img1), bits(img4))
     for a, b in zip(rep1, rep4):
         assert (a.nstars, a.k, a.err) == (b.nstars, b.k, b.err) and list(a.M) == list(b.M)
+    # ... nor on how many pipelines (streams) the batches alternate between: the warp kernels are chained
+    for pipes in (1, 2):
+        eng.set_pipelines(pipes)
+        (imgp, tvp), repp = run_stack(eng, ds, w, h, 1, 20, 2)
+        assert tvp == tv1 and np.array_equal(bits(imgp), bits(img1))
+        for a, b in zip(rep1, repp):
+            assert (a.nstars, a.k, a.err) == (b.nstars, b.k, b.err) and list(a.M) == list(b.M)
+    eng.set_pipelines(3)
     # identical frames: every residual is 0 -> lim = 0 rejects all pairs -> every light is skipped, in the
     # reference (oracle) and here alike; the stack then ends with the reference's own error
     same = [ds["ref"]] * 3
