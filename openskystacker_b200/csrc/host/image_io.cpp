@@ -1,0 +1,323 @@
+#include "image_io.hpp"
+
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <map>
+
+namespace openskystacker {
+namespace {
+
+struct Reader {
+    std::vector<uint8_t> buf;
+    bool big = false;
+    uint16_t u16(size_t o) const { return big ? (uint16_t)(buf[o] << 8 | buf[o + 1]) : (uint16_t)(buf[o] | buf[o + 1] << 8); }
+    uint32_t u32(size_t o) const
+    {
+        return big ? ((uint32_t)buf[o] << 24 | (uint32_t)buf[o + 1] << 16 | (uint32_t)buf[o + 2] << 8 | buf[o + 3])
+                   : ((uint32_t)buf[o] | (uint32_t)buf[o + 1] << 8 | (uint32_t)buf[o + 2] << 16 | (uint32_t)buf[o + 3] << 24);
+    }
+};
+
+struct Ifd {
+    int width = 0, height = 0, spp = 1, bps = 8, compression = 1, photometric = 1, planar = 1, predictor = 1, format = 1;
+    long rows_per_strip = -1;
+    std::vector<uint32_t> offsets, counts;
+    bool tiled = false;
+};
+
+bool fail(std::string *err, const std::string &m)
+{
+    if (err) *err = m;
+    return false;
+}
+
+bool loadFile(const std::string &path, std::vector<uint8_t> *out, size_t limit, std::string *err)
+{
+    std::ifstream f(path, std::ios::binary);
+    if (!f) return fail(err, "cannot open " + path);
+    f.seekg(0, std::ios::end);
+    size_t n = (size_t)f.tellg();
+    f.seekg(0);
+    if (limit && n > limit) n = limit;
+    out->resize(n);
+    f.read((char *)out->data(), (std::streamsize)n);
+    return true;
+}
+
+bool parseIfd(const Reader &r, Ifd *ifd, std::string *err)
+{
+    if (r.buf.size() < 8) return fail(err, "not a TIFF file");
+    if (r.u16(2) != 42) return fail(err, "not a classic TIFF (BigTIFF is not supported)");
+    size_t off = r.u32(4);
+    if (off + 2 > r.buf.size()) return fail(err, "TIFF directory lies beyond the probed header");
+    int n = r.u16(off);
+    if (off + 2 + (size_t)n * 12 > r.buf.size()) return fail(err, "truncated TIFF directory");
+    auto values = [&](size_t e, std::vector<uint32_t> *v) {
+        int type = r.u16(e + 2);
+        uint32_t cnt = r.u32(e + 4);
+        size_t sz = type == 3 ? 2 : (type == 4 ? 4 : 1);
+        size_t p = cnt * sz <= 4 ? e + 8 : r.u32(e + 8);
+        if (p + cnt * sz > r.buf.size()) return false;
+        v->resize(cnt);
+        for (uint32_t i = 0; i < cnt; i++) (*v)[i] = type == 3 ? r.u16(p + 2 * i) : (type == 4 ? r.u32(p + 4 * i) : r.buf[p + i]);
+        return true;
+    };
+    for (int i = 0; i < n; i++) {
+        size_t e = off + 2 + (size_t)i * 12;
+        int tag = r.u16(e);
+        std::vector<uint32_t> v;
+        bool bulk = tag == 273 || tag == 279;
+        if (!values(e, &v)) {
+            if (bulk) continue; // strip tables may lie beyond a header-only probe
+            return fail(err, "truncated TIFF tag");
+        }
+        if (v.empty()) continue;
+        switch (tag) {
+        case 256: ifd->width = (int)v[0]; break;
+        case 257: ifd->height = (int)v[0]; break;
+        case 258: ifd->bps = (int)v[0]; break;
+        case 259: ifd->compression = (int)v[0]; break;
+        case 262: ifd->photometric = (int)v[0]; break;
+        case 273: ifd->offsets = v; break;
+        case 277: ifd->spp = (int)v[0]; break;
+        case 278: ifd->rows_per_strip = (long)v[0]; break;
+        case 279: ifd->counts = v; break;
+        case 284: ifd->planar = (int)v[0]; break;
+        case 317: ifd->predictor = (int)v[0]; break;
+        case 339: ifd->format = (int)v[0]; break;
+        case 322: case 323: case 324: case 325: ifd->tiled = true; break;
+        default: break;
+        }
+    }
+    return true;
+}
+
+bool describe(const Ifd &d, ImageInfo *info, std::string *err)
+{
+    if (d.width <= 0 || d.height <= 0) return fail(err, "TIFF without dimensions");
+    if (d.tiled) return fail(err, "tiled TIFFs are not supported");
+    if (d.planar != 1 && d.spp > 1) return fail(err, "planar TIFFs are not supported");
+    if (d.spp != 1 && d.spp != 3 && d.spp != 4) return fail(err, "unsupported samples per pixel");
+    info->width = d.width;
+    info->height = d.height;
+    info->channels = d.spp == 1 ? 1 : 3; // an alpha channel is dropped, like IMREAD_ANYCOLOR does
+    if (d.bps == 8 && d.format == 1) info->sample = SAMPLE_U8;
+    else if (d.bps == 16 && d.format == 1) info->sample = SAMPLE_U16;
+    else if (d.bps == 32 && d.format == 3) info->sample = SAMPLE_F32;
+    else return fail(err, "unsupported TIFF sample format");
+    if (d.compression != 1 && d.compression != 5) return fail(err, "unsupported TIFF compression (only none / LZW)");
+    return true;
+}
+
+// TIFF-flavoured LZW (MSB-first codes, 9..12 bits, early change)
+bool lzwDecode(const uint8_t *src, size_t n, std::vector<uint8_t> *out, size_t expect)
+{
+    struct Entry { int prev; uint8_t ch; uint16_t len; };
+    static thread_local std::vector<Entry> table(4096);
+    out->clear();
+    out->reserve(expect);
+    size_t bitpos = 0;
+    int width = 9, next = 258, prev = -1;
+    std::vector<uint8_t> tmp(4096);
+    auto emit = [&](int code) {
+        int len = code < 256 ? 1 : table[code].len;
+        size_t base = out->size();
+        out->resize(base + len);
+        int c = code;
+        for (int i = len - 1; i >= 0; i--) {
+            if (c < 256) { (*out)[base + i] = (uint8_t)c; break; }
+            (*out)[base + i] = table[c].ch;
+            c = table[c].prev;
+        }
+        return (*out)[base];
+    };
+    while (bitpos + width <= n * 8 && out->size() < expect) {
+        uint32_t v = 0;
+        size_t byte = bitpos >> 3;
+        for (int i = 0; i < 4; i++) v = v << 8 | (byte + i < n ? src[byte + i] : 0);
+        int code = (int)((v >> (32 - width - (bitpos & 7))) & ((1u << width) - 1));
+        bitpos += width;
+        if (code == 257) break;
+        if (code == 256) { width = 9; next = 258; prev = -1; continue; }
+        if (prev < 0) {
+            if (code >= 256) return false;
+            emit(code);
+            prev = code;
+            continue;
+        }
+        uint8_t first;
+        if (code < next) {
+            first = emit(code);
+        } else if (code == next) { // KwKwK
+            int c = prev;
+            while (c >= 256) c = table[c].prev;
+            first = (uint8_t)c;
+            table[next] = {prev, first, (uint16_t)((prev < 256 ? 1 : table[prev].len) + 1)};
+            emit(next);
+        } else return false;
+        if (next < 4096) {
+            table[next] = {prev, first, (uint16_t)((prev < 256 ? 1 : table[prev].len) + 1)};
+            next++;
+            if (next + 1 >= (1 << width) && width < 12) width++;
+        }
+        prev = code;
+    }
+    return true;
+}
+
+template <typename T>
+void storeRow(const uint8_t *row, int width, int spp, int channels, bool swap_bytes, T *dst)
+{
+    for (int x = 0; x < width; x++) {
+        T px[4];
+        for (int c = 0; c < spp; c++) {
+            T v;
+            memcpy(&v, row + ((size_t)x * spp + c) * sizeof(T), sizeof(T));
+            if (swap_bytes && sizeof(T) == 2) { uint16_t u; memcpy(&u, &v, 2); u = (uint16_t)(u << 8 | u >> 8); memcpy(&v, &u, 2); }
+            if (swap_bytes && sizeof(T) == 4) { uint32_t u; memcpy(&u, &v, 4); u = __builtin_bswap32(u); memcpy(&v, &u, 4); }
+            px[c] = v;
+        }
+        if (channels == 1) dst[x] = px[0];
+        else { dst[3 * x] = px[2]; dst[3 * x + 1] = px[1]; dst[3 * x + 2] = px[0]; } // RGB in file -> BGR like imread
+    }
+}
+
+bool decode(const Reader &r, const Ifd &d, const ImageInfo &info, void *dst, std::string *err)
+{
+    const size_t ssz = info.sample == SAMPLE_U8 ? 1 : info.sample == SAMPLE_U16 ? 2 : 4;
+    const size_t row_bytes = (size_t)d.width * d.spp * ssz;
+    long rps = d.rows_per_strip <= 0 || d.rows_per_strip > d.height ? d.height : d.rows_per_strip;
+    size_t nstrips = ((size_t)d.height + rps - 1) / rps;
+    if (d.offsets.size() < nstrips || d.counts.size() < nstrips) return fail(err, "TIFF strip table is incomplete");
+    const bool host_little = true;
+    const bool swap = r.big == host_little && ssz > 1;
+    std::vector<uint8_t> strip;
+    for (size_t s = 0; s < nstrips; s++) {
+        int y0 = (int)(s * rps), rows = (int)std::min<long>(rps, d.height - y0);
+        size_t want = row_bytes * rows;
+        if ((size_t)d.offsets[s] + d.counts[s] > r.buf.size()) return fail(err, "TIFF strip lies beyond the file");
+        const uint8_t *data = r.buf.data() + d.offsets[s];
+        if (d.compression == 5) {
+            if (!lzwDecode(data, d.counts[s], &strip, want) || strip.size() < want) return fail(err, "corrupt LZW strip");
+            data = strip.data();
+        } else if (d.counts[s] < want) return fail(err, "short TIFF strip");
+        if (d.predictor == 2) { // horizontal differencing, per sample, in the file's byte order
+            if (data != strip.data()) { strip.assign(data, data + want); data = strip.data(); }
+            uint8_t *p = strip.data();
+            for (int y = 0; y < rows; y++) {
+                uint8_t *row = p + (size_t)y * row_bytes;
+                for (size_t i = (size_t)d.spp; i < (size_t)d.width * d.spp; i++) {
+                    if (ssz == 1) row[i] = (uint8_t)(row[i] + row[i - d.spp]);
+                    else if (ssz == 2) {
+                        auto get = [&](size_t k) { return r.big ? (uint16_t)(row[2 * k] << 8 | row[2 * k + 1]) : (uint16_t)(row[2 * k] | row[2 * k + 1] << 8); };
+                        uint16_t v = (uint16_t)(get(i) + get(i - d.spp));
+                        if (r.big) { row[2 * i] = (uint8_t)(v >> 8); row[2 * i + 1] = (uint8_t)v; }
+                        else { row[2 * i] = (uint8_t)v; row[2 * i + 1] = (uint8_t)(v >> 8); }
+                    } else return fail(err, "predictor on 32-bit samples is not supported");
+                }
+            }
+        }
+        for (int y = 0; y < rows; y++) {
+            const uint8_t *row = data + (size_t)y * row_bytes;
+            size_t o = (size_t)(y0 + y) * d.width * info.channels;
+            if (ssz == 1) storeRow<uint8_t>(row, d.width, d.spp, info.channels, false, (uint8_t *)dst + o);
+            else if (ssz == 2) storeRow<uint16_t>(row, d.width, d.spp, info.channels, swap, (uint16_t *)dst + o);
+            else storeRow<float>(row, d.width, d.spp, info.channels, swap, (float *)dst + o);
+        }
+    }
+    return true;
+}
+
+bool open(const std::string &path, size_t limit, Reader *r, Ifd *d, ImageInfo *info, std::string *err)
+{
+    if (!loadFile(path, &r->buf, limit, err)) return false;
+    if (r->buf.size() < 8) return fail(err, path + ": not a TIFF file");
+    if (r->buf[0] == 'I' && r->buf[1] == 'I') r->big = false;
+    else if (r->buf[0] == 'M' && r->buf[1] == 'M') r->big = true;
+    else return fail(err, path + ": not a TIFF file (only TIFF input is supported by this build)");
+    if (!parseIfd(*r, d, err)) {
+        if (limit) { // directory at the end of the file: read it all
+            if (!loadFile(path, &r->buf, 0, err)) return false;
+            *d = Ifd();
+            if (!parseIfd(*r, d, err)) return false;
+        } else return false;
+    }
+    return describe(*d, info, err);
+}
+
+void putU16(std::vector<uint8_t> &b, uint16_t v) { b.push_back((uint8_t)v); b.push_back((uint8_t)(v >> 8)); }
+void putU32(std::vector<uint8_t> &b, uint32_t v) { for (int i = 0; i < 4; i++) b.push_back((uint8_t)(v >> (8 * i))); }
+
+template <typename T>
+bool writeTiff(const std::string &path, const T *px, int w, int h, int c, int format, std::string *err)
+{
+    const size_t ssz = sizeof(T), data_bytes = (size_t)w * h * c * ssz;
+    if (data_bytes + 1024 > 0xffffffffull) return fail(err, "image too large for a classic TIFF");
+    std::vector<uint8_t> head;
+    head.push_back('I'); head.push_back('I');
+    putU16(head, 42);
+    putU32(head, 8);
+    struct Tag { uint16_t id, type; uint32_t count, value; };
+    const uint32_t ifd_size = 2 + 12 * 12 + 4, bps_off = 8 + ifd_size, fmt_off = bps_off + 8, data_off = fmt_off + 8;
+    std::vector<Tag> tags = {
+        {256, 4, 1, (uint32_t)w}, {257, 4, 1, (uint32_t)h},
+        {258, 3, (uint32_t)c, c == 1 ? (uint32_t)(8 * ssz) : bps_off},
+        {259, 3, 1, 1}, {262, 3, 1, c == 1 ? 1u : 2u}, {273, 4, 1, data_off}, {277, 3, 1, (uint32_t)c},
+        {278, 4, 1, (uint32_t)h}, {279, 4, 1, (uint32_t)data_bytes}, {284, 3, 1, 1},
+        {339, 3, (uint32_t)c, c == 1 ? (uint32_t)format : fmt_off}, {305, 2, 4, 0x0073736fu /* "oss" */},
+    };
+    putU16(head, (uint16_t)tags.size());
+    for (auto &t : tags) { putU16(head, t.id); putU16(head, t.type); putU32(head, t.count); putU32(head, t.value); }
+    putU32(head, 0);
+    for (int i = 0; i < 4; i++) putU16(head, (uint16_t)(8 * ssz));
+    for (int i = 0; i < 4; i++) putU16(head, (uint16_t)format);
+    FILE *f = fopen(path.c_str(), "wb");
+    if (!f) return fail(err, "cannot create " + path);
+    bool ok = fwrite(head.data(), 1, head.size(), f) == head.size();
+    if (c == 1) ok = ok && fwrite(px, ssz, (size_t)w * h, f) == (size_t)w * h;
+    else {
+        std::vector<T> row((size_t)w * 3);
+        for (int y = 0; ok && y < h; y++) {
+            const T *s = px + (size_t)y * w * 3;
+            for (int x = 0; x < w; x++) { row[3 * x] = s[3 * x + 2]; row[3 * x + 1] = s[3 * x + 1]; row[3 * x + 2] = s[3 * x]; }
+            ok = fwrite(row.data(), ssz, row.size(), f) == row.size();
+        }
+    }
+    ok = fclose(f) == 0 && ok;
+    return ok ? true : fail(err, "write to " + path + " failed");
+}
+
+}  // namespace
+
+bool probeImage(const std::string &path, ImageInfo *info, std::string *err)
+{
+    Reader r;
+    Ifd d;
+    return open(path, 1 << 16, &r, &d, info, err);
+}
+
+bool readImageInto(const std::string &path, const ImageInfo &expect, void *dst, std::string *err)
+{
+    Reader r;
+    Ifd d;
+    ImageInfo info;
+    if (!open(path, 0, &r, &d, &info, err)) return false;
+    if (info.width != expect.width || info.height != expect.height || info.channels != expect.channels || info.sample != expect.sample)
+        return fail(err, path + ": geometry differs from the reference frame");
+    return decode(r, d, info, dst, err);
+}
+
+bool readImage(const std::string &path, ImageInfo *info, std::vector<uint8_t> *pixels, std::string *err)
+{
+    Reader r;
+    Ifd d;
+    if (!open(path, 0, &r, &d, info, err)) return false;
+    pixels->resize(info->bytes());
+    return decode(r, d, *info, pixels->data(), err);
+}
+
+bool writeTiffF32(const std::string &path, const float *px, int w, int h, int c, std::string *err) { return writeTiff<float>(path, px, w, h, c, 3, err); }
+bool writeTiffU16(const std::string &path, const uint16_t *px, int w, int h, int c, std::string *err) { return writeTiff<uint16_t>(path, px, w, h, c, 1, err); }
+
+}  // namespace openskystacker

@@ -1,0 +1,30 @@
+// Host-side image decode / encode for the ImageStacker facade (file codecs stay on the host,
+// as in the reference: readImage -> cv::imread, libstacker/src/util.cpp:277-298; cl/cl.cpp:205
+// cv::imwrite).  TIFF only: baseline strips, 8/16-bit unsigned or 32-bit float samples, 1 or 3
+// channels, uncompressed or LZW (+ horizontal predictor), either byte order.  Frames come back
+// interleaved HWC in cv::imread's channel order (B, G, R).
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace openskystacker {
+
+enum SampleKind { SAMPLE_U8 = 0, SAMPLE_U16 = 1, SAMPLE_F32 = 2 }; // == oss_sample
+
+struct ImageInfo {
+    int width = -1, height = -1, channels = 0;
+    SampleKind sample = SAMPLE_U8;
+    size_t bytes() const { return (size_t)width * height * channels * (sample == SAMPLE_U8 ? 1 : sample == SAMPLE_U16 ? 2 : 4); }
+};
+
+// header only: what validateImageSizes (imagestacker.cpp:402-557) needs, without decoding pixels
+bool probeImage(const std::string &path, ImageInfo *info, std::string *err);
+// decode into dst (info->bytes() bytes, e.g. pinned memory from oss_host_alloc)
+bool readImageInto(const std::string &path, const ImageInfo &expect, void *dst, std::string *err);
+bool readImage(const std::string &path, ImageInfo *info, std::vector<uint8_t> *pixels, std::string *err);
+// float32 / uint16 TIFF, channel order flipped back to RGB like cv::imwrite does
+bool writeTiffF32(const std::string &path, const float *hwc_bgr, int width, int height, int channels, std::string *err);
+bool writeTiffU16(const std::string &path, const uint16_t *hwc_bgr, int width, int height, int channels, std::string *err);
+
+}  // namespace openskystacker

@@ -1,0 +1,48 @@
+"""Multi-GPU plumbing: one process per GPU, frames sharded across ranks exactly like the
+reference shards them across `-j` worker threads (libstacker/src/util.cpp:738: worker i
+takes lights i, i+N, i+2N, ...), masters + reference broadcast from rank 0, and ONE
+ncclReduce of the float32 sum image + the valid-frame count back to rank 0
+(libstacker/src/imagestacker.cpp:348-351 is the reference's serial version of that reduce).
+torch.distributed is used only to ship the 128-byte NCCL id and for barriers."""
+from . import binding as B
+
+
+def light_shard(nlights, rank, world):
+    """Indices of the lights rank `rank` of `world` processes: the reference's strided split."""
+    if world < 1 or not 0 <= rank < world:
+        raise ValueError("bad rank/world")
+    return list(range(rank, nlights, world))
+
+
+def init_comm(eng, dist):
+    """Create the engine's NCCL communicator over the ranks of torch.distributed's default group."""
+    rank, world = dist.get_rank(), dist.get_world_size()
+    box = [B.Engine.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    eng.comm_init(box[0], rank, world)
+    return rank, world
+
+
+def sharded_stack(eng, dist, ref, lights, threshold, calib=None, mem=B.HOST, want_image=True):
+    """Whole stack over all ranks.  `lights` is the FULL list on every rank (each rank picks its
+    shard); `ref` and `calib` (dict kind -> frames) are only read on rank 0.  Returns
+    (image, total_valid) on rank 0 and (None, 0) elsewhere."""
+    rank, world = dist.get_rank(), dist.get_world_size()
+    if rank == 0:
+        eng.clear_masters()
+        for kind in (B.BIAS, B.DARK, B.DARKFLAT, B.FLAT):   # imagestacker.cpp:262-281 order
+            if calib and calib.get(kind):
+                eng.build_master(kind, calib[kind], mem)
+        eng.set_reference(ref, threshold, mem)
+    if world > 1:
+        eng.comm_broadcast_masters(0)
+        eng.comm_broadcast_reference(0)
+    mine = [lights[i] for i in light_shard(len(lights), rank, world)]
+    if mine:
+        eng.add_lights(mine, mem)
+    eng.sync()
+    if world > 1:
+        eng.comm_reduce(0)
+    if rank == 0:
+        return eng.finish(want_image)
+    return None, 0

@@ -1,0 +1,150 @@
+"""Host C++ layer above the C ABI (openskystacker_b200/csrc/host): TIFF codecs, image-list JSON,
+openskystacker-cl argument handling (CPU), and the CLI end to end against the oracle (GPU)."""
+import ctypes as C
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle
+import openskystacker_b200 as ob
+from openskystacker_b200 import synth
+
+cv2 = pytest.importorskip("cv2")
+CSRC = ob.binding.CSRC
+CLI = os.path.join(CSRC, "openskystacker-cl")
+
+
+@pytest.fixture(scope="module")
+def host():
+    ob.build()
+    L = C.CDLL(os.path.join(CSRC, "liboss_stacker.so"))
+    return L
+
+
+def read_tiff(L, path):
+    whcs = (C.c_int * 4)()
+    err = C.create_string_buffer(256)
+    assert L.oss_host_probe_image(path.encode(), whcs, err, 256) == 0, err.value
+    w, h, c, s = list(whcs)
+    dt = [np.uint8, np.uint16, np.float32][s]
+    out = np.empty((h, w) if c == 1 else (h, w, c), dt)
+    assert L.oss_host_read_image(path.encode(), whcs, C.c_void_p(out.ctypes.data), err, 256) == 0, err.value
+    return out
+
+
+@pytest.mark.parametrize("dtype,channels,compression", [(np.uint16, 3, 5), (np.uint16, 1, 5), (np.uint8, 3, 5),
+                                                        (np.uint16, 3, 1), (np.float32, 1, 1), (np.uint16, 3, 32773)])
+def test_tiff_reader_matches_imread(host, tmp_path, dtype, channels, compression):
+    rng = np.random.default_rng(channels + compression)
+    shape = (57, 83) if channels == 1 else (57, 83, channels)
+    if dtype == np.float32:
+        img = rng.random(shape, dtype=np.float32)
+    else:
+        # smooth + noise so that LZW actually builds long strings
+        base = np.linspace(0, np.iinfo(dtype).max * 0.8, shape[1])[None, :, None] if channels == 3 else np.linspace(0, np.iinfo(dtype).max * 0.8, shape[1])[None, :]
+        img = (np.broadcast_to(base, shape) + rng.integers(0, 4, shape)).astype(dtype)
+    path = str(tmp_path / "a.tif")
+    assert cv2.imwrite(path, img, [cv2.IMWRITE_TIFF_COMPRESSION, compression])
+    want = cv2.imread(path, cv2.IMREAD_ANYDEPTH | cv2.IMREAD_ANYCOLOR)   # util.cpp:292
+    if compression == 32773:  # PackBits: unsupported, must fail loudly rather than decode garbage
+        whcs = (C.c_int * 4)()
+        err = C.create_string_buffer(256)
+        assert host.oss_host_probe_image(path.encode(), whcs, err, 256) != 0 and b"compression" in err.value
+        return
+    got = read_tiff(host, path)
+    assert got.dtype == want.dtype and got.shape == want.shape and np.array_equal(got, want)
+
+
+def test_float_tiff_writer_round_trips_through_cv2(host, tmp_path):
+    rng = np.random.default_rng(3)
+    for shape in [(31, 45, 3), (31, 45)]:
+        img = rng.random(shape, dtype=np.float32)
+        path = str(tmp_path / "o.tif")
+        c = 1 if img.ndim == 2 else 3
+        assert host.oss_host_write_tiff_f32(path.encode(), C.c_void_p(img.ctypes.data), shape[1], shape[0], c) == 0
+        back = cv2.imread(path, cv2.IMREAD_ANYDEPTH | cv2.IMREAD_ANYCOLOR)
+        assert back.dtype == np.float32 and np.array_equal(back, img)
+        assert np.array_equal(read_tiff(host, path), img)
+
+
+def write_list(tmp_path, entries):
+    p = tmp_path / "list.json"
+    p.write_text(json.dumps(entries))
+    return str(p)
+
+
+def test_image_list_loader(host, tmp_path):
+    img = np.zeros((10, 12, 3), np.uint16)
+    for n in ("r.tif", "l1.tif", "d1.tif"):
+        cv2.imwrite(str(tmp_path / n), img)
+    path = write_list(tmp_path, [{"filename": "r.tif", "type": "ref", "checked": True},
+                                 {"filename": "l1.tif", "type": "light", "checked": True},
+                                 {"filename": str(tmp_path / "d1.tif"), "type": "dark", "checked": False}])
+    buf = C.create_string_buffer(4096)
+    assert host.oss_host_load_image_list(path.encode(), buf, 4096) == 0
+    rows = [r.split(" ", 5) for r in buf.value.decode().strip().split("\n")]
+    assert [r[:5] for r in rows] == [["0", "1", "1", "12", "10"], ["0", "0", "1", "12", "10"], ["1", "0", "0", "12", "10"]]
+    assert rows[0][5] == str(tmp_path / "r.tif") and rows[2][5] == str(tmp_path / "d1.tif")   # relative -> JSON dir
+    # error codes of util.cpp:480-520
+    for text, code in [('{"a": 1}', -1), ('[1]', -2), ('[{"type": "light"}]', -3),
+                       ('[{"filename": "r.tif", "type": "lite"}]', -4), ('not json', -1)]:
+        (tmp_path / "bad.json").write_text(text)
+        assert host.oss_host_load_image_list(str(tmp_path / "bad.json").encode(), buf, 4096) == code
+
+
+def test_time_string(host):
+    buf = C.create_string_buffer(128)
+    for s, want in [(1, "1 second"), (42, "42 seconds"), (61, "1 minute and 1 second"), (3725, "1 hour, 2 minutes, and 5 seconds"),
+                    (90061, "1 day, 1 hour, 1 minute, and 1 second")]:
+        host.oss_host_time_string(s, buf, 128)
+        assert buf.value.decode() == want
+
+
+def test_cli_argument_errors(host, tmp_path):
+    run = lambda *a: subprocess.run([CLI, *a], capture_output=True, text=True)
+    r = run()
+    assert r.returncode == 1 and "Error: Must specify an image list" in r.stdout
+    (tmp_path / "bad.json").write_text("{}")
+    r = run("-f", str(tmp_path / "bad.json"), "-o", "x")
+    assert r.returncode == 1 and "Error -1: Couldn't load image list" in r.stdout
+    r = run("-f", str(tmp_path / "bad.json"), "-t", "500")
+    assert r.returncode == 1 and "must be an integer between 1 and 100" in r.stdout
+
+
+@pytest.mark.gpu
+def test_cli_end_to_end_matches_oracle(host, tmp_path):
+    w, h = 1000, 700
+    ds = synth.dataset(w, h, 4, 3, nstars=120, ndarks=2, nflats=2, nbias=2, seed=1234)
+    entries = []
+
+    def put(name, frame, kind):
+        cv2.imwrite(str(tmp_path / name), frame)          # cv2 default: LZW-compressed 16-bit TIFF
+        entries.append({"filename": name, "type": kind, "checked": True})
+    # files hold what imread will return: the dataset arrays ARE the decoded (BGR) frames
+    put("ref.tif", ds["ref"], "ref")
+    for i, f in enumerate(ds["lights"]):
+        put(f"light{i}.tif", f, "light")
+    for i, f in enumerate(ds["darks"]):
+        put(f"dark{i}.tif", f, "dark")
+    for i, f in enumerate(ds["flats"]):
+        put(f"flat{i}.tif", f, "flat")
+    for i, f in enumerate(ds["bias"]):
+        put(f"bias{i}.tif", f, "bias")
+    lst = write_list(tmp_path, entries)
+    out = str(tmp_path / "stack")
+    r = subprocess.run([CLI, "-f", lst, "-o", out, "-t", "20", "-j", "4", "-v"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert f"File saved to {out}.tif" in r.stdout and "Stacking light frames..." in r.stdout and "Stacking completed in" in r.stdout
+    got = cv2.imread(out + ".tif", cv2.IMREAD_ANYDEPTH | cv2.IMREAD_ANYCOLOR)
+    frames = lambda key: [cv2.imread(str(tmp_path / f"{key}{i}.tif"), cv2.IMREAD_ANYDEPTH | cv2.IMREAD_ANYCOLOR) for i in range(len(ds[{"light": "lights", "dark": "darks", "flat": "flats", "bias": "bias"}[key]]))]
+    want = oracle.stack(cv2.imread(str(tmp_path / "ref.tif"), cv2.IMREAD_ANYDEPTH | cv2.IMREAD_ANYCOLOR), frames("light"), 20,
+                        bias_frames=frames("bias"), dark_frames=frames("dark"), flat_frames=frames("flat"))
+    assert want["total_valid"] == 5
+    assert got.shape == want["image"].shape and np.array_equal(got.view(np.uint32), want["image"].view(np.uint32))
+    # -s: star count of the (uncalibrated) reference, one integer line (cl/cl.cpp:215-219)
+    r = subprocess.run([CLI, "-f", lst, "-s", "-t", "20"], capture_output=True, text=True)
+    nref = len(oracle.get_stars(oracle.u16_to_f32(ds["ref"]), 20)[0])
+    assert r.returncode == 0 and r.stdout.strip().splitlines()[-1] == str(nref)

@@ -1,0 +1,127 @@
+"""N > 1: frames shard across ranks, one reduce of (sum image, valid count) to rank 0.
+CPU: two gloo ranks run the sharding + combine with the oracle as the per-rank worker and
+must reproduce the single-process reference result.  GPU (needs >= 2 devices): two NCCL
+ranks through the C ABI (oss_comm_*) against the single-GPU result and the oracle."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import oracle
+from openskystacker_b200 import synth
+from openskystacker_b200.distributed import light_shard
+
+W, H = 1000, 700
+
+
+def free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def dataset():
+    return synth.dataset(W, H, 5, 1, nstars=120, ndarks=2, seed=1234)
+
+
+def test_light_shard_is_the_reference_stride():
+    for n in (0, 1, 5, 50, 401):
+        for world in (1, 2, 3, 8):
+            shards = [light_shard(n, r, world) for r in range(world)]
+            assert sorted(i for s in shards for i in s) == list(range(n))
+            for r, s in enumerate(shards):
+                assert s == list(range(r, n, world))          # util.cpp:738
+    with pytest.raises(ValueError):
+        light_shard(4, 2, 2)
+
+
+def _gloo_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ds = dataset()
+    conv = oracle.u16_to_f32
+    # rank 0 builds the master + calibrates/detects the reference, then broadcasts (here: as arrays over gloo)
+    if rank == 0:
+        dark = oracle.stack_mean([conv(f) for f in ds["darks"]])
+        ref_cal = oracle.calibrate(conv(ds["ref"]), None, dark, None)
+        stars, _ = oracle.get_stars(ref_cal, 20)
+        xy = np.stack([stars["x"], stars["y"]], 1).astype(np.int32)
+        meta = torch.tensor([len(xy)])
+    else:
+        dark = np.zeros((H, W), np.float32)
+        meta = torch.tensor([0])
+    dist.broadcast(meta, 0)
+    if rank != 0:
+        xy = np.zeros((int(meta[0]), 2), np.int32)
+    td, tx = torch.from_numpy(dark), torch.from_numpy(xy)
+    dist.broadcast(td, 0)
+    dist.broadcast(tx, 0)
+    total = np.zeros((H, W), np.float32)
+    valid = 0
+    for i in light_shard(len(ds["lights"]), rank, world):
+        err, _ = oracle.process_light(ds["lights"][i], None, td.numpy(), None, 20, None, tx.numpy(), total)
+        valid += 0 if err else 1
+    tsum, tval = torch.from_numpy(total), torch.tensor([valid])
+    dist.reduce(tsum, 0)
+    dist.reduce(tval, 0)
+    if rank == 0:
+        n = int(tval[0]) + 1                       # the reference frame counts once, on the root only
+        out["image"] = oracle.scale(ref_cal + tsum.numpy(), n)
+        out["valid"] = n
+    dist.destroy_process_group()
+
+
+def test_two_gloo_ranks_reproduce_the_single_process_stack():
+    ds = dataset()
+    want = oracle.stack(ds["ref"], ds["lights"], 20, dark_frames=ds["darks"])
+    assert want["total_valid"] >= 5
+    with mp.Manager() as m:
+        out = m.dict()
+        mp.spawn(_gloo_worker, args=(2, free_port(), out), nprocs=2, join=True)
+        assert out["valid"] == want["total_valid"]
+        # only the association of the fp32 sum differs (ref + (p0 + p1) vs ref + (a1 + a2 + ...))
+        assert np.max(np.abs(out["image"] - want["image"])) <= 1e-6
+
+
+def _nccl_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    import openskystacker_b200 as ob
+    from openskystacker_b200 import binding as B
+    from openskystacker_b200.distributed import init_comm, sharded_stack
+    ds = dataset()
+    eng = ob.Engine(rank)
+    eng.set_geometry(W, H, 1, np.uint16, 2)
+    init_comm(eng, dist)
+    img, tv = sharded_stack(eng, dist, ds["ref"], ds["lights"], 20, {B.DARK: ds["darks"]})
+    reps = [(r.nstars, r.k, r.err) for r in eng.reports()]
+    gathered = [None] * world
+    dist.all_gather_object(gathered, reps)
+    if rank == 0:
+        out["image"], out["valid"], out["reports"] = img, tv, gathered
+    eng.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_two_nccl_ranks_match_single_gpu_and_oracle():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    ds = dataset()
+    want = oracle.stack(ds["ref"], ds["lights"], 20, dark_frames=ds["darks"])
+    with mp.Manager() as m:
+        out = m.dict()
+        mp.spawn(_nccl_worker, args=(2, free_port(), out), nprocs=2, join=True)
+        assert out["valid"] == want["total_valid"]
+        assert np.max(np.abs(out["image"] - want["image"])) <= 1e-6
+        per_rank = out["reports"]
+        for r in range(2):
+            idx = light_shard(len(ds["lights"]), r, 2)
+            assert per_rank[r] == [(want["reports"][i].nstars, want["reports"][i].k, want["reports"][i].err) for i in idx]
