@@ -148,19 +148,24 @@ k_sky_sub_stats(const float *__restrict__ gray, long long strideGray, const floa
     __syncthreads();
     const int r_lo = lr_min, nlr = lr_max - lr_min + 1;
 
-    // phase 1
+    // phase 1 (warp w takes rows w, w+8, ...; lanes sweep the 94 columns)
+    const int lane = tid & 31, wid = tid >> 5;
     if (nlr <= SKY_HROWS) {
-        for (int i = tid; i < nlr * SKY_AX; i += 256) {
-            int lr = i / SKY_AX, c = i - lr * SKY_AX;
-            ResizeTap a = tcol[c];
+        for (int lr = wid; lr < nlr; lr += 8) {
             const float *row = L + (long long)(r_lo + lr) * lw;
-            hrow[lr * SKY_UP_LD + c] = lerp2(__ldg(row + a.i0), a.w0, __ldg(row + a.i1), a.w1);
+#pragma unroll
+            for (int c = lane; c < SKY_AX; c += 32) {
+                ResizeTap a = tcol[c];
+                hrow[lr * SKY_UP_LD + c] = lerp2(__ldg(row + a.i0), a.w0, __ldg(row + a.i1), a.w1);
+            }
         }
         __syncthreads();
-        for (int i = tid; i < SKY_AY * SKY_AX; i += 256) {
-            int r = i / SKY_AX, c = i - r * SKY_AX;
-            ResizeTap b = trow[r];
-            up[r * SKY_UP_LD + c] = lerp2(hrow[(b.i0 - r_lo) * SKY_UP_LD + c], b.w0, hrow[(b.i1 - r_lo) * SKY_UP_LD + c], b.w1);
+        for (int r = wid; r < SKY_AY; r += 8) {
+            const ResizeTap b = trow[r];
+            const float *h0 = hrow + (b.i0 - r_lo) * SKY_UP_LD, *h1 = hrow + (b.i1 - r_lo) * SKY_UP_LD;
+            float *dst = up + r * SKY_UP_LD;
+#pragma unroll
+            for (int c = lane; c < SKY_AX; c += 32) dst[c] = lerp2(h0[c], b.w0, h1[c], b.w1);
         }
     } else { // pathological geometry (tiny low-res grid folded many times): direct evaluation
         for (int i = tid; i < SKY_AY * SKY_AX; i += 256) {
@@ -197,6 +202,47 @@ k_sky_sub_stats(const float *__restrict__ gray, long long strideGray, const floa
     double sum = 0.0, sq = 0.0;
     const float *G = gray + f * strideGray;
     float *S = stars + f * strideStars;
+    float *SM = segmax + f * strideSeg;
+    // tile-uniform classification: interior tiles skip every per-pixel bounds / ROI test
+    const bool tile_in_image = x0 + SKY_TX <= g.W && y0 + SKY_TY <= g.H;
+    const bool tile_in_roi = x0 >= g.roi_x && x0 + SKY_TX <= g.roi_x + g.roi_w && y0 >= g.roi_y && y0 + SKY_TY <= g.roi_y + g.roi_h;
+    const bool tile_off_roi = x0 >= g.roi_x + g.roi_w || x0 + SKY_TX <= g.roi_x || y0 >= g.roi_y + g.roi_h || y0 + SKY_TY <= g.roi_y;
+    if (tile_in_image && (tile_in_roi || tile_off_roi)) {
+        for (int i = tid; i < (SKY_TY / 4) * SKY_TX; i += 256) {
+            const int gy = i >> 6, c = i & 63;
+            const long long p = (long long)(y0 + 4 * gy) * g.W + x0 + c;
+            const float *gp = G + p;
+            float gv[4];
+#pragma unroll
+            for (int e = 0; e < 4; e++) gv[e] = __ldg(gp + (long long)e * g.W);
+            const float *q = rf + (4 * gy) * SKY_TX + c;
+            float w[34];
+#pragma unroll
+            for (int j = 0; j < 34; j++) w[j] = q[j * SKY_TX];
+            float *sp = S + p;
+            float *mp = SM + (long long)(y0 + 4 * gy) * nseg + ((x0 + c) >> 5);
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                float sk = __fmul_rn(c_gauss[15], w[e + 15]);
+#pragma unroll
+                for (int j = 1; j <= 15; j++) sk = __fadd_rn(sk, __fmul_rn(c_gauss[15 + j], __fadd_rn(w[e + 15 + j], w[e + 15 - j])));
+                const float v = __fsub_rn(gv[e], sk);
+                sp[(long long)e * g.W] = v;
+                if (tile_in_roi) {
+                    double d = (double)v;
+                    sum += d;
+                    sq += d * d;
+                }
+                unsigned key = __float_as_uint(v);
+                key ^= (unsigned)((int)key >> 31) | 0x80000000u;
+                key = __reduce_max_sync(0xffffffffu, key);
+                if (lane == 0) {
+                    key ^= (key & 0x80000000u) ? 0x80000000u : 0xffffffffu;
+                    mp[(long long)e * nseg] = __uint_as_float(key);
+                }
+            }
+        }
+    } else
     for (int i = tid; i < (SKY_TY / 4) * SKY_TX; i += 256) {
         const int gy = i >> 6, c = i & 63;
         const int x = x0 + c;
@@ -233,7 +279,7 @@ k_sky_sub_stats(const float *__restrict__ gray, long long strideGray, const floa
             key = __reduce_max_sync(0xffffffffu, key);
             if ((tid & 31) == 0 && y < g.H && (x >> 5) < nseg) {
                 key ^= (key & 0x80000000u) ? 0x80000000u : 0xffffffffu;
-                segmax[f * strideSeg + (long long)y * nseg + (x >> 5)] = __uint_as_float(key);
+                SM[(long long)y * nseg + (x >> 5)] = __uint_as_float(key);
             }
         }
     }

@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "common.cuh"
@@ -486,9 +487,32 @@ static int launch_calibrate(oss_ctx *c, const FramePtrs &fp, int n, const float 
 {
     Workspace &w = c->ws;
     const Geom &g = c->g;
-    dim3 grid((unsigned)((g.P + 256ll * Sample<T>::PX - 1) / (256ll * Sample<T>::PX)), n);
-#define CAL(HB, HD, HF) { auto kf = k_calibrate_gray<T, C, HB, HD, HF>; LAUNCH("calibrate_gray", kf, grid, 256, 0, fp, b, d, f, w.cal, w.stridePC, w.gray, w.strideP, g.P); }
-    int key = (b ? 4 : 0) | (d ? 2 : 0) | (f ? 1 : 0);
+    const int key = (b ? 4 : 0) | (d ? 2 : 0) | (f ? 1 : 0);
+    // batches of u16 frames that share masters: masters stay in registers across the batch
+    const bool batched = std::is_same<T, uint16_t>::value && key != 0 && n > 1;
+    long long P_tail_from = 0; // pixels [P_tail_from, P) still need the generic kernel
+    if (batched) {
+        constexpr int PXB = C == 3 ? 4 : 8;
+        unsigned gridb = (unsigned)((g.P / PXB + 255) / 256);
+#define CALB(HB, HD, HF) { auto kf = k_calibrate_gray_batch<C, HB, HD, HF>; LAUNCH("calibrate_gray", kf, gridb, 256, 0, fp, n, b, d, f, w.cal, w.stridePC, w.gray, w.strideP, g.P); }
+        switch (key) {
+        case 1: CALB(false, false, true); break;
+        case 2: CALB(false, true, false); break;
+        case 3: CALB(false, true, true); break;
+        case 4: CALB(true, false, false); break;
+        case 5: CALB(true, false, true); break;
+        case 6: CALB(true, true, false); break;
+        case 7: CALB(true, true, true); break;
+        }
+#undef CALB
+        P_tail_from = g.P / PXB * PXB;
+        if (P_tail_from == g.P) return OSS_OK;
+    }
+    // generic kernel: whole frames, or only the ragged tail the batched kernel left
+    const long long first_group = P_tail_from / Sample<T>::PX; // tail starts inside this PX-group
+    const long long groups = (g.P + Sample<T>::PX - 1) / Sample<T>::PX - first_group;
+    dim3 grid((unsigned)((groups + 255) / 256), n);
+#define CAL(HB, HD, HF) { auto kf = k_calibrate_gray<T, C, HB, HD, HF>; LAUNCH(batched ? "calibrate_tail" : "calibrate_gray", kf, grid, 256, 0, fp, b, d, f, w.cal, w.stridePC, w.gray, w.strideP, g.P, first_group); }
     switch (key) {
     case 0: CAL(false, false, false); break;
     case 1: CAL(false, false, true); break;
