@@ -71,6 +71,8 @@ struct Workspace {
     oss_star *star_out; // [slots][cap]
     int *blocksum;  // [slots][scan blocks]
     AlignOut *align; // [slots]
+    int2 *warp_ab;   // [slots][W]   (adelta, bdelta) of cv::warpAffine's fixed-point coordinates
+    int2 *warp_xy;   // [slots][H]   (X0, Y0)
     long long strideP, stridePC, strideLo, strideSeg, stridePart, strideScan;
     int stat_blocks;
 };

@@ -309,7 +309,9 @@ int oss_create(oss_ctx **out, int device)
     if (cudaMemcpyToSymbol(c_gauss, taps, sizeof taps) != cudaSuccess ||
         cudaMemcpyToSymbol(d_tri_ijk, ijk.data(), ijk.size() * 4) != cudaSuccess ||
         cudaFuncSetAttribute(k_sky_sub_stats, cudaFuncAttributeMaxDynamicSharedMemorySize, kSkySmemBytes) != cudaSuccess ||
-        cudaFuncSetAttribute(k_focas, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FocasSmem)) != cudaSuccess) {
+        cudaFuncSetAttribute(k_focas, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FocasSmem)) != cudaSuccess ||
+        cudaFuncSetAttribute(k_warp_accumulate_tiled<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, warp_tiled_smem<3>()) != cudaSuccess ||
+        cudaFuncSetAttribute(k_warp_accumulate_tiled<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, warp_tiled_smem<1>()) != cudaSuccess) {
         for (int p = 0; p < OSS_MAX_PIPES; p++) { cudaStreamDestroy(c->pipes[p].stream); cudaStreamDestroy(c->pipes[p].copy_stream); }
         delete c;
         return OSS_E_CUDA;
@@ -414,7 +416,7 @@ int oss_set_geometry(oss_ctx *c, int W, int H, int C, int sample, int slots)
         w.stridePart = 2ll * w.stat_blocks;
         long long scan_max = nsegs + 1 > cap ? nsegs + 1 : cap;
         w.strideScan = (scan_max + SCAN_ITEMS - 1) / SCAN_ITEMS + 1;
-        DA(w.cal, slots * w.stridePC);
+        DA(w.cal, slots * w.stridePC + 1024); // + slack: staged warp rows may run past the last frame's end
         if (C == 3) { DA(w.gray, slots * w.strideP); } else w.gray = w.cal;
         DA(w.stars, slots * w.strideP);
         DA(w.lo, slots * lo); DA(w.med, slots * lo);
@@ -430,6 +432,7 @@ int oss_set_geometry(oss_ctx *c, int W, int H, int C, int sample, int slots)
         DA(w.star_tmp, slots * cap); DA(w.star_out, slots * cap);
         DA(w.blocksum, slots * w.strideScan);
         DA(w.align, slots);
+        DA(w.warp_ab, (long long)slots * W); DA(w.warp_xy, (long long)slots * H);
         DA(pp.d_xy, (slots + 1) * 2 * OSS_NOBJS); DA(pp.d_nxy, slots + 1);
         for (int i = 0; i < 2; i++) {
             DA(pp.raw_stage[i], (size_t)slots * c->stage_stride);
@@ -792,12 +795,15 @@ int oss_add_lights(oss_ctx *c, const void *const *frames, int n, int mem)
                (int *)nullptr, (int *)nullptr, (long long *)nullptr);
         // accumulate in batch order: wait for the previous batch's warp (it ran on another pipeline)
         if (c->last_warp && c->npipes > 1) CK(cudaStreamWaitEvent(c->stream, c->last_warp, 0));
+        LAUNCH("warp_tables", k_warp_tables, dim3((g.W + g.H + 255) / 256, nb), 256, 0, w.align, w.warp_ab, (long long)g.W, w.warp_xy,
+               (long long)g.H, g.W, g.H);
+        const dim3 wgrid((g.W + WT_W - 1) / WT_W, (g.H + WT_H - 1) / WT_H);
         if (g.C == 3) {
-            LAUNCH("warp_accumulate", k_warp_accumulate<3>, dim3((g.W + 31) / 32, (g.H + 7) / 8), dim3(32, 8), 0, w.cal, w.stridePC,
-                   w.align, nb, c->sum, g.W, g.H);
+            LAUNCH("warp_accumulate", k_warp_accumulate_tiled<3>, wgrid, 256, warp_tiled_smem<3>(), w.cal, w.stridePC, w.align, nb, w.warp_ab,
+                   (long long)g.W, w.warp_xy, (long long)g.H, c->sum, g.W, g.H);
         } else {
-            LAUNCH("warp_accumulate", k_warp_accumulate<1>, dim3((g.W + 31) / 32, (g.H + 7) / 8), dim3(32, 8), 0, w.cal, w.stridePC,
-                   w.align, nb, c->sum, g.W, g.H);
+            LAUNCH("warp_accumulate", k_warp_accumulate_tiled<1>, wgrid, 256, warp_tiled_smem<1>(), w.cal, w.stridePC, w.align, nb, w.warp_ab,
+                   (long long)g.W, w.warp_xy, (long long)g.H, c->sum, g.W, g.H);
         }
         CK(cudaEventRecord(c->pipes[c->cur].warp_done, c->stream));
         c->last_warp = c->pipes[c->cur].warp_done;
@@ -975,12 +981,23 @@ int oss_warp_affine(oss_ctx *c, const float *src, float *dst, const float *M)
     if (!src || !dst || !M) return fail(c, OSS_E_ARG, "null argument");
     const Geom &g = c->g;
     const size_t bytes = (size_t)g.P * g.C * sizeof(float);
-    CK(cudaMemcpyAsync(c->ws.cal, src, bytes, cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemcpyAsync(c->d_M, M, 6 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    // same kernels as the stacking path (coordinate tables + tiled warp) onto a zeroed accumulator: 0.f + v == v
+    Workspace &w = c->ws;
+    AlignOut ao{};
+    ao.k = 0; ao.err = 0;
+    memcpy(ao.M, M, sizeof ao.M);
+    CK(cudaMemcpyAsync(w.cal, src, bytes, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(w.align, &ao, sizeof ao, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemsetAsync(c->result, 0, bytes, c->stream));
+    LAUNCH("warp_tables", k_warp_tables, dim3((g.W + g.H + 255) / 256, 1), 256, 0, w.align, w.warp_ab, (long long)g.W, w.warp_xy,
+           (long long)g.H, g.W, g.H);
+    const dim3 wgrid((g.W + WT_W - 1) / WT_W, (g.H + WT_H - 1) / WT_H);
     if (g.C == 3) {
-        LAUNCH("warp_only", k_warp_only<3>, dim3((g.W + 31) / 32, (g.H + 7) / 8), dim3(32, 8), 0, c->ws.cal, c->result, c->d_M, g.W, g.H);
+        LAUNCH("warp_accumulate", k_warp_accumulate_tiled<3>, wgrid, 256, warp_tiled_smem<3>(), w.cal, w.stridePC, w.align, 1, w.warp_ab, (long long)g.W,
+               w.warp_xy, (long long)g.H, c->result, g.W, g.H);
     } else {
-        LAUNCH("warp_only", k_warp_only<1>, dim3((g.W + 31) / 32, (g.H + 7) / 8), dim3(32, 8), 0, c->ws.cal, c->result, c->d_M, g.W, g.H);
+        LAUNCH("warp_accumulate", k_warp_accumulate_tiled<1>, wgrid, 256, warp_tiled_smem<1>(), w.cal, w.stridePC, w.align, 1, w.warp_ab, (long long)g.W,
+               w.warp_xy, (long long)g.H, c->result, g.W, g.H);
     }
     CK(cudaMemcpyAsync(dst, c->result, bytes, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));

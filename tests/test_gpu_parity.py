@@ -189,14 +189,16 @@ def test_alignment_matches_oracle(eng):
 # ------------------------------------------------------------------------------- K8
 @pytest.mark.parametrize("c", [1, 3])
 def test_warp_bit_exact(eng, c):
-    w, h = 131, 97
+    w, h = 331, 197          # several 64x32 tiles, ragged right/bottom edges, width not a multiple of 4
     eng.set_geometry(w, h, c, np.float32, 1)
     rng = np.random.default_rng(30 + c)
     src = rng.random((h, w, c), dtype=np.float32) if c == 3 else rng.random((h, w), dtype=np.float32)
-    for _ in range(6):
-        ang, s = rng.uniform(-0.2, 0.2), rng.uniform(0.8, 1.2)
-        M = np.array([[s * np.cos(ang), -s * np.sin(ang), rng.uniform(-30, 30)],
-                      [s * np.sin(ang), s * np.cos(ang), rng.uniform(-30, 30)]], np.float32)
+    cases = [(rng.uniform(-0.2, 0.2), rng.uniform(0.8, 1.2), 30) for _ in range(4)]   # footprints too big to stage: direct gathers
+    cases += [(rng.uniform(-0.004, 0.004), 1.0, 9) for _ in range(6)]                  # stack-like motions: staged tiles
+    cases += [(0.0, 1.0, 0.0), (0.003, 1.0, 250.0)]                                    # identity; mostly outside the frame
+    for ang, s, sh in cases:
+        M = np.array([[s * np.cos(ang), -s * np.sin(ang), rng.uniform(-sh, sh)],
+                      [s * np.sin(ang), s * np.cos(ang), rng.uniform(-sh, sh)]], np.float32)
         assert np.array_equal(bits(eng.warp_affine(src, M)), bits(oracle.warp_affine(src, M)))
     M = np.array([[1, 0, 1000], [0, 1, 1000]], np.float32)  # fully outside: constant-0 border
     assert not eng.warp_affine(src, M).any()
@@ -317,3 +319,17 @@ def test_full_size_24mp_rgb_parity(eng):
     ds = synth.dataset(w, h, 2, 3, nstars=600, ndarks=2)
     want = check_stack(eng, ds, w, h, 3, 20, 2)
     assert want["total_valid"] == 3 and len(want["ref_stars"]) > 100
+
+
+def test_full_size_61mp_mono_star_heavy(eng):
+    """Config-4 geometry: 9576x6388 mono 16-bit (non-integer vertical sky scale 6388/798), 4000 seeded stars,
+    threshold 5 -> thousands of components: star count, every centroid, sigma/threshold against the oracle."""
+    w, h = 9576, 6388
+    f = synth.Field(w, h, 4000, seed=1234)
+    frame = synth.light(f, 0, 1)
+    eng.set_geometry(w, h, 1, np.uint16, 1)
+    got, info = eng.detect_stars(frame, 5)
+    want, oinfo = oracle.get_stars(oracle.u16_to_f32(frame), 5)
+    assert len(want) > 3000
+    assert np.float32(info.threshold) == np.float32(oinfo.threshold) and info.ncomponents == oinfo.ncomponents
+    same_stars(got, want)
