@@ -177,7 +177,7 @@ def main():
     ap.add_argument("--height", type=int, default=4000)
     ap.add_argument("--lights", type=int, default=50)
     ap.add_argument("--ncal", type=int, default=10)
-    ap.add_argument("--slots", type=int, default=8)
+    ap.add_argument("--slots", type=int, default=10)
     ap.add_argument("--cpu-lights", type=int, default=0, help="lights in the CPU sample (0 = host cores)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")

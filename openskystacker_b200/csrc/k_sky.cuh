@@ -107,6 +107,26 @@ static const uint32_t kGaussBits[16] = {
 // HBM traffic: gray read once (4 B/px), stars written once (4 B/px).  About 120 non-fusable
 // fp32 operations per pixel make this kernel FP32-pipe bound, not HBM bound; the register
 // windows keep shared-memory traffic (22 words/px) below the FP32 time.
+// Packed fp32x2 arithmetic (Blackwell FMUL2 / FADD2): two IEEE-rounded fp32 operations per issue slot.
+// Only products and the symmetric pair sums are packed; every accumulation stays a scalar add.rn —
+// ptxas contracts mul.f32x2 + add.f32x2 into FFMA2 even with explicit .rn, which would break the
+// bit-exact operation order, while it leaves FMUL2 followed by scalar FADD alone (checked in SASS).
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t mul2_bcast(float k, f32x2_t b)
+{
+    f32x2_t r, kk;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(kk) : "f"(k));
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(kk), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2_t add2(f32x2_t a, f32x2_t b)
+{
+    f32x2_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2_t v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+
 #define SKY_TX 64
 #define SKY_TY 128
 #define SKY_R 15
@@ -160,12 +180,16 @@ k_sky_sub_stats(const float *__restrict__ gray, long long strideGray, const floa
             }
         }
         __syncthreads();
-        for (int r = wid; r < SKY_AY; r += 8) {
-            const ResizeTap b = trow[r];
+        // `up` is stored with rows interleaved in pairs: up2[rp][c] = (up[2rp][c], up[2rp+1][c]), the operand
+        // layout of the packed row filter below
+        for (int rp = wid; rp < SKY_AY / 2; rp += 8) {
+            const ResizeTap b = trow[2 * rp], d = trow[2 * rp + 1];
             const float *h0 = hrow + (b.i0 - r_lo) * SKY_UP_LD, *h1 = hrow + (b.i1 - r_lo) * SKY_UP_LD;
-            float *dst = up + r * SKY_UP_LD;
+            const float *g0 = hrow + (d.i0 - r_lo) * SKY_UP_LD, *g1 = hrow + (d.i1 - r_lo) * SKY_UP_LD;
+            float2 *dst = (float2 *)up + rp * SKY_UP_LD;
 #pragma unroll
-            for (int c = lane; c < SKY_AX; c += 32) dst[c] = lerp2(h0[c], b.w0, h1[c], b.w1);
+            for (int c = lane; c < SKY_AX; c += 32)
+                dst[c] = make_float2(lerp2(h0[c], b.w0, h1[c], b.w1), lerp2(g0[c], d.w0, g1[c], d.w1));
         }
     } else { // pathological geometry (tiny low-res grid folded many times): direct evaluation
         for (int i = tid; i < SKY_AY * SKY_AX; i += 256) {
@@ -174,27 +198,34 @@ k_sky_sub_stats(const float *__restrict__ gray, long long strideGray, const floa
             const float *r0 = L + (long long)b.i0 * lw, *r1 = L + (long long)b.i1 * lw;
             float h0 = lerp2(__ldg(r0 + a.i0), a.w0, __ldg(r0 + a.i1), a.w1);
             float h1 = lerp2(__ldg(r1 + a.i0), a.w0, __ldg(r1 + a.i1), a.w1);
-            up[r * SKY_UP_LD + c] = lerp2(h0, b.w0, h1, b.w1);
+            up[((r >> 1) * SKY_UP_LD + c) * 2 + (r & 1)] = lerp2(h0, b.w0, h1, b.w1);
         }
     }
     __syncthreads();
 
-    // phase 2: rf[r][4gx .. 4gx+3] from up[r][4gx .. 4gx+33]
-    for (int i = tid; i < SKY_AY * (SKY_TX / 4); i += 256) {
-        const int r = i >> 4, gx = i & 15;
-        const float4 *src = (const float4 *)(up + r * SKY_UP_LD + 4 * gx);
-        float w[36];
+    // phase 2: rows (2rp, 2rp+1), columns 4gx .. 4gx+3 of rf from the 36-column window of the row pair
+    for (int i = tid; i < (SKY_AY / 2) * (SKY_TX / 4); i += 256) {
+        const int rp = i >> 4, gx = i & 15;
+        const ulonglong2 *src = (const ulonglong2 *)((const float2 *)up + rp * SKY_UP_LD + 4 * gx);
+        f32x2_t w[36];
 #pragma unroll
-        for (int q = 0; q < 9; q++) { float4 v = src[q]; w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w; }
-        float o[4];
+        for (int q = 0; q < 18; q++) { ulonglong2 v = src[q]; w[2 * q] = v.x; w[2 * q + 1] = v.y; }
+        float o0[4], o1[4];
 #pragma unroll
         for (int e = 0; e < 4; e++) {
-            float s = __fmul_rn(c_gauss[0], w[e]);
+            float a, b;
+            unpack2(mul2_bcast(c_gauss[0], w[e]), a, b);
 #pragma unroll
-            for (int j = 1; j < 31; j++) s = __fadd_rn(s, __fmul_rn(c_gauss[j], w[e + j]));
-            o[e] = s;
+            for (int j = 1; j < 31; j++) {
+                float x, y;
+                unpack2(mul2_bcast(c_gauss[j], w[e + j]), x, y);
+                a = __fadd_rn(a, x);
+                b = __fadd_rn(b, y);
+            }
+            o0[e] = a; o1[e] = b;
         }
-        ((float4 *)(rf + r * SKY_TX + 4 * gx))[0] = make_float4(o[0], o[1], o[2], o[3]);
+        ((float4 *)(rf + (2 * rp) * SKY_TX + 4 * gx))[0] = make_float4(o0[0], o0[1], o0[2], o0[3]);
+        ((float4 *)(rf + (2 * rp + 1) * SKY_TX + 4 * gx))[0] = make_float4(o1[0], o1[1], o1[2], o1[3]);
     }
     __syncthreads();
 
@@ -207,36 +238,42 @@ k_sky_sub_stats(const float *__restrict__ gray, long long strideGray, const floa
     const bool tile_in_image = x0 + SKY_TX <= g.W && y0 + SKY_TY <= g.H;
     const bool tile_in_roi = x0 >= g.roi_x && x0 + SKY_TX <= g.roi_x + g.roi_w && y0 >= g.roi_y && y0 + SKY_TY <= g.roi_y + g.roi_h;
     const bool tile_off_roi = x0 >= g.roi_x + g.roi_w || x0 + SKY_TX <= g.roi_x || y0 >= g.roi_y + g.roi_h || y0 + SKY_TY <= g.roi_y;
-    if (tile_in_image && (tile_in_roi || tile_off_roi)) {
-        for (int i = tid; i < (SKY_TY / 4) * SKY_TX; i += 256) {
-            const int gy = i >> 6, c = i & 63;
-            const long long p = (long long)(y0 + 4 * gy) * g.W + x0 + c;
-            const float *gp = G + p;
-            float gv[4];
+    if (tile_in_image && (tile_in_roi || tile_off_roi) && (g.W & 1) == 0) {
+        // interior tiles: thread = rows 4gy..4gy+3 of the column pair (2cp, 2cp+1); one warp spans the 64 columns
+        const unsigned half = lane < 16 ? 0x0000ffffu : 0xffff0000u; // a 32-px segment = 16 lanes
+        for (int i = tid; i < (SKY_TY / 4) * (SKY_TX / 2); i += 256) {
+            const int gy = i >> 5, cp = i & 31;
+            const long long p = (long long)(y0 + 4 * gy) * g.W + x0 + 2 * cp;
+            float2 gv[4];
 #pragma unroll
-            for (int e = 0; e < 4; e++) gv[e] = __ldg(gp + (long long)e * g.W);
-            const float *q = rf + (4 * gy) * SKY_TX + c;
-            float w[34];
+            for (int e = 0; e < 4; e++) gv[e] = __ldg((const float2 *)(G + p + (long long)e * g.W));
+            const f32x2_t *q = (const f32x2_t *)(rf + (4 * gy) * SKY_TX + 2 * cp);
+            f32x2_t w[34];
 #pragma unroll
-            for (int j = 0; j < 34; j++) w[j] = q[j * SKY_TX];
-            float *sp = S + p;
-            float *mp = SM + (long long)(y0 + 4 * gy) * nseg + ((x0 + c) >> 5);
+            for (int j = 0; j < 34; j++) w[j] = q[j * (SKY_TX / 2)];
+            float *mp = SM + (long long)(y0 + 4 * gy) * nseg + ((x0 + 2 * cp) >> 5);
 #pragma unroll
             for (int e = 0; e < 4; e++) {
-                float sk = __fmul_rn(c_gauss[15], w[e + 15]);
+                float a, b;
+                unpack2(mul2_bcast(c_gauss[15], w[e + 15]), a, b);
 #pragma unroll
-                for (int j = 1; j <= 15; j++) sk = __fadd_rn(sk, __fmul_rn(c_gauss[15 + j], __fadd_rn(w[e + 15 + j], w[e + 15 - j])));
-                const float v = __fsub_rn(gv[e], sk);
-                sp[(long long)e * g.W] = v;
-                if (tile_in_roi) {
-                    double d = (double)v;
-                    sum += d;
-                    sq += d * d;
+                for (int j = 1; j <= 15; j++) {
+                    float x, y;
+                    unpack2(mul2_bcast(c_gauss[15 + j], add2(w[e + 15 + j], w[e + 15 - j])), x, y);
+                    a = __fadd_rn(a, x);
+                    b = __fadd_rn(b, y);
                 }
-                unsigned key = __float_as_uint(v);
+                const float va = __fsub_rn(gv[e].x, a), vb = __fsub_rn(gv[e].y, b);
+                *(float2 *)(S + p + (long long)e * g.W) = make_float2(va, vb);
+                if (tile_in_roi) {
+                    double da = (double)va, db = (double)vb;
+                    sum += da; sq += da * da;
+                    sum += db; sq += db * db;
+                }
+                unsigned key = __float_as_uint(fmaxf(va, vb));
                 key ^= (unsigned)((int)key >> 31) | 0x80000000u;
-                key = __reduce_max_sync(0xffffffffu, key);
-                if (lane == 0) {
+                key = __reduce_max_sync(half, key);
+                if ((lane & 15) == 0) {
                     key ^= (key & 0x80000000u) ? 0x80000000u : 0xffffffffu;
                     mp[(long long)e * nseg] = __uint_as_float(key);
                 }
