@@ -158,6 +158,11 @@ OSS_API int oss_detect_stars(oss_ctx *ctx, const void *frame, int mem, int thres
 OSS_API int oss_detect_stars_batch(oss_ctx *ctx, const void *const *frames, int n, int mem,
                                    int threshold, int32_t *counts);
 
+/* Threshold sweep of the -s mode on one frame (config: "star-detect-only threshold sweep 1-100"): the sky
+ * background, subtraction and sigma are computed once, thresholding + components + deblending per
+ * threshold.  counts[i] = number of stars at threshold t_first + i (-1 = workspace overflow). */
+OSS_API int oss_detect_sweep(oss_ctx *ctx, const void *frame, int mem, int t_first, int t_last, int32_t *counts);
+
 /* ---- alignment only: generateTriangleList + findMatches + findTransform (focas.cpp) -----
  * xy are interleaved int32 (x0,y0,x1,y1,...) star lists in detection order; only the first
  * 40 of each are used (focas.cpp:7-8).  matches_out (may be NULL) receives 3 rows of 120

@@ -80,6 +80,7 @@ _SIGS = {
     "oss_result_device_ptr": (C.c_void_p, [C.c_void_p]),
     "oss_detect_stars": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(DetectInfo)]),
     "oss_detect_stars_batch": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "oss_detect_sweep": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "oss_align_lists": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                   C.c_void_p, C.c_void_p, C.c_void_p]),
     "oss_warp_affine": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -279,6 +280,12 @@ class Engine:
         ptrs, keep = self._ptrs(frames, mem)
         counts = np.zeros(len(frames), np.int32)
         self._ck(self._L.oss_detect_stars_batch(self._h, ptrs, len(frames), mem, threshold, _ptr(counts)))
+        return counts
+
+    def detect_sweep(self, frame, t_first, t_last):
+        frame = self._frame(frame)
+        counts = np.zeros(t_last - t_first + 1, np.int32)
+        self._ck(self._L.oss_detect_sweep(self._h, _ptr(frame), HOST, t_first, t_last, _ptr(counts)))
         return counts
 
     def align_lists(self, xy_ref, xy_tgt):

@@ -156,7 +156,7 @@ void ImageStacker::process(int tolerance, int threads)
         if (st) error(st == OSS_E_NO_ALIGNED ? oss_status_string(st) : oss_last_error(ctx));
         return st == 0;
     };
-    const int slots = 8;
+    const int slots = 10;
     if (!check(oss_set_geometry(ctx, ref.width, ref.height, ref.channels, (int)ref.sample, slots))) return;
     const size_t frame_bytes = ref.bytes();
     const int hw = (int)std::max(1u, std::thread::hardware_concurrency());
@@ -164,7 +164,7 @@ void ImageStacker::process(int tolerance, int threads)
 
     // two sets of pinned staging frames: one being decoded while the other feeds the GPU
     d->releasePinned();
-    void *stage[2][8];
+    void *stage[2][10];
     for (int s = 0; s < 2; s++)
         for (int i = 0; i < slots; i++) {
             stage[s][i] = oss_host_alloc(frame_bytes);

@@ -566,6 +566,8 @@ static int stage_frames(oss_ctx *c, const void *const *frames, int n, int mem, F
     return OSS_OK;
 }
 
+static int run_detect_tail(oss_ctx *c, int n, int threshold);
+
 // calibrate (optional) + full star detection for n frames sitting in fp; results in ws slots 0..n-1
 static int run_detect(oss_ctx *c, const FramePtrs &fp, int n, bool use_masters, int threshold, int stage_set)
 {
@@ -581,6 +583,15 @@ static int run_detect(oss_ctx *c, const FramePtrs &fp, int n, bool use_masters, 
     LAUNCH("sky_sub_stats", k_sky_sub_stats, dim3((g.W + SKY_TX - 1) / SKY_TX, (g.H + SKY_TY - 1) / SKY_TY, n), 256, kSkySmemBytes,
            w.gray, strideGray, w.med, w.strideLo, g.lw, c->ux, c->uy, w.stars, w.strideP, w.segmax, w.strideSeg, g.nseg,
            w.partials, w.stridePart, g);
+    return run_detect_tail(c, n, threshold);
+}
+
+// threshold -> candidates -> components -> stars, from the sky-subtracted planes already in the work space
+static int run_detect_tail(oss_ctx *c, int n, int threshold)
+{
+    Workspace &w = c->ws;
+    const Geom &g = c->g;
+    int r;
     LAUNCH("finalize_stats", k_finalize_stats, n, 256, 0, w.partials, w.stridePart, w.stat_blocks, w.ds, threshold, g);
     const long long nsegs = w.strideSeg;
     const int segblocks = (int)((nsegs + 255) / 256);
@@ -931,6 +942,28 @@ int oss_detect_stars_batch(oss_ctx *c, const void *const *frames, int n, int mem
         CK(cudaMemcpyAsync(d.data(), c->ws.ds, sizeof(DetectState) * nb, cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
         for (int i = 0; i < nb; i++) counts[b0 + i] = d[i].overflow ? -1 : d[i].nstars;
+    }
+    return OSS_OK;
+}
+
+// -s threshold sweep (BASELINE config 5): sky background, subtraction and sigma once, then
+// thresholding + components + deblending per threshold.  counts[i] = stars at t_first + i.
+int oss_detect_sweep(oss_ctx *c, const void *frame, int mem, int t_first, int t_last, int32_t *counts)
+{
+    USE_PIPE0();
+    if (!frame || !counts || t_first < 1 || t_last < t_first) return fail(c, OSS_E_ARG, "bad sweep arguments");
+    FramePtrs fp{};
+    int set;
+    int rc = stage_frames(c, &frame, 1, mem, &fp, &set);
+    if (rc) return rc;
+    rc = run_detect(c, fp, 1, false, t_first, set);
+    if (rc) return rc;
+    for (int t = t_first; t <= t_last; t++) {
+        if (t > t_first) { rc = run_detect_tail(c, 1, t); if (rc) return rc; }
+        DetectState d;
+        CK(cudaMemcpyAsync(&d, c->ws.ds, sizeof d, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        counts[t - t_first] = d.overflow ? -1 : d.nstars;
     }
     return OSS_OK;
 }

@@ -155,6 +155,17 @@ def test_detect_rgb_u16_matches_cli_star_count(eng):
     assert counts[1] == len(oracle.get_stars(oracle.u16_to_f32(synth.light(f, 1, 3)), 20)[0])
 
 
+def test_threshold_sweep_matches_per_threshold_detection(eng):
+    w, h = 600, 400
+    eng.set_geometry(w, h, 1, np.float32, 1)
+    g = blob_image(w, h, 80, seed=11)
+    ts = list(range(1, 41))
+    counts = eng.detect_sweep(g, ts[0], ts[-1])
+    for t in (1, 2, 5, 13, 20, 40):
+        assert counts[t - 1] == len(oracle.get_stars(g, t)[0])
+    assert counts[0] > counts[-1]
+
+
 # ------------------------------------------------------------------------------- K7
 def test_alignment_matches_oracle(eng):
     eng.set_geometry(64, 64, 1, np.float32, 1)
