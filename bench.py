@@ -42,36 +42,46 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks + throttle reasons during the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons DURING the timed region, polled through NVML every ~2 ms
+    (the timed region is tens of milliseconds: too short for `nvidia-smi -lms`)."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag, self.proc = index, [], False, None
+        self.index, self.sm, self.reasons, self.max_mhz, self.stop_flag = index, [], set(), None, False
+        self.nv = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
 
     def run(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            for line in self.proc.stdout:
-                if self.stop_flag:
-                    break
-                self.rows.append([x.strip() for x in line.split(",")])
-        except Exception:
-            pass
+        nv = self.nv
+        if nv is None:
+            return
+        names = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                 "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                 "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for n, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(n)
+            except Exception:
+                break
+            time.sleep(0.002)
 
     def finish(self):
         self.stop_flag = True
-        if self.proc:
-            self.proc.terminate()
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+        self.join(timeout=1.0)
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.sm), "source": "NVML polled every 2 ms inside the timed region"}
 
 
 def star_motion(field, index, w, h):
@@ -369,8 +379,17 @@ def main():
     if hbm:
         name = max(hbm, key=lambda k: prof[k][0])
         k = kernels[name]
+        # dram__bytes_read + dram__bytes_write per launch from the committed ncu --set full capture
+        # (profiles/r01_ncu_summary.md), valid for the default shape only: 24 MP RGB16, M = 3, 10 frames per launch
+        ncu_traffic = {"calibrate_gray": 2.307e9 + 3.782e9, "warp_accumulate": 3.183e9 + 0.292e9}
+        default_shape = (W, H, a.slots, a.lights) == (6000, 4000, 10, 50)
+        traffic = ncu_traffic.get(name) if default_shape else None
         roof = {"bound": "hbm", "kernel": name, "achieved": k["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                "frac": k["hbm_frac"], "traffic": None, "peak_source": peak_src, "launches": k["launches"],
+                "frac": k["hbm_frac"], "traffic": traffic, "peak_source": peak_src, "launches": k["launches"],
+                "note": ("achieved counts SURVEY section 8(d)'s algorithmic bytes (masters re-read for every frame: 58 B/px); the kernel "
+                         "keeps the masters in registers across the frames of a launch and really moves `traffic` bytes, which is why "
+                         "frac can exceed 1; traffic / launch time is the physical DRAM rate") if name == "calibrate_gray" else None,
+                "physical_gbs": (traffic / a.slots / (k["us_per_frame"] * 1e-6) / 1e9) if traffic else None,
                 "avg_launch_ms": k["avg_launch_ms"], "algorithmic_bytes_per_launch": per_frame[name] * min(a.slots, a.lights),
                 "measured": "CUDA events around every launch on the launching stream, one extra serial step (1 pipeline) of the "
                             "same job inside this run; the timed region overlaps 3 streams",
