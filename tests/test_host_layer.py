@@ -114,6 +114,31 @@ def test_cli_argument_errors(host, tmp_path):
     assert r.returncode == 1 and "must be an integer between 1 and 100" in r.stdout
 
 
+def test_cli_reports_the_reference_errors_before_touching_the_gpu(host, tmp_path):
+    """Type and size validation (imagestacker.cpp:236-258) happen on file headers, before any device work."""
+    a = np.zeros((20, 30, 3), np.uint16)
+    cv2.imwrite(str(tmp_path / "ref.tif"), a)
+    cv2.imwrite(str(tmp_path / "ok.tif"), a)
+    cv2.imwrite(str(tmp_path / "small.tif"), a[:10])
+    (tmp_path / "l.fits").write_bytes(b"SIMPLE")
+    run = lambda lst: subprocess.run([CLI, "-f", lst, "-o", str(tmp_path / "o")], capture_output=True, text=True)
+    lst = write_list(tmp_path, [{"filename": "ref.tif", "type": "ref", "checked": True},
+                                {"filename": "l.fits", "type": "light", "checked": True}])
+    r = run(lst)
+    assert r.returncode == 1 and "Error: Images must be the same type." in r.stdout
+    lst = write_list(tmp_path, [{"filename": "ref.tif", "type": "ref", "checked": True},
+                                {"filename": "ok.tif", "type": "light", "checked": True},
+                                {"filename": "small.tif", "type": "light", "checked": True}])
+    r = run(lst)
+    assert r.returncode == 1 and "Error: Images must all be the same size." in r.stdout
+    # unchecked frames are ignored (cl/cl.cpp:134-135): the bad one no longer matters, the run proceeds to the GPU stage
+    lst = write_list(tmp_path, [{"filename": "ref.tif", "type": "ref", "checked": True},
+                                {"filename": "ok.tif", "type": "light", "checked": True},
+                                {"filename": "small.tif", "type": "light", "checked": False}])
+    r = run(lst)
+    assert "same size" not in r.stdout
+
+
 @pytest.mark.gpu
 def test_cli_end_to_end_matches_oracle(host, tmp_path):
     w, h = 1000, 700
