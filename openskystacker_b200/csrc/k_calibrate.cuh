@@ -11,7 +11,7 @@
 
 namespace oss {
 
-#define OSS_MAX_BATCH 16
+#define OSS_MAX_BATCH 32
 struct FramePtrs { const void *p[OSS_MAX_BATCH]; };
 
 template <typename T> struct Sample;

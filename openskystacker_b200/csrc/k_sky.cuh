@@ -94,19 +94,26 @@ static const uint32_t kGaussBits[16] = {
     0x3d88bfb5u, 0x3d972180u, 0x3da079edu, 0x3da3b7d6u};
 
 // ---------------------------------------------------------------------------------------
-// K3  sky_sub_stats.  One CTA produces a 64 x 128 tile of stars = gray - sky:
-//   phase 1  upsample the median grid over the tile + 15 px apron (horizontal lerp of the few
-//            low-res rows the tile touches, then vertical lerp), with the Gaussian's
-//            BORDER_REFLECT_101 applied to the FULL-RES coordinates;
-//   phase 2  31-tap row filter, taps accumulated k = 0..30 in order; each thread makes 4
-//            neighbouring outputs from one 36-float register window (9 LDS.128);
-//   phase 3  column filter as centre + 15 symmetric pairs, 4 vertically adjacent outputs per
-//            thread from a 34-float window; subtract from gray; write; fp64 sum / sum of
-//            squares over the statistics ROI; per-32-px-segment maximum (lets the
-//            thresholding pass skip empty segments).
-// HBM traffic: gray read once (4 B/px), stars written once (4 B/px).  About 120 non-fusable
-// fp32 operations per pixel make this kernel FP32-pipe bound, not HBM bound; the register
-// windows keep shared-memory traffic (22 words/px) below the FP32 time.
+// K3  sky_sub_stats, marching form.  One CTA owns a strip of SKY_W = 64 output columns and a
+// segment of rows [ya, yb) of one frame and walks down it in steps of SKY_H = 32 rows.  Per step b:
+//   phase 1  horizontal lerp of the low-res rows that are new for this step ("hrow" ring, keyed by
+//            low-res row & 15), read from the segment's low-res patch staged in shared memory once;
+//   phase 2  vertical lerp -> `up2`, the upsampled sky over the step's 32 rows x (64 + 2*15) columns,
+//            rows interleaved in pairs (operand layout of the packed row filter); the Gaussian's
+//            BORDER_REFLECT_101 is applied to the FULL-RES coordinates of rows and columns;
+//            meanwhile cp.async fetches the gray tile of the output block finished in phase 4 and
+//            warp 0 looks up the next step's row taps;
+//   phase 3  31-tap row filter, taps accumulated k = 0..30 in order; a thread makes 2 rows x 4
+//            columns from one 36-wide register window of row pairs; results go to a ring of
+//            3 x 32 row-filtered rows (+ a mirror of the first block so windows never wrap);
+//   phase 4  column filter (centre + 15 symmetric pairs) of the PREVIOUS block, whose 15-row lower
+//            apron has just been produced: 4 rows x 2 columns per thread from a 34-row window;
+//            subtract from gray; write; fp64 sum / sum of squares over the statistics ROI;
+//            per-32-px-segment maximum (lets the thresholding pass skip empty segments).
+// Marching removes the vertical apron of a tiled design (each row is upsampled and row-filtered
+// once per strip instead of 1.23x) and every dependent global load from the steady state.
+// HBM traffic: gray read once (4 B/px), stars written once (4 B/px).  About 112 non-fusable
+// fp32 operations per pixel make this kernel FP32-pipe bound, not HBM bound.
 // Packed fp32x2 arithmetic (Blackwell FMUL2 / FADD2): two IEEE-rounded fp32 operations per issue slot.
 // Only products and the symmetric pair sums are packed; every accumulation stays a scalar add.rn —
 // ptxas contracts mul.f32x2 + add.f32x2 into FFMA2 even with explicit .rn, which would break the
@@ -127,215 +134,285 @@ __device__ __forceinline__ f32x2_t add2(f32x2_t a, f32x2_t b)
 }
 __device__ __forceinline__ void unpack2(f32x2_t v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
 
-#define SKY_TX 64
-#define SKY_TY 128
-#define SKY_R 15
-#define SKY_AX (SKY_TX + 2 * SKY_R) // 94 columns of apron
-#define SKY_AY (SKY_TY + 2 * SKY_R) // 158 rows of apron
-#define SKY_UP_LD 100               // 36-float windows starting at 4*gx stay inside the row
-#define SKY_HROWS 40                // low-res rows a tile may touch (158/8 + reflections)
-constexpr int kSkySmemBytes = (SKY_AY * SKY_UP_LD + SKY_AY * SKY_TX) * 4 + (SKY_AX + SKY_AY) * (int)sizeof(ResizeTap);
+#define SKY_W 64                    // strip width
+#define SKY_H 32                    // rows per step
+#define SKY_R 15                    // Gaussian radius
+#define SKY_UW (SKY_W + 2 * SKY_R)  // 94 upsampled columns per strip
+#define SKY_ULD 100                 // float2 per row pair of up2: 36-wide windows starting at 4*gx stay inside
+#define SKY_HRS 16                  // hrow ring slots
+#define SKY_HLD 96                  // floats per hrow row
+#define SKY_RING (3 * SKY_H)        // row-filtered ring rows; rows [96, 128) mirror rows [0, 32)
+#define SKY_LRC 16                  // low-res patch columns (94/8 + 2 = 14 needed)
+#define SKY_LRR 144                 // low-res patch rows: covers segments of up to 1024 rows
+#define SKY_SEG_MAX 1024            // rows per segment (multiple of SKY_H)
+// a row tap with the hrow-ring offsets of its two low-res rows already resolved
+struct SkyRowTap { int o0, o1; float w0, w1; };
+struct SkySmem {
+    float rf[(SKY_RING + SKY_H) * SKY_W];    // 32 KB
+    float2 up2[(SKY_H / 2) * SKY_ULD];       // 12.5 KB
+    float hr[SKY_HRS * SKY_HLD];             // 6 KB
+    float gray[2][SKY_H * SKY_W];            // 16 KB, double-buffered cp.async target
+    float lr[SKY_LRR * SKY_LRC];             // 9 KB
+    ResizeTap tcol[SKY_UW];
+    SkyRowTap trow[2][SKY_H];
+    int blk_lo[2], blk_hi[2];
+    double red[2][8];
+};
+constexpr int kSkySmemBytes = (int)sizeof(SkySmem);
+
+// image of the coordinate interval [va, vb] under reflect101(., n): [lo, hi]
+__device__ __forceinline__ void reflect_range(int va, int vb, int n, int &lo, int &hi)
+{
+    if (va < -(n - 1) || vb > 2 * (n - 1)) { lo = 0; hi = n - 1; return; } // several folds: whole axis
+    const int ra = reflect101(va, n), rb = reflect101(vb, n);
+    lo = (va <= 0 && vb >= 0) ? 0 : min(ra, rb);
+    hi = (va <= n - 1 && vb >= n - 1) ? n - 1 : max(ra, rb);
+}
+
+// column filter + subtraction + statistics + segment maxima of one 32-row output block.
+// MODE 0: block inside the image and inside the statistics ROI; 1: inside the image, outside the ROI;
+// 2: anything else (per-pixel tests).
+template <int MODE>
+__device__ __forceinline__ void sky_column_pass(const SkySmem &sm, const float *__restrict__ gtile, int ring_row0, int x0, int yblk,
+                                                int tid, float *__restrict__ S, float *__restrict__ SM, int nseg, const Geom &g,
+                                                double &sum, double &sq)
+{
+    const int gy = tid >> 5, cp = tid & 31, lane = cp;
+    const int x = x0 + 2 * cp, y = yblk + 4 * gy;
+    const f32x2_t *q = (const f32x2_t *)(sm.rf + (ring_row0 + 4 * gy + 1) * SKY_W + 2 * cp);
+    f32x2_t w[34];
+#pragma unroll
+    for (int j = 0; j < 34; j++) w[j] = q[j * (SKY_W / 2)];
+    const float2 *gq = (const float2 *)(gtile + (4 * gy) * SKY_W + 2 * cp);
+    float *sp = S + (long long)y * g.W + x;
+    float *mp = SM + (long long)y * nseg + (x0 >> 5); // warp-uniform: the two segments of this warp's row
+    const bool seg2 = (x0 >> 5) + 1 < nseg;
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+        float a, b;
+        unpack2(mul2_bcast(c_gauss[15], w[e + 15]), a, b);
+#pragma unroll
+        for (int j = 1; j <= 15; j++) {
+            float u, v;
+            unpack2(mul2_bcast(c_gauss[15 + j], add2(w[e + 15 + j], w[e + 15 - j])), u, v);
+            a = __fadd_rn(a, u);
+            b = __fadd_rn(b, v);
+        }
+        const float2 gv = gq[e * (SKY_W / 2)];
+        float va = __fsub_rn(gv.x, a), vb = __fsub_rn(gv.y, b);
+        if (MODE < 2) {
+            *(float2 *)(sp + e * g.W) = make_float2(va, vb);
+            if (MODE == 0) {
+                const double da = (double)va, db = (double)vb;
+                sum += da; sq = __fma_rn(da, da, sq); // da*da is exact in fp64: same value as sq + da*da
+                sum += db; sq = __fma_rn(db, db, sq);
+            }
+        } else {
+            const bool row_ok = y + e < g.H, in_y = y + e >= g.roi_y && y + e < g.roi_y + g.roi_h;
+            const bool oka = row_ok && x < g.W, okb = row_ok && x + 1 < g.W;
+            if (oka) sp[e * g.W] = va; else va = 0.f;
+            if (okb) sp[e * g.W + 1] = vb; else vb = 0.f;
+            if (oka && in_y && x >= g.roi_x && x < g.roi_x + g.roi_w) { const double d = (double)va; sum += d; sq = __fma_rn(d, d, sq); }
+            if (okb && in_y && x + 1 >= g.roi_x && x + 1 < g.roi_x + g.roi_w) { const double d = (double)vb; sum += d; sq = __fma_rn(d, d, sq); }
+        }
+        // segment maxima clamped at 0 (thresholds are >= 0 and consumers only test `> threshold`): for non-negative
+        // floats the unsigned order of the bit patterns is the float order.  Two full-mask REDUX, one per 16-lane half
+        // (a partial-mask reduction compiles to a divergent slow path).
+        const unsigned key = __float_as_uint(fmaxf(fmaxf(va, vb), 0.f));
+        const unsigned klo = __reduce_max_sync(0xffffffffu, lane < 16 ? key : 0u);
+        const unsigned khi = __reduce_max_sync(0xffffffffu, lane < 16 ? 0u : key);
+        if (lane == 0 && (MODE < 2 || y + e < g.H)) {
+            mp[e * nseg] = __uint_as_float(klo);
+            if (MODE < 2 || seg2) mp[e * nseg + 1] = __uint_as_float(khi);
+        }
+    }
+}
 
 __global__ void __launch_bounds__(256, 2)
 k_sky_sub_stats(const float *__restrict__ gray, long long strideGray, const float *__restrict__ med,
                 long long strideLo, int lw, const ResizeTap *__restrict__ ux, const ResizeTap *__restrict__ uy,
                 float *__restrict__ stars, long long strideStars, float *__restrict__ segmax, long long strideSeg,
-                int nseg, double *__restrict__ partials, long long stridePart, Geom g)
+                int nseg, double *__restrict__ partials, long long stridePart, Geom g, int seg_h)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float *up = (float *)smem_raw;                  // [SKY_AY][SKY_UP_LD]
-    float *rf = up + SKY_AY * SKY_UP_LD;            // [SKY_AY][SKY_TX]
-    float *hrow = rf;                               // [SKY_HROWS][SKY_UP_LD], dead before phase 2 writes rf
-    ResizeTap *tcol = (ResizeTap *)(rf + SKY_AY * SKY_TX); // [SKY_AX]
-    ResizeTap *trow = tcol + SKY_AX;                // [SKY_AY]
-    __shared__ int lr_min, lr_max;
-
-    const int tid = threadIdx.x;
-    const int x0 = blockIdx.x * SKY_TX, y0 = blockIdx.y * SKY_TY, f = blockIdx.z;
+    SkySmem &sm = *(SkySmem *)smem_raw;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int x0 = blockIdx.x * SKY_W, ya = blockIdx.y * seg_h, yb = min(ya + seg_h, g.H), f = blockIdx.z;
+    const int nk = (yb - ya + SKY_H - 1) / SKY_H; // output blocks; row-filtered blocks are 0..nk
     const float *L = med + f * strideLo;
-
-    if (tid == 0) { lr_min = 1 << 30; lr_max = -1; }
-    __syncthreads();
-    for (int i = tid; i < SKY_AX + SKY_AY; i += 256) {
-        if (i < SKY_AX) tcol[i] = ux[reflect101(x0 - SKY_R + i, g.W)];
-        else {
-            ResizeTap t = uy[reflect101(y0 - SKY_R + (i - SKY_AX), g.H)];
-            trow[i - SKY_AX] = t;
-            atomicMin(&lr_min, t.i0);
-            atomicMax(&lr_max, t.i1);
-        }
-    }
-    __syncthreads();
-    const int r_lo = lr_min, nlr = lr_max - lr_min + 1;
-
-    // phase 1 (warp w takes rows w, w+8, ...; lanes sweep the 94 columns)
-    const int lane = tid & 31, wid = tid >> 5;
-    if (nlr <= SKY_HROWS) {
-        for (int lr = wid; lr < nlr; lr += 8) {
-            const float *row = L + (long long)(r_lo + lr) * lw;
-#pragma unroll
-            for (int c = lane; c < SKY_AX; c += 32) {
-                ResizeTap a = tcol[c];
-                hrow[lr * SKY_UP_LD + c] = lerp2(__ldg(row + a.i0), a.w0, __ldg(row + a.i1), a.w1);
-            }
-        }
-        __syncthreads();
-        // `up` is stored with rows interleaved in pairs: up2[rp][c] = (up[2rp][c], up[2rp+1][c]), the operand
-        // layout of the packed row filter below
-        for (int rp = wid; rp < SKY_AY / 2; rp += 8) {
-            const ResizeTap b = trow[2 * rp], d = trow[2 * rp + 1];
-            const float *h0 = hrow + (b.i0 - r_lo) * SKY_UP_LD, *h1 = hrow + (b.i1 - r_lo) * SKY_UP_LD;
-            const float *g0 = hrow + (d.i0 - r_lo) * SKY_UP_LD, *g1 = hrow + (d.i1 - r_lo) * SKY_UP_LD;
-            float2 *dst = (float2 *)up + rp * SKY_UP_LD;
-#pragma unroll
-            for (int c = lane; c < SKY_AX; c += 32)
-                dst[c] = make_float2(lerp2(h0[c], b.w0, h1[c], b.w1), lerp2(g0[c], d.w0, g1[c], d.w1));
-        }
-    } else { // pathological geometry (tiny low-res grid folded many times): direct evaluation
-        for (int i = tid; i < SKY_AY * SKY_AX; i += 256) {
-            int r = i / SKY_AX, c = i - r * SKY_AX;
-            ResizeTap a = tcol[c], b = trow[r];
-            const float *r0 = L + (long long)b.i0 * lw, *r1 = L + (long long)b.i1 * lw;
-            float h0 = lerp2(__ldg(r0 + a.i0), a.w0, __ldg(r0 + a.i1), a.w1);
-            float h1 = lerp2(__ldg(r1 + a.i0), a.w0, __ldg(r1 + a.i1), a.w1);
-            up[((r >> 1) * SKY_UP_LD + c) * 2 + (r & 1)] = lerp2(h0, b.w0, h1, b.w1);
-        }
-    }
-    __syncthreads();
-
-    // phase 2: rows (2rp, 2rp+1), columns 4gx .. 4gx+3 of rf from the 36-column window of the row pair
-    for (int i = tid; i < (SKY_AY / 2) * (SKY_TX / 4); i += 256) {
-        const int rp = i >> 4, gx = i & 15;
-        const ulonglong2 *src = (const ulonglong2 *)((const float2 *)up + rp * SKY_UP_LD + 4 * gx);
-        f32x2_t w[36];
-#pragma unroll
-        for (int q = 0; q < 18; q++) { ulonglong2 v = src[q]; w[2 * q] = v.x; w[2 * q + 1] = v.y; }
-        float o0[4], o1[4];
-#pragma unroll
-        for (int e = 0; e < 4; e++) {
-            float a, b;
-            unpack2(mul2_bcast(c_gauss[0], w[e]), a, b);
-#pragma unroll
-            for (int j = 1; j < 31; j++) {
-                float x, y;
-                unpack2(mul2_bcast(c_gauss[j], w[e + j]), x, y);
-                a = __fadd_rn(a, x);
-                b = __fadd_rn(b, y);
-            }
-            o0[e] = a; o1[e] = b;
-        }
-        ((float4 *)(rf + (2 * rp) * SKY_TX + 4 * gx))[0] = make_float4(o0[0], o0[1], o0[2], o0[3]);
-        ((float4 *)(rf + (2 * rp + 1) * SKY_TX + 4 * gx))[0] = make_float4(o1[0], o1[1], o1[2], o1[3]);
-    }
-    __syncthreads();
-
-    // phase 3: out[4gy .. 4gy+3][c] from rf[4gy .. 4gy+33][c]
-    double sum = 0.0, sq = 0.0;
     const float *G = gray + f * strideGray;
     float *S = stars + f * strideStars;
     float *SM = segmax + f * strideSeg;
-    // tile-uniform classification: interior tiles skip every per-pixel bounds / ROI test
-    const bool tile_in_image = x0 + SKY_TX <= g.W && y0 + SKY_TY <= g.H;
-    const bool tile_in_roi = x0 >= g.roi_x && x0 + SKY_TX <= g.roi_x + g.roi_w && y0 >= g.roi_y && y0 + SKY_TY <= g.roi_y + g.roi_h;
-    const bool tile_off_roi = x0 >= g.roi_x + g.roi_w || x0 + SKY_TX <= g.roi_x || y0 >= g.roi_y + g.roi_h || y0 + SKY_TY <= g.roi_y;
-    if (tile_in_image && (tile_in_roi || tile_off_roi) && (g.W & 1) == 0) {
-        // interior tiles: thread = rows 4gy..4gy+3 of the column pair (2cp, 2cp+1); one warp spans the 64 columns
-        const unsigned half = lane < 16 ? 0x0000ffffu : 0xffff0000u; // a 32-px segment = 16 lanes
-        for (int i = tid; i < (SKY_TY / 4) * (SKY_TX / 2); i += 256) {
-            const int gy = i >> 5, cp = i & 31;
-            const long long p = (long long)(y0 + 4 * gy) * g.W + x0 + 2 * cp;
-            float2 gv[4];
-#pragma unroll
-            for (int e = 0; e < 4; e++) gv[e] = __ldg((const float2 *)(G + p + (long long)e * g.W));
-            const f32x2_t *q = (const f32x2_t *)(rf + (4 * gy) * SKY_TX + 2 * cp);
-            f32x2_t w[34];
-#pragma unroll
-            for (int j = 0; j < 34; j++) w[j] = q[j * (SKY_TX / 2)];
-            float *mp = SM + (long long)(y0 + 4 * gy) * nseg + ((x0 + 2 * cp) >> 5);
-#pragma unroll
-            for (int e = 0; e < 4; e++) {
-                float a, b;
-                unpack2(mul2_bcast(c_gauss[15], w[e + 15]), a, b);
-#pragma unroll
-                for (int j = 1; j <= 15; j++) {
-                    float x, y;
-                    unpack2(mul2_bcast(c_gauss[15 + j], add2(w[e + 15 + j], w[e + 15 - j])), x, y);
-                    a = __fadd_rn(a, x);
-                    b = __fadd_rn(b, y);
-                }
-                const float va = __fsub_rn(gv[e].x, a), vb = __fsub_rn(gv[e].y, b);
-                *(float2 *)(S + p + (long long)e * g.W) = make_float2(va, vb);
-                if (tile_in_roi) {
-                    double da = (double)va, db = (double)vb;
-                    sum += da; sq += da * da;
-                    sum += db; sq += db * db;
-                }
-                unsigned key = __float_as_uint(fmaxf(va, vb));
-                key ^= (unsigned)((int)key >> 31) | 0x80000000u;
-                key = __reduce_max_sync(half, key);
-                if ((lane & 15) == 0) {
-                    key ^= (key & 0x80000000u) ? 0x80000000u : 0xffffffffu;
-                    mp[(long long)e * nseg] = __uint_as_float(key);
-                }
-            }
-        }
-    } else
-    for (int i = tid; i < (SKY_TY / 4) * SKY_TX; i += 256) {
-        const int gy = i >> 6, c = i & 63;
-        const int x = x0 + c;
-        // gray first: its HBM latency hides behind the window loads and ~190 fp32 operations
-        float gv[4];
-#pragma unroll
-        for (int e = 0; e < 4; e++) {
-            const int y = y0 + 4 * gy + e;
-            gv[e] = (x < g.W && y < g.H) ? __ldg(G + (long long)y * g.W + x) : 0.f;
-        }
-        const float *q = rf + (4 * gy) * SKY_TX + c;
-        float w[34];
-#pragma unroll
-        for (int j = 0; j < 34; j++) w[j] = q[j * SKY_TX];
-#pragma unroll
-        for (int e = 0; e < 4; e++) {
-            float s = __fmul_rn(c_gauss[15], w[e + 15]);
-#pragma unroll
-            for (int j = 1; j <= 15; j++) s = __fadd_rn(s, __fmul_rn(c_gauss[15 + j], __fadd_rn(w[e + 15 + j], w[e + 15 - j])));
-            const int y = y0 + 4 * gy + e;
-            float v = -INFINITY;
-            if (x < g.W && y < g.H) {
-                v = __fsub_rn(gv[e], s);
-                S[(long long)y * g.W + x] = v;
-                if (x >= g.roi_x && x < g.roi_x + g.roi_w && y >= g.roi_y && y < g.roi_y + g.roi_h) {
-                    double d = (double)v;
-                    sum += d;
-                    sq += d * d;
-                }
-            }
-            // warp maximum through one REDUX on an order-preserving integer image of the float
-            unsigned key = __float_as_uint(v);
-            key ^= (unsigned)((int)key >> 31) | 0x80000000u;
-            key = __reduce_max_sync(0xffffffffu, key);
-            if ((tid & 31) == 0 && y < g.H && (x >> 5) < nseg) {
-                key ^= (key & 0x80000000u) ? 0x80000000u : 0xffffffffu;
-                SM[(long long)y * nseg + (x >> 5)] = __uint_as_float(key);
-            }
+
+    // row taps of block bb (rows ya - 16 + 32 bb ...), by warp 0
+    auto load_row_taps = [&](int bb) {
+        const ResizeTap t = uy[reflect101(ya - 16 + SKY_H * bb + lane, g.H)];
+        SkyRowTap r;
+        r.o0 = (t.i0 & (SKY_HRS - 1)) * SKY_HLD; r.o1 = (t.i1 & (SKY_HRS - 1)) * SKY_HLD; r.w0 = t.w0; r.w1 = t.w1;
+        sm.trow[bb & 1][lane] = r;
+        const int lo = __reduce_min_sync(0xffffffffu, t.i0), hi = __reduce_max_sync(0xffffffffu, t.i1);
+        if (lane == 0) { sm.blk_lo[bb & 1] = lo; sm.blk_hi[bb & 1] = hi; }
+    };
+
+    // ---- prologue: column taps, first block's row taps, the segment's low-res patch
+    for (int i = tid; i < SKY_UW; i += 256) sm.tcol[i] = ux[reflect101(x0 - SKY_R + i, g.W)];
+    if (wid == 0) load_row_taps(0);
+    int xlo, xhi, ylo, yhi;
+    reflect_range(x0 - SKY_R, x0 + SKY_W + SKY_R - 1, g.W, xlo, xhi);
+    reflect_range(ya - 16, ya - 16 + SKY_H * (nk + 1) - 1, g.H, ylo, yhi);
+    const int pc0 = ux[xlo].i0, pc1 = ux[xhi].i1, pr0 = uy[ylo].i0, pr1 = uy[yhi].i1; // taps are monotone
+    const bool patch_ok = pc1 - pc0 < SKY_LRC && pr1 - pr0 < SKY_LRR;
+    if (patch_ok) {
+        const int nrow = pr1 - pr0 + 1, ncol = pc1 - pc0 + 1;
+        for (int i = tid; i < nrow * SKY_LRC; i += 256) {
+            const int r = i >> 4, cc = i & 15;
+            if (cc < ncol) sm.lr[i] = __ldg(L + (long long)(pr0 + r) * lw + pc0 + cc);
         }
     }
+    // low-res source of the hrow pass: the staged patch, or (segments / strips that do not fit) global memory
+    const float *hsrc = patch_ok ? sm.lr - (pr0 * SKY_LRC + pc0) : L;
+    const int hld = patch_ok ? SKY_LRC : lw;
+    __syncthreads();
+
+    int hr_lo = 0, hr_hi = -1; // low-res rows currently valid in the hrow ring (block-uniform)
+    // horizontal lerp of the low-res rows block bb needs and the ring does not hold yet: thread = (column, row parity)
+    auto hrow_pass = [&](int bb) {
+        const int lo = sm.blk_lo[bb & 1], hi = sm.blk_hi[bb & 1]; // hi - lo <= 32/8 + 2 < SKY_HRS (the scale is 8)
+        int first;
+        if (lo >= hr_lo && lo <= hr_hi + 1) { first = max(hr_hi + 1, lo); hr_hi = max(hr_hi, hi); }
+        else { first = lo; hr_lo = lo; hr_hi = hi; }
+        hr_lo = max(hr_lo, hr_hi - (SKY_HRS - 1));
+        const int c = tid & 127;
+        if (c < SKY_UW && first <= hi) {
+            const ResizeTap a = sm.tcol[c];
+            for (int r = first + (tid >> 7); r <= hi; r += 2) {
+                const float *row = hsrc + r * hld;
+                sm.hr[(r & (SKY_HRS - 1)) * SKY_HLD + c] = lerp2(row[a.i0], a.w0, row[a.i1], a.w1);
+            }
+        }
+    };
+    // vertical lerp -> up2 for the 16 row pairs of block bb (warp w: pairs w, w + 8; lanes sweep the 94 columns)
+    auto up_pass = [&](int bb) {
+        const float *hl = sm.hr + lane;
+#pragma unroll
+        for (int it = 0; it < 2; it++) {
+            const int rp = wid + 8 * it;
+            const SkyRowTap t0 = sm.trow[bb & 1][2 * rp], t1 = sm.trow[bb & 1][2 * rp + 1];
+            const float *h0 = hl + t0.o0, *h1 = hl + t0.o1, *g0 = hl + t1.o0, *g1 = hl + t1.o1;
+            float2 *dst = sm.up2 + rp * SKY_ULD + lane;
+            dst[0] = make_float2(lerp2(h0[0], t0.w0, h1[0], t0.w1), lerp2(g0[0], t1.w0, g1[0], t1.w1));
+            dst[32] = make_float2(lerp2(h0[32], t0.w0, h1[32], t0.w1), lerp2(g0[32], t1.w0, g1[32], t1.w1));
+            if (lane < SKY_UW - 64) dst[64] = make_float2(lerp2(h0[64], t0.w0, h1[64], t0.w1), lerp2(g0[64], t1.w0, g1[64], t1.w1));
+        }
+    };
+    // gray tile of output block k -> sm.gray[k & 1] (asynchronously when rows are 16-byte aligned)
+    const bool vec_gray = (g.W & 3) == 0 && x0 + SKY_W <= g.W;
+    const int pr = tid >> 4, pq = tid & 15;
+    const float *gp = G + (long long)(ya + pr) * g.W + x0 + 4 * pq; // this thread's chunk of row pr (and pr + 16) of block 0
+    auto gray_prefetch = [&](int k) {
+        const int y0 = ya + SKY_H * k;
+        float *dst = sm.gray[k & 1];
+        if (vec_gray) {
+            const float *src = gp + (long long)(SKY_H * k) * g.W;
+            const unsigned sa = (unsigned)__cvta_generic_to_shared(dst + pr * SKY_W + 4 * pq);
+            if (y0 + pr < g.H) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(src));
+            if (y0 + pr + 16 < g.H)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa + 16 * SKY_W * 4), "l"(src + 16ll * g.W));
+        } else {
+            for (int i = tid; i < SKY_H * SKY_W; i += 256) {
+                const int r = i >> 6, c = i & 63;
+                dst[i] = (y0 + r < g.H && x0 + c < g.W) ? __ldg(G + (long long)(y0 + r) * g.W + x0 + c) : 0.f;
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    hrow_pass(0);
+    __syncthreads();
+    up_pass(0);
+    if (wid == 0 && nk >= 1) load_row_taps(1);
+
+    const bool strip_in_roi_x = x0 >= g.roi_x && x0 + SKY_W <= g.roi_x + g.roi_w;
+    const bool strip_off_roi_x = x0 >= g.roi_x + g.roi_w || x0 + SKY_W <= g.roi_x;
+    double sum = 0.0, sq = 0.0;
+    int slot = 0; // ring block that step b writes = b % 3
+
+    // Two barriers per step.  Between B and C: row filter of block b + hrow of block b+1.  After C: column pass of
+    // block b-1, then (no barrier needed) up2 / row taps / gray prefetch for the next step.
+    for (int b = 0; b <= nk; b++) {
+        __syncthreads(); // B: up2(b), row taps of b+1 visible; everyone left the column pass of b-2
+        {   // rows (2rp, 2rp+1), columns 4gx .. 4gx+3 of this step's row-filtered block
+            const int rp = tid >> 4, gx = tid & 15;
+            const ulonglong2 *src = (const ulonglong2 *)(sm.up2 + rp * SKY_ULD + 4 * gx);
+            f32x2_t w[36];
+#pragma unroll
+            for (int q = 0; q < 18; q++) { ulonglong2 v = src[q]; w[2 * q] = v.x; w[2 * q + 1] = v.y; }
+            float o0[4], o1[4];
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                float a0, a1;
+                unpack2(mul2_bcast(c_gauss[0], w[e]), a0, a1);
+#pragma unroll
+                for (int j = 1; j < 31; j++) {
+                    float u, v;
+                    unpack2(mul2_bcast(c_gauss[j], w[e + j]), u, v);
+                    a0 = __fadd_rn(a0, u);
+                    a1 = __fadd_rn(a1, v);
+                }
+                o0[e] = a0; o1[e] = a1;
+            }
+            float *d0 = sm.rf + (slot * SKY_H + 2 * rp) * SKY_W + 4 * gx;
+            ((float4 *)d0)[0] = make_float4(o0[0], o0[1], o0[2], o0[3]);
+            ((float4 *)(d0 + SKY_W))[0] = make_float4(o1[0], o1[1], o1[2], o1[3]);
+            if (slot == 0) { // mirror of block 0 behind block 2: 34-row windows never wrap
+                ((float4 *)(d0 + SKY_RING * SKY_W))[0] = make_float4(o0[0], o0[1], o0[2], o0[3]);
+                ((float4 *)(d0 + (SKY_RING + 1) * SKY_W))[0] = make_float4(o1[0], o1[1], o1[2], o1[3]);
+            }
+        }
+        if (b < nk) hrow_pass(b + 1);
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncthreads(); // C: row-filtered block b, hrow rows of b+1 and the gray tile of b-1 are visible
+        if (b >= 1) {
+            const int yblk = ya + SKY_H * (b - 1);
+            const int ring_row0 = (slot == 0 ? 2 : slot - 1) * SKY_H; // block b - 1
+            const float *gtile = sm.gray[(b - 1) & 1];
+            const bool in_image = x0 + SKY_W <= g.W && yblk + SKY_H <= g.H && (g.W & 1) == 0;
+            const bool in_roi = strip_in_roi_x && yblk >= g.roi_y && yblk + SKY_H <= g.roi_y + g.roi_h;
+            const bool off_roi = strip_off_roi_x || yblk >= g.roi_y + g.roi_h || yblk + SKY_H <= g.roi_y;
+            if (in_image && in_roi) sky_column_pass<0>(sm, gtile, ring_row0, x0, yblk, tid, S, SM, nseg, g, sum, sq);
+            else if (in_image && off_roi) sky_column_pass<1>(sm, gtile, ring_row0, x0, yblk, tid, S, SM, nseg, g, sum, sq);
+            else sky_column_pass<2>(sm, gtile, ring_row0, x0, yblk, tid, S, SM, nseg, g, sum, sq);
+        }
+        if (b < nk) {
+            up_pass(b + 1);
+            if (wid == 0 && b + 2 <= nk) load_row_taps(b + 2);
+            gray_prefetch(b); // consumed by the column pass of the next step
+        }
+        slot = slot == 2 ? 0 : slot + 1;
+    }
     // block reduction of the fp64 partial sums, fixed order
-    __shared__ double sh[2][8];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         sum += __shfl_xor_sync(0xffffffffu, sum, o);
         sq += __shfl_xor_sync(0xffffffffu, sq, o);
     }
-    if ((tid & 31) == 0) { sh[0][tid >> 5] = sum; sh[1][tid >> 5] = sq; }
+    if (lane == 0) { sm.red[0][wid] = sum; sm.red[1][wid] = sq; }
     __syncthreads();
     if (tid == 0) {
         double a = 0.0, b = 0.0;
-        for (int w = 0; w < 8; w++) { a += sh[0][w]; b += sh[1][w]; }
-        long long blk = (long long)blockIdx.y * gridDim.x + blockIdx.x;
+        for (int w = 0; w < 8; w++) { a += sm.red[0][w]; b += sm.red[1][w]; }
+        const long long blk = (long long)blockIdx.y * gridDim.x + blockIdx.x;
         partials[f * stridePart + 2 * blk] = a;
         partials[f * stridePart + 2 * blk + 1] = b;
     }
+}
+
+// rows per segment of the marching kernel: as few segments as keep every one <= SKY_SEG_MAX rows
+static inline int sky_segment_rows(int H)
+{
+    const int nseg = (H + SKY_SEG_MAX - 1) / SKY_SEG_MAX;
+    const int rows = (H + nseg - 1) / nseg;
+    return (rows + SKY_H - 1) / SKY_H * SKY_H;
 }
 
 // sigma, threshold = float(sigma*t*1.5), minPeak = float(sigma*t*2.0)  [stardetector.cpp:125-129]

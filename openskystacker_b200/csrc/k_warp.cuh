@@ -89,8 +89,8 @@ k_warp_accumulate_tiled(const float *__restrict__ cal, long long strideCal, cons
     extern __shared__ __align__(16) unsigned char wsm[];
     float *tiles = (float *)wsm;                                  // [2][WT_ROWS * ROWF]
     int2 *sxy = (int2 *)(tiles + 2 * WT_ROWS * ROWF);             // [2][WT_H]
-    int *valid = (int *)(sxy + 2 * WT_H);                         // [16 + 1]
-    __shared__ WarpFoot sfoot[16];
+    int *valid = (int *)(sxy + 2 * WT_H);                         // [OSS_MAX_BATCH + 1]
+    __shared__ WarpFoot sfoot[OSS_MAX_BATCH];
     const int tid = threadIdx.x, tx = tid & 63, ty = tid >> 6, lane = tid & 31, wid = tid >> 5;
     const int x0 = blockIdx.x * WT_W, y0 = blockIdx.y * WT_H;
     const int x = x0 + tx;
@@ -244,7 +244,7 @@ k_warp_accumulate_tiled(const float *__restrict__ cal, long long strideCal, cons
     }
 }
 
-template <int C> constexpr int warp_tiled_smem() { return 2 * WT_ROWS * WT_COLS * C * 4 + 2 * WT_H * 8 + (16 + 1) * 4; }
+template <int C> constexpr int warp_tiled_smem() { return 2 * WT_ROWS * WT_COLS * C * 4 + 2 * WT_H * 8 + (OSS_MAX_BATCH + 1) * 4; }
 
 // plain copy (keeps the calibrated reference frame, imagestacker.cpp:286)
 __global__ void __launch_bounds__(256)

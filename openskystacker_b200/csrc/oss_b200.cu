@@ -412,7 +412,7 @@ int oss_set_geometry(oss_ctx *c, int W, int H, int C, int sample, int slots)
         Workspace &w = pp.ws;
         w = Workspace{};
         w.strideP = pad64(g.P); w.stridePC = pad64(PC); w.strideLo = lo; w.strideSeg = nsegs;
-        w.stat_blocks = ((W + SKY_TX - 1) / SKY_TX) * ((H + SKY_TY - 1) / SKY_TY);
+        w.stat_blocks = ((W + SKY_W - 1) / SKY_W) * ((H + sky_segment_rows(H) - 1) / sky_segment_rows(H));
         w.stridePart = 2ll * w.stat_blocks;
         long long scan_max = nsegs + 1 > cap ? nsegs + 1 : cap;
         w.strideScan = (scan_max + SCAN_ITEMS - 1) / SCAN_ITEMS + 1;
@@ -580,9 +580,10 @@ static int run_detect(oss_ctx *c, const FramePtrs &fp, int n, bool use_masters, 
            c->dx, c->dy, w.lo, w.strideLo, g.lw, g.lh);
     LAUNCH("median5", k_median5, dim3((g.lw + 31) / 32, (g.lh + 7) / 8, n), 256, 0, w.lo, w.med, w.strideLo, g.lw, g.lh);
     const long long strideGray = g.C == 3 ? w.strideP : w.stridePC;
-    LAUNCH("sky_sub_stats", k_sky_sub_stats, dim3((g.W + SKY_TX - 1) / SKY_TX, (g.H + SKY_TY - 1) / SKY_TY, n), 256, kSkySmemBytes,
+    const int seg_h = sky_segment_rows(g.H);
+    LAUNCH("sky_sub_stats", k_sky_sub_stats, dim3((g.W + SKY_W - 1) / SKY_W, (g.H + seg_h - 1) / seg_h, n), 256, kSkySmemBytes,
            w.gray, strideGray, w.med, w.strideLo, g.lw, c->ux, c->uy, w.stars, w.strideP, w.segmax, w.strideSeg, g.nseg,
-           w.partials, w.stridePart, g);
+           w.partials, w.stridePart, g, seg_h);
     return run_detect_tail(c, n, threshold);
 }
 
