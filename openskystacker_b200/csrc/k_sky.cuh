@@ -138,7 +138,8 @@ __device__ __forceinline__ void unpack2(f32x2_t v, float &lo, float &hi) { asm("
 #define SKY_H 32                    // rows per step
 #define SKY_R 15                    // Gaussian radius
 #define SKY_UW (SKY_W + 2 * SKY_R)  // 94 upsampled columns per strip
-#define SKY_ULD 100                 // float2 per row pair of up2: 36-wide windows starting at 4*gx stay inside
+#define SKY_ULD 102                 // float2 per row pair of up2: 36-wide windows starting at 4*gx stay inside; an ODD number
+                                    // of 16-byte chunks (51), so neighbouring row pairs start 4 banks apart (see the row filter)
 #define SKY_HRS 16                  // hrow ring slots
 #define SKY_HLD 96                  // floats per hrow row
 #define SKY_RING (3 * SKY_H)        // row-filtered ring rows; rows [96, 128) mirror rows [0, 32)
@@ -244,9 +245,9 @@ k_sky_sub_stats(const float *__restrict__ gray, long long strideGray, const floa
     float *S = stars + f * strideStars;
     float *SM = segmax + f * strideSeg;
 
-    // row taps of block bb (rows ya - 16 + 32 bb ...), by warp 0
-    auto load_row_taps = [&](int bb) {
-        const ResizeTap t = uy[reflect101(ya - 16 + SKY_H * bb + lane, g.H)];
+    // row taps of block bb (rows ya - 16 + 32 bb ...), by warp 0: the table lookup is issued a phase early
+    auto fetch_row_tap = [&](int bb) { return uy[reflect101(ya - 16 + SKY_H * bb + lane, g.H)]; };
+    auto publish_row_taps = [&](int bb, const ResizeTap &t) {
         SkyRowTap r;
         r.o0 = (t.i0 & (SKY_HRS - 1)) * SKY_HLD; r.o1 = (t.i1 & (SKY_HRS - 1)) * SKY_HLD; r.w0 = t.w0; r.w1 = t.w1;
         sm.trow[bb & 1][lane] = r;
@@ -256,7 +257,7 @@ k_sky_sub_stats(const float *__restrict__ gray, long long strideGray, const floa
 
     // ---- prologue: column taps, first block's row taps, the segment's low-res patch
     for (int i = tid; i < SKY_UW; i += 256) sm.tcol[i] = ux[reflect101(x0 - SKY_R + i, g.W)];
-    if (wid == 0) load_row_taps(0);
+    if (wid == 0) publish_row_taps(0, fetch_row_tap(0));
     int xlo, xhi, ylo, yhi;
     reflect_range(x0 - SKY_R, x0 + SKY_W + SKY_R - 1, g.W, xlo, xhi);
     reflect_range(ya - 16, ya - 16 + SKY_H * (nk + 1) - 1, g.H, ylo, yhi);
@@ -269,40 +270,50 @@ k_sky_sub_stats(const float *__restrict__ gray, long long strideGray, const floa
             if (cc < ncol) sm.lr[i] = __ldg(L + (long long)(pr0 + r) * lw + pc0 + cc);
         }
     }
-    // low-res source of the hrow pass: the staged patch, or (segments / strips that do not fit) global memory
-    const float *hsrc = patch_ok ? sm.lr - (pr0 * SKY_LRC + pc0) : L;
-    const int hld = patch_ok ? SKY_LRC : lw;
     __syncthreads();
 
     int hr_lo = 0, hr_hi = -1; // low-res rows currently valid in the hrow ring (block-uniform)
-    // horizontal lerp of the low-res rows block bb needs and the ring does not hold yet: thread = (column, row parity)
+    // horizontal lerp of the low-res rows block bb needs and the ring does not hold yet: warps 0..2, thread = column
     auto hrow_pass = [&](int bb) {
         const int lo = sm.blk_lo[bb & 1], hi = sm.blk_hi[bb & 1]; // hi - lo <= 32/8 + 2 < SKY_HRS (the scale is 8)
         int first;
         if (lo >= hr_lo && lo <= hr_hi + 1) { first = max(hr_hi + 1, lo); hr_hi = max(hr_hi, hi); }
         else { first = lo; hr_lo = lo; hr_hi = hi; }
         hr_lo = max(hr_lo, hr_hi - (SKY_HRS - 1));
-        const int c = tid & 127;
-        if (c < SKY_UW && first <= hi) {
-            const ResizeTap a = sm.tcol[c];
-            for (int r = first + (tid >> 7); r <= hi; r += 2) {
-                const float *row = hsrc + r * hld;
-                sm.hr[(r & (SKY_HRS - 1)) * SKY_HLD + c] = lerp2(row[a.i0], a.w0, row[a.i1], a.w1);
+        if (tid < SKY_UW && first <= hi) {
+            const ResizeTap a = sm.tcol[tid];
+            if (patch_ok) {
+                const float *p0 = sm.lr + (first - pr0) * SKY_LRC - pc0;
+                for (int r = first; r <= hi; r++, p0 += SKY_LRC)
+                    sm.hr[(r & (SKY_HRS - 1)) * SKY_HLD + tid] = lerp2(p0[a.i0], a.w0, p0[a.i1], a.w1);
+            } else {
+                for (int r = first; r <= hi; r++) {
+                    const float *row = L + (long long)r * lw;
+                    sm.hr[(r & (SKY_HRS - 1)) * SKY_HLD + tid] = lerp2(__ldg(row + a.i0), a.w0, __ldg(row + a.i1), a.w1);
+                }
             }
         }
     };
-    // vertical lerp -> up2 for the 16 row pairs of block bb (warp w: pairs w, w + 8; lanes sweep the 94 columns)
+    // vertical lerp -> up2 for the 16 row pairs x 47 column pairs of block bb: products packed over the column pair,
+    // sums scalar (lerp2's order); LDS.64 from the hrow ring, one STS.128 per item
     auto up_pass = [&](int bb) {
-        const float *hl = sm.hr + lane;
+        const SkyRowTap *tr = sm.trow[bb & 1];
 #pragma unroll
-        for (int it = 0; it < 2; it++) {
-            const int rp = wid + 8 * it;
-            const SkyRowTap t0 = sm.trow[bb & 1][2 * rp], t1 = sm.trow[bb & 1][2 * rp + 1];
-            const float *h0 = hl + t0.o0, *h1 = hl + t0.o1, *g0 = hl + t1.o0, *g1 = hl + t1.o1;
-            float2 *dst = sm.up2 + rp * SKY_ULD + lane;
-            dst[0] = make_float2(lerp2(h0[0], t0.w0, h1[0], t0.w1), lerp2(g0[0], t1.w0, g1[0], t1.w1));
-            dst[32] = make_float2(lerp2(h0[32], t0.w0, h1[32], t0.w1), lerp2(g0[32], t1.w0, g1[32], t1.w1));
-            if (lane < SKY_UW - 64) dst[64] = make_float2(lerp2(h0[64], t0.w0, h1[64], t0.w1), lerp2(g0[64], t1.w0, g1[64], t1.w1));
+        for (int it = 0; it < 3; it++) {
+            const int i = tid + 256 * it;
+            if (i < (SKY_H / 2) * (SKY_UW / 2)) {
+                const int rp = i / (SKY_UW / 2), c = 2 * (i - rp * (SKY_UW / 2));
+                const SkyRowTap t0 = tr[2 * rp], t1 = tr[2 * rp + 1];
+                const f32x2_t h0 = *(const f32x2_t *)(sm.hr + t0.o0 + c), h1 = *(const f32x2_t *)(sm.hr + t0.o1 + c);
+                const f32x2_t g0 = *(const f32x2_t *)(sm.hr + t1.o0 + c), g1 = *(const f32x2_t *)(sm.hr + t1.o1 + c);
+                float a0, a1, b0, b1, c0, c1, d0, d1;
+                unpack2(mul2_bcast(t0.w0, h0), a0, a1);
+                unpack2(mul2_bcast(t0.w1, h1), b0, b1);
+                unpack2(mul2_bcast(t1.w0, g0), c0, c1);
+                unpack2(mul2_bcast(t1.w1, g1), d0, d1);
+                // (row 2rp, row 2rp+1) of column c, then of column c+1
+                *(float4 *)(sm.up2 + rp * SKY_ULD + c) = make_float4(__fadd_rn(a0, b0), __fadd_rn(c0, d0), __fadd_rn(a1, b1), __fadd_rn(c1, d1));
+            }
         }
     };
     // gray tile of output block k -> sm.gray[k & 1] (asynchronously when rows are 16-byte aligned)
@@ -330,7 +341,7 @@ k_sky_sub_stats(const float *__restrict__ gray, long long strideGray, const floa
     hrow_pass(0);
     __syncthreads();
     up_pass(0);
-    if (wid == 0 && nk >= 1) load_row_taps(1);
+    if (wid == 0 && nk >= 1) publish_row_taps(1, fetch_row_tap(1));
 
     const bool strip_in_roi_x = x0 >= g.roi_x && x0 + SKY_W <= g.roi_x + g.roi_w;
     const bool strip_off_roi_x = x0 >= g.roi_x + g.roi_w || x0 + SKY_W <= g.roi_x;
@@ -341,8 +352,15 @@ k_sky_sub_stats(const float *__restrict__ gray, long long strideGray, const floa
     // block b-1, then (no barrier needed) up2 / row taps / gray prefetch for the next step.
     for (int b = 0; b <= nk; b++) {
         __syncthreads(); // B: up2(b), row taps of b+1 visible; everyone left the column pass of b-2
+        ResizeTap tnext;
+        const bool taps_due = wid == 0 && b + 2 <= nk;
+        if (taps_due) tnext = fetch_row_tap(b + 2); // lands behind the row filter
         {   // rows (2rp, 2rp+1), columns 4gx .. 4gx+3 of this step's row-filtered block
-            const int rp = tid >> 4, gx = tid & 15;
+            // a quarter-warp (8 lanes, one LDS.128 wavefront) = 4 neighbouring column groups x 2 neighbouring row pairs:
+            // the groups start 32 B apart (banks 0,8,16,24) and the odd chunk stride shifts the second row pair by
+            // 4 banks, so the 8 x 16 B of a wavefront cover all 32 banks (a plain (rp, gx) = (tid / 16, tid % 16)
+            // mapping is a 2-way conflict on every window load)
+            const int rp = 2 * wid + ((lane >> 2) & 1), gx = (lane & 3) | ((lane >> 3) << 2);
             const ulonglong2 *src = (const ulonglong2 *)(sm.up2 + rp * SKY_ULD + 4 * gx);
             f32x2_t w[36];
 #pragma unroll
@@ -385,7 +403,7 @@ k_sky_sub_stats(const float *__restrict__ gray, long long strideGray, const floa
         }
         if (b < nk) {
             up_pass(b + 1);
-            if (wid == 0 && b + 2 <= nk) load_row_taps(b + 2);
+            if (taps_due) publish_row_taps(b + 2, tnext);
             gray_prefetch(b); // consumed by the column pass of the next step
         }
         slot = slot == 2 ? 0 : slot + 1;
