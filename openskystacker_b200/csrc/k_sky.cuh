@@ -134,30 +134,38 @@ __device__ __forceinline__ f32x2_t add2(f32x2_t a, f32x2_t b)
 }
 __device__ __forceinline__ void unpack2(f32x2_t v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
 
+#ifndef SKY_CTAS
+#define SKY_CTAS (512 / SKY_NT)      // 16 warps per SM at 128 registers
+#endif
 #define SKY_W 64                    // strip width
-#define SKY_H 32                    // rows per step
+#ifndef SKY_H
+#define SKY_H 16                    // rows per step (16 or 32)
+#endif
+#define SKY_NT (SKY_H * 8)          // threads per CTA: 8 pixels per thread and step
+#define SKY_LA (1 + 30 / SKY_H)     // row-filtered blocks the column pass of a block waits for (its 15-row lower apron)
+#define SKY_NSLOT (SKY_LA + 2)      // ring blocks: those a column pass reads + the one being written
 #define SKY_R 15                    // Gaussian radius
 #define SKY_UW (SKY_W + 2 * SKY_R)  // 94 upsampled columns per strip
 #define SKY_ULD 102                 // float2 per row pair of up2: 36-wide windows starting at 4*gx stay inside; an ODD number
                                     // of 16-byte chunks (51), so neighbouring row pairs start 4 banks apart (see the row filter)
 #define SKY_HRS 16                  // hrow ring slots
 #define SKY_HLD 96                  // floats per hrow row
-#define SKY_RING (3 * SKY_H)        // row-filtered ring rows; rows [96, 128) mirror rows [0, 32)
+#define SKY_RING (SKY_NSLOT * SKY_H) // row-filtered ring rows; the first SKY_LA blocks are mirrored behind the ring
 #define SKY_LRC 16                  // low-res patch columns (94/8 + 2 = 14 needed)
 #define SKY_LRR 144                 // low-res patch rows: covers segments of up to 1024 rows
 #define SKY_SEG_MAX 1024            // rows per segment (multiple of SKY_H)
 // a row tap with the hrow-ring offsets of its two low-res rows already resolved
 struct SkyRowTap { int o0, o1; float w0, w1; };
 struct SkySmem {
-    float rf[(SKY_RING + SKY_H) * SKY_W];    // 32 KB
-    float2 up2[(SKY_H / 2) * SKY_ULD];       // 12.5 KB
+    float rf[(SKY_RING + SKY_LA * SKY_H) * SKY_W];
+    float2 up2[(SKY_H / 2) * SKY_ULD];
     float hr[SKY_HRS * SKY_HLD];             // 6 KB
-    float gray[2][SKY_H * SKY_W];            // 16 KB, double-buffered cp.async target
+    float gray[SKY_H * SKY_W];               // cp.async target
     float lr[SKY_LRR * SKY_LRC];             // 9 KB
     ResizeTap tcol[SKY_UW];
     SkyRowTap trow[2][SKY_H];
     int blk_lo[2], blk_hi[2];
-    double red[2][8];
+    double red[2][SKY_NT / 32];
 };
 constexpr int kSkySmemBytes = (int)sizeof(SkySmem);
 
@@ -229,7 +237,7 @@ __device__ __forceinline__ void sky_column_pass(const SkySmem &sm, const float *
     }
 }
 
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(SKY_NT, SKY_CTAS)
 k_sky_sub_stats(const float *__restrict__ gray, long long strideGray, const float *__restrict__ med,
                 long long strideLo, int lw, const ResizeTap *__restrict__ ux, const ResizeTap *__restrict__ uy,
                 float *__restrict__ stars, long long strideStars, float *__restrict__ segmax, long long strideSeg,
@@ -239,33 +247,34 @@ k_sky_sub_stats(const float *__restrict__ gray, long long strideGray, const floa
     SkySmem &sm = *(SkySmem *)smem_raw;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int x0 = blockIdx.x * SKY_W, ya = blockIdx.y * seg_h, yb = min(ya + seg_h, g.H), f = blockIdx.z;
-    const int nk = (yb - ya + SKY_H - 1) / SKY_H; // output blocks; row-filtered blocks are 0..nk
+    const int nk = (yb - ya + SKY_H - 1) / SKY_H; // output blocks 0..nk-1
+    const int bmax = nk - 1 + SKY_LA;             // row-filtered blocks 0..bmax; block j = rows ya - 16 + j*SKY_H ...
     const float *L = med + f * strideLo;
     const float *G = gray + f * strideGray;
     float *S = stars + f * strideStars;
     float *SM = segmax + f * strideSeg;
 
     // row taps of block bb (rows ya - 16 + 32 bb ...), by warp 0: the table lookup is issued a phase early
-    auto fetch_row_tap = [&](int bb) { return uy[reflect101(ya - 16 + SKY_H * bb + lane, g.H)]; };
+    auto fetch_row_tap = [&](int bb) { return uy[reflect101(ya - 16 + SKY_H * bb + (lane & (SKY_H - 1)), g.H)]; };
     auto publish_row_taps = [&](int bb, const ResizeTap &t) {
         SkyRowTap r;
         r.o0 = (t.i0 & (SKY_HRS - 1)) * SKY_HLD; r.o1 = (t.i1 & (SKY_HRS - 1)) * SKY_HLD; r.w0 = t.w0; r.w1 = t.w1;
-        sm.trow[bb & 1][lane] = r;
+        if (lane < SKY_H) sm.trow[bb & 1][lane] = r;
         const int lo = __reduce_min_sync(0xffffffffu, t.i0), hi = __reduce_max_sync(0xffffffffu, t.i1);
         if (lane == 0) { sm.blk_lo[bb & 1] = lo; sm.blk_hi[bb & 1] = hi; }
     };
 
     // ---- prologue: column taps, first block's row taps, the segment's low-res patch
-    for (int i = tid; i < SKY_UW; i += 256) sm.tcol[i] = ux[reflect101(x0 - SKY_R + i, g.W)];
+    for (int i = tid; i < SKY_UW; i += SKY_NT) sm.tcol[i] = ux[reflect101(x0 - SKY_R + i, g.W)];
     if (wid == 0) publish_row_taps(0, fetch_row_tap(0));
     int xlo, xhi, ylo, yhi;
     reflect_range(x0 - SKY_R, x0 + SKY_W + SKY_R - 1, g.W, xlo, xhi);
-    reflect_range(ya - 16, ya - 16 + SKY_H * (nk + 1) - 1, g.H, ylo, yhi);
+    reflect_range(ya - 16, ya - 16 + SKY_H * (bmax + 1) - 1, g.H, ylo, yhi);
     const int pc0 = ux[xlo].i0, pc1 = ux[xhi].i1, pr0 = uy[ylo].i0, pr1 = uy[yhi].i1; // taps are monotone
     const bool patch_ok = pc1 - pc0 < SKY_LRC && pr1 - pr0 < SKY_LRR;
     if (patch_ok) {
         const int nrow = pr1 - pr0 + 1, ncol = pc1 - pc0 + 1;
-        for (int i = tid; i < nrow * SKY_LRC; i += 256) {
+        for (int i = tid; i < nrow * SKY_LRC; i += SKY_NT) {
             const int r = i >> 4, cc = i & 15;
             if (cc < ncol) sm.lr[i] = __ldg(L + (long long)(pr0 + r) * lw + pc0 + cc);
         }
@@ -299,8 +308,8 @@ k_sky_sub_stats(const float *__restrict__ gray, long long strideGray, const floa
     auto up_pass = [&](int bb) {
         const SkyRowTap *tr = sm.trow[bb & 1];
 #pragma unroll
-        for (int it = 0; it < 3; it++) {
-            const int i = tid + 256 * it;
+        for (int it = 0; it < ((SKY_H / 2) * (SKY_UW / 2) + SKY_NT - 1) / SKY_NT; it++) {
+            const int i = tid + SKY_NT * it;
             if (i < (SKY_H / 2) * (SKY_UW / 2)) {
                 const int rp = i / (SKY_UW / 2), c = 2 * (i - rp * (SKY_UW / 2));
                 const SkyRowTap t0 = tr[2 * rp], t1 = tr[2 * rp + 1];
@@ -316,21 +325,21 @@ k_sky_sub_stats(const float *__restrict__ gray, long long strideGray, const floa
             }
         }
     };
-    // gray tile of output block k -> sm.gray[k & 1] (asynchronously when rows are 16-byte aligned)
+    // gray tile of output block k -> sm.gray (asynchronously when rows are 16-byte aligned)
     const bool vec_gray = (g.W & 3) == 0 && x0 + SKY_W <= g.W;
     const int pr = tid >> 4, pq = tid & 15;
-    const float *gp = G + (long long)(ya + pr) * g.W + x0 + 4 * pq; // this thread's chunk of row pr (and pr + 16) of block 0
+    const float *gp = G + (long long)(ya + pr) * g.W + x0 + 4 * pq; // this thread's chunk of row pr (and pr + SKY_H/2) of block 0
     auto gray_prefetch = [&](int k) {
         const int y0 = ya + SKY_H * k;
-        float *dst = sm.gray[k & 1];
+        float *dst = sm.gray;
         if (vec_gray) {
             const float *src = gp + (long long)(SKY_H * k) * g.W;
             const unsigned sa = (unsigned)__cvta_generic_to_shared(dst + pr * SKY_W + 4 * pq);
             if (y0 + pr < g.H) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(src));
-            if (y0 + pr + 16 < g.H)
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa + 16 * SKY_W * 4), "l"(src + 16ll * g.W));
+            if (y0 + pr + SKY_H / 2 < g.H)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa + (SKY_H / 2) * SKY_W * 4), "l"(src + (long long)(SKY_H / 2) * g.W));
         } else {
-            for (int i = tid; i < SKY_H * SKY_W; i += 256) {
+            for (int i = tid; i < SKY_H * SKY_W; i += SKY_NT) {
                 const int r = i >> 6, c = i & 63;
                 dst[i] = (y0 + r < g.H && x0 + c < g.W) ? __ldg(G + (long long)(y0 + r) * g.W + x0 + c) : 0.f;
             }
@@ -341,19 +350,20 @@ k_sky_sub_stats(const float *__restrict__ gray, long long strideGray, const floa
     hrow_pass(0);
     __syncthreads();
     up_pass(0);
-    if (wid == 0 && nk >= 1) publish_row_taps(1, fetch_row_tap(1));
+    if (wid == 0 && bmax >= 1) publish_row_taps(1, fetch_row_tap(1));
 
     const bool strip_in_roi_x = x0 >= g.roi_x && x0 + SKY_W <= g.roi_x + g.roi_w;
     const bool strip_off_roi_x = x0 >= g.roi_x + g.roi_w || x0 + SKY_W <= g.roi_x;
     double sum = 0.0, sq = 0.0;
-    int slot = 0; // ring block that step b writes = b % 3
+    int slot = 0; // ring block that step b writes = b % SKY_NSLOT
 
     // Two barriers per step.  Between B and C: row filter of block b + hrow of block b+1.  After C: column pass of
-    // block b-1, then (no barrier needed) up2 / row taps / gray prefetch for the next step.
-    for (int b = 0; b <= nk; b++) {
-        __syncthreads(); // B: up2(b), row taps of b+1 visible; everyone left the column pass of b-2
+    // output block b - SKY_LA, then (no barrier needed) up2 / row taps for the next step.
+    for (int b = 0; b <= bmax; b++) {
+        __syncthreads(); // B: up2(b), row taps of b+1 visible; everyone left the previous column pass
+        if (b >= SKY_LA) gray_prefetch(b - SKY_LA); // lands behind the row filter
         ResizeTap tnext;
-        const bool taps_due = wid == 0 && b + 2 <= nk;
+        const bool taps_due = wid == 0 && b + 2 <= bmax;
         if (taps_due) tnext = fetch_row_tap(b + 2); // lands behind the row filter
         {   // rows (2rp, 2rp+1), columns 4gx .. 4gx+3 of this step's row-filtered block
             // a quarter-warp (8 lanes, one LDS.128 wavefront) = 4 neighbouring column groups x 2 neighbouring row pairs:
@@ -382,18 +392,18 @@ k_sky_sub_stats(const float *__restrict__ gray, long long strideGray, const floa
             float *d0 = sm.rf + (slot * SKY_H + 2 * rp) * SKY_W + 4 * gx;
             ((float4 *)d0)[0] = make_float4(o0[0], o0[1], o0[2], o0[3]);
             ((float4 *)(d0 + SKY_W))[0] = make_float4(o1[0], o1[1], o1[2], o1[3]);
-            if (slot == 0) { // mirror of block 0 behind block 2: 34-row windows never wrap
+            if (slot < SKY_LA) { // mirror of the first blocks behind the ring: 34-row windows never wrap
                 ((float4 *)(d0 + SKY_RING * SKY_W))[0] = make_float4(o0[0], o0[1], o0[2], o0[3]);
                 ((float4 *)(d0 + (SKY_RING + 1) * SKY_W))[0] = make_float4(o1[0], o1[1], o1[2], o1[3]);
             }
         }
-        if (b < nk) hrow_pass(b + 1);
+        if (b < bmax) hrow_pass(b + 1);
         asm volatile("cp.async.wait_all;" ::: "memory");
-        __syncthreads(); // C: row-filtered block b, hrow rows of b+1 and the gray tile of b-1 are visible
-        if (b >= 1) {
-            const int yblk = ya + SKY_H * (b - 1);
-            const int ring_row0 = (slot == 0 ? 2 : slot - 1) * SKY_H; // block b - 1
-            const float *gtile = sm.gray[(b - 1) & 1];
+        __syncthreads(); // C: row-filtered block b, hrow rows of b+1 and the gray tile are visible
+        if (b >= SKY_LA) {
+            const int yblk = ya + SKY_H * (b - SKY_LA);
+            const int ring_row0 = (slot >= SKY_LA ? slot - SKY_LA : slot + SKY_NSLOT - SKY_LA) * SKY_H; // block b - SKY_LA
+            const float *gtile = sm.gray;
             const bool in_image = x0 + SKY_W <= g.W && yblk + SKY_H <= g.H && (g.W & 1) == 0;
             const bool in_roi = strip_in_roi_x && yblk >= g.roi_y && yblk + SKY_H <= g.roi_y + g.roi_h;
             const bool off_roi = strip_off_roi_x || yblk >= g.roi_y + g.roi_h || yblk + SKY_H <= g.roi_y;
@@ -401,12 +411,11 @@ k_sky_sub_stats(const float *__restrict__ gray, long long strideGray, const floa
             else if (in_image && off_roi) sky_column_pass<1>(sm, gtile, ring_row0, x0, yblk, tid, S, SM, nseg, g, sum, sq);
             else sky_column_pass<2>(sm, gtile, ring_row0, x0, yblk, tid, S, SM, nseg, g, sum, sq);
         }
-        if (b < nk) {
+        if (b < bmax) {
             up_pass(b + 1);
             if (taps_due) publish_row_taps(b + 2, tnext);
-            gray_prefetch(b); // consumed by the column pass of the next step
         }
-        slot = slot == 2 ? 0 : slot + 1;
+        slot = slot == SKY_NSLOT - 1 ? 0 : slot + 1;
     }
     // block reduction of the fp64 partial sums, fixed order
 #pragma unroll
@@ -418,7 +427,7 @@ k_sky_sub_stats(const float *__restrict__ gray, long long strideGray, const floa
     __syncthreads();
     if (tid == 0) {
         double a = 0.0, b = 0.0;
-        for (int w = 0; w < 8; w++) { a += sm.red[0][w]; b += sm.red[1][w]; }
+        for (int w = 0; w < SKY_NT / 32; w++) { a += sm.red[0][w]; b += sm.red[1][w]; }
         const long long blk = (long long)blockIdx.y * gridDim.x + blockIdx.x;
         partials[f * stridePart + 2 * blk] = a;
         partials[f * stridePart + 2 * blk + 1] = b;

@@ -581,7 +581,7 @@ static int run_detect(oss_ctx *c, const FramePtrs &fp, int n, bool use_masters, 
     LAUNCH("median5", k_median5, dim3((g.lw + 31) / 32, (g.lh + 7) / 8, n), 256, 0, w.lo, w.med, w.strideLo, g.lw, g.lh);
     const long long strideGray = g.C == 3 ? w.strideP : w.stridePC;
     const int seg_h = sky_segment_rows(g.H);
-    LAUNCH("sky_sub_stats", k_sky_sub_stats, dim3((g.W + SKY_W - 1) / SKY_W, (g.H + seg_h - 1) / seg_h, n), 256, kSkySmemBytes,
+    LAUNCH("sky_sub_stats", k_sky_sub_stats, dim3((g.W + SKY_W - 1) / SKY_W, (g.H + seg_h - 1) / seg_h, n), SKY_NT, kSkySmemBytes,
            w.gray, strideGray, w.med, w.strideLo, g.lw, c->ux, c->uy, w.stars, w.strideP, w.segmax, w.strideSeg, g.nseg,
            w.partials, w.stridePart, g, seg_h);
     return run_detect_tail(c, n, threshold);
