@@ -57,6 +57,15 @@ k_resize_down(const float *__restrict__ gray, long long strideGray, int W, const
     lo[blockIdx.z * strideLo + (long long)dy * lw + dx] = lerp2(h0, b.w0, h1, b.w1);
 }
 
+// median-of-25 selection network: 99 compare-exchange pairs (a, b) -> (min, max)
+__device__ constexpr unsigned char kMed25[198] = {
+    0,1, 3,4, 2,4, 2,3, 6,7, 5,7, 5,6, 9,10, 8,10, 8,9, 12,13, 11,13, 11,12, 15,16, 14,16, 14,15, 18,19, 17,19, 17,18,
+    21,22, 20,22, 20,21, 23,24, 2,5, 3,6, 0,6, 0,3, 4,7, 1,7, 1,4, 11,14, 8,14, 8,11, 12,15, 9,15, 9,12, 13,16, 10,16,
+    10,13, 20,23, 17,23, 17,20, 21,24, 18,24, 18,21, 19,22, 8,17, 9,18, 0,18, 0,9, 10,19, 1,19, 1,10, 11,20, 2,20, 2,11,
+    12,21, 3,21, 3,12, 13,22, 4,22, 4,13, 14,23, 5,23, 5,14, 15,24, 6,24, 6,15, 7,16, 7,19, 13,21, 15,23, 7,13, 7,15,
+    1,9, 3,11, 5,17, 11,17, 9,17, 4,10, 6,12, 7,14, 4,6, 4,7, 12,14, 10,14, 6,7, 10,12, 6,10, 6,17, 12,17, 7,17, 7,10,
+    12,18, 7,12, 10,18, 12,20, 10,20, 10,12};
+
 // medianBlur ksize 5, BORDER_REPLICATE: exact median of 25 (Appendix B.4)
 __global__ void __launch_bounds__(256)
 k_median5(const float *__restrict__ lo, float *__restrict__ med, long long strideLo, int lw, int lh)
@@ -74,14 +83,14 @@ k_median5(const float *__restrict__ lo, float *__restrict__ med, long long strid
             v[(dy + 2) * 5 + dx + 2] = __ldg(s + (long long)yy * lw + xx);
         }
     }
-    // 13 rounds of min-extraction, fully unrolled so v[] stays in registers
+    // 99 compare-exchanges that leave the median of 25 in v[12] (a selection network, not a full sort; the
+    // pair list is checked exhaustively with the 0/1 principle in tests/test_kernel_tables.py);
+    // fully unrolled so v[] stays in registers
 #pragma unroll
-    for (int i = 0; i <= 12; i++) {
-#pragma unroll
-        for (int j = i + 1; j < 25; j++) {
-            float lo_ = fminf(v[i], v[j]), hi_ = fmaxf(v[i], v[j]);
-            v[i] = lo_; v[j] = hi_;
-        }
+    for (int i = 0; i < 99; i++) {
+        const int a = kMed25[2 * i], b = kMed25[2 * i + 1];
+        const float lo_ = fminf(v[a], v[b]), hi_ = fmaxf(v[a], v[b]);
+        v[a] = lo_; v[b] = hi_;
     }
     med[blockIdx.z * strideLo + (long long)y * lw + x] = v[12];
 }

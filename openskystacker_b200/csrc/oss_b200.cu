@@ -25,7 +25,7 @@ using namespace oss;
 
 // ----------------------------------------------------------------------------------------
 struct ProfEntry { std::string name; double ms; int launches; };
-struct ProfPending { int entry; cudaEvent_t a, b; };
+struct ProfPending { int entry; cudaEvent_t a, b; int pipe; };
 
 struct NcclApi {
     void *handle = nullptr;
@@ -69,11 +69,12 @@ static bool nccl_load(std::string *why)
 #define OSS_MAX_PIPES 4
 struct Pipe {
     cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaStream_t chain_stream = nullptr; // high priority: the latency-bound detection tail + alignment of a batch
     Workspace ws{};
     int *d_xy = nullptr, *d_nxy = nullptr;
     unsigned char *raw_stage[2] = {nullptr, nullptr};
     cudaEvent_t copy_done[2] = {nullptr, nullptr}, raw_free[2] = {nullptr, nullptr};
-    cudaEvent_t warp_done = nullptr;
+    cudaEvent_t warp_done = nullptr, detect_done = nullptr, sky_done = nullptr;
     long long batch_counter = 0;
 };
 
@@ -83,7 +84,10 @@ struct oss_ctx {
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     Pipe pipes[OSS_MAX_PIPES];
     int npipes = 3, want_pipes = 3, cur = 0;
-    cudaEvent_t last_warp = nullptr; // warp_done of the most recently queued batch
+    // every warp + accumulate kernel runs on this one stream: accumulation order = batch order = frame order
+    cudaStream_t warp_stream = nullptr;
+    bool stagger = false;
+    int prev_pipe = -1;
     long long light_batches = 0;
     std::string err;
     Geom g{};
@@ -115,6 +119,12 @@ struct oss_ctx {
     int nlights = 0;
     std::vector<oss_star> ref_stars;
     oss_detect_info ref_info{};
+    // oss_set_reference is asynchronous: its results are kept on the device / in pinned memory and pulled on demand
+    oss_star *d_ref_stars = nullptr;   // [cap] copy of the reference's star list (the work space slot is reused by lights)
+    DetectState *h_ref_ds = nullptr;   // pinned
+    cudaEvent_t ref_ready = nullptr;   // reference triangles built (alignment kernels of every pipeline wait for it)
+    cudaEvent_t ref_copied = nullptr;  // d_ref_stars / h_ref_ds written
+    bool ref_host_valid = true;
     // instrumentation
     bool profiling = false;
     std::vector<ProfEntry> prof;
@@ -160,7 +170,9 @@ static cudaError_t sync_all(oss_ctx *c)
     for (int p = 0; p < OSS_MAX_PIPES; p++) {
         if (c->pipes[p].copy_stream) { cudaError_t r = cudaStreamSynchronize(c->pipes[p].copy_stream); if (r != cudaSuccess) e = r; }
         if (c->pipes[p].stream) { cudaError_t r = cudaStreamSynchronize(c->pipes[p].stream); if (r != cudaSuccess) e = r; }
+        if (c->pipes[p].chain_stream) { cudaError_t r = cudaStreamSynchronize(c->pipes[p].chain_stream); if (r != cudaSuccess) e = r; }
     }
+    if (c->warp_stream) { cudaError_t r = cudaStreamSynchronize(c->warp_stream); if (r != cudaSuccess) e = r; }
     return e;
 }
 
@@ -197,6 +209,21 @@ static cudaEvent_t get_event(oss_ctx *c)
 
 static void prof_flush(oss_ctx *c)
 {
+    // dev aid: OSS_B200_TIMELINE=<file> appends "name pipe start_ms end_ms" per launch, relative to the first launch of the flush
+    if (const char *path = getenv("OSS_B200_TIMELINE")) {
+        if (!c->prof_pending.empty()) {
+            if (FILE *fp = fopen(path, "a")) {
+                fprintf(fp, "# flush of %zu launches\n", c->prof_pending.size());
+                for (auto &p : c->prof_pending) {
+                    float t0 = 0.f, t1 = 0.f;
+                    cudaEventElapsedTime(&t0, c->prof_pending[0].a, p.a);
+                    cudaEventElapsedTime(&t1, c->prof_pending[0].a, p.b);
+                    fprintf(fp, "%s %d %.4f %.4f\n", c->prof[p.entry].name.c_str(), p.pipe, t0, t1);
+                }
+                fclose(fp);
+            }
+        }
+    }
     for (auto &p : c->prof_pending) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) { c->prof[p.entry].ms += ms; c->prof[p.entry].launches++; }
@@ -208,7 +235,7 @@ static void prof_flush(oss_ctx *c)
 
 #define LAUNCH(name, kern, grid, block, smem, ...)                                   \
     do {                                                                             \
-        ProfPending pp_{-1, nullptr, nullptr};                                       \
+        ProfPending pp_{-1, nullptr, nullptr, c->cur};                               \
         if (c->profiling) {                                                          \
             pp_.entry = prof_entry(c, name);                                         \
             pp_.a = get_event(c); pp_.b = get_event(c);                              \
@@ -246,12 +273,14 @@ static void free_geometry(oss_ctx *c)
             if (pp.raw_free[i]) { cudaEventDestroy(pp.raw_free[i]); pp.raw_free[i] = nullptr; }
         }
         if (pp.warp_done) { cudaEventDestroy(pp.warp_done); pp.warp_done = nullptr; }
+        if (pp.detect_done) { cudaEventDestroy(pp.detect_done); pp.detect_done = nullptr; }
+        if (pp.sky_done) { cudaEventDestroy(pp.sky_done); pp.sky_done = nullptr; }
         pp.ws = Workspace{};
         pp.d_xy = pp.d_nxy = nullptr;
         pp.batch_counter = 0;
     }
-    c->last_warp = nullptr;
     c->light_batches = 0;
+    c->prev_pipe = -1;
     c->has_geom = false;
     c->has_ref = false;
     c->synth_plane = nullptr;
@@ -289,14 +318,31 @@ int oss_create(oss_ctx **out, int device)
     oss_ctx *c = new oss_ctx();
     c->device = device;
     bool ok = cudaSetDevice(device) == cudaSuccess;
+    // Two priority levels.  The block scheduler dispatches kernels of equal priority in launch order, so a small kernel
+    // queued behind another stream's 10^4-CTA kernel waits for that whole grid to be dispatched.  The latency-bound
+    // detection tail (thresholding, scans, components, alignment: dozens of dependent launches of a few CTAs each)
+    // therefore runs on a high-priority stream per pipeline and takes SM slots as they free up, while the bulk kernels
+    // (calibration, sky, warp, masters) of all pipelines share the low level.
+    int prio_least = 0, prio_greatest = 0;
+    ok = ok && cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest) == cudaSuccess; // numerically greatest <= least
+    if (const char *e = getenv("OSS_B200_CHAIN_PRIO")) if (atoi(e) == 0) prio_greatest = prio_least;
     for (int p = 0; ok && p < OSS_MAX_PIPES; p++)
-        ok = cudaStreamCreateWithFlags(&c->pipes[p].stream, cudaStreamNonBlocking) == cudaSuccess &&
-             cudaStreamCreateWithFlags(&c->pipes[p].copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+        ok = cudaStreamCreateWithPriority(&c->pipes[p].stream, cudaStreamNonBlocking, prio_least) == cudaSuccess &&
+             cudaStreamCreateWithPriority(&c->pipes[p].chain_stream, cudaStreamNonBlocking, prio_greatest) == cudaSuccess &&
+             cudaStreamCreateWithPriority(&c->pipes[p].copy_stream, cudaStreamNonBlocking, prio_greatest) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithPriority(&c->warp_stream, cudaStreamNonBlocking, prio_least) == cudaSuccess;
     if (!ok) {
         delete c;
         return OSS_E_CUDA;
     }
+    if (cudaEventCreateWithFlags(&c->ref_ready, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ref_copied, cudaEventDisableTiming) != cudaSuccess ||
+        cudaMallocHost((void **)&c->h_ref_ds, sizeof(DetectState)) != cudaSuccess) {
+        delete c;
+        return OSS_E_CUDA;
+    }
     if (const char *e = getenv("OSS_B200_PIPES")) c->want_pipes = atoi(e);
+    if (const char *e = getenv("OSS_B200_STAGGER")) c->stagger = atoi(e) != 0;
     c->stream = c->pipes[0].stream;
     c->copy_stream = c->pipes[0].copy_stream;
     // constant tables
@@ -312,7 +358,9 @@ int oss_create(oss_ctx **out, int device)
         cudaFuncSetAttribute(k_focas, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FocasSmem)) != cudaSuccess ||
         cudaFuncSetAttribute(k_warp_accumulate_tiled<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, warp_tiled_smem<3>()) != cudaSuccess ||
         cudaFuncSetAttribute(k_warp_accumulate_tiled<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, warp_tiled_smem<1>()) != cudaSuccess) {
-        for (int p = 0; p < OSS_MAX_PIPES; p++) { cudaStreamDestroy(c->pipes[p].stream); cudaStreamDestroy(c->pipes[p].copy_stream); }
+        for (int p = 0; p < OSS_MAX_PIPES; p++) { cudaStreamDestroy(c->pipes[p].stream); cudaStreamDestroy(c->pipes[p].copy_stream); if (c->pipes[p].chain_stream) cudaStreamDestroy(c->pipes[p].chain_stream); }
+    cudaStreamDestroy(c->warp_stream);
+        cudaStreamDestroy(c->warp_stream);
         delete c;
         return OSS_E_CUDA;
     }
@@ -332,7 +380,11 @@ void oss_destroy(oss_ctx *c)
     for (auto p : c->h_al_chunks) cudaFreeHost(p);
     prof_flush(c);
     for (auto e : c->event_pool) cudaEventDestroy(e);
-    for (int p = 0; p < OSS_MAX_PIPES; p++) { cudaStreamDestroy(c->pipes[p].stream); cudaStreamDestroy(c->pipes[p].copy_stream); }
+    for (int p = 0; p < OSS_MAX_PIPES; p++) { cudaStreamDestroy(c->pipes[p].stream); cudaStreamDestroy(c->pipes[p].copy_stream); if (c->pipes[p].chain_stream) cudaStreamDestroy(c->pipes[p].chain_stream); }
+    cudaStreamDestroy(c->warp_stream);
+    if (c->ref_ready) cudaEventDestroy(c->ref_ready);
+    if (c->ref_copied) cudaEventDestroy(c->ref_copied);
+    if (c->h_ref_ds) cudaFreeHost(c->h_ref_ds);
     delete c;
 }
 
@@ -440,6 +492,8 @@ int oss_set_geometry(oss_ctx *c, int W, int H, int C, int sample, int slots)
             CK(cudaEventCreateWithFlags(&pp.raw_free[i], cudaEventDisableTiming));
         }
         CK(cudaEventCreateWithFlags(&pp.warp_done, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&pp.detect_done, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&pp.sky_done, cudaEventDisableTiming));
         pp.batch_counter = 0;
     }
     c->cur = 0;
@@ -449,6 +503,7 @@ int oss_set_geometry(oss_ctx *c, int W, int H, int C, int sample, int slots)
     DA(c->sum, PC); DA(c->ref_cal, PC); DA(c->result, PC);
     DA(c->d_valid, 4);
     DA(c->d_ref, 1); DA(c->d_ref_tmp, 1);
+    DA(c->d_ref_stars, g.cap);
     DA(c->d_dbg_matches, 3 * OSS_MAX_MATCH); DA(c->d_dbg_table, OSS_NOBJS * OSS_NOBJS); DA(c->d_dbg_clk, 8);
     DA(c->d_M, 8); DA(c->d_flat_ratio, 4); DA(c->d_flat_partial, 1024);
     LAUNCH("resize_taps", k_resize_taps, (g.lw + 255) / 256, 256, 0, c->dx, W, g.lw, 1);
@@ -584,6 +639,10 @@ static int run_detect(oss_ctx *c, const FramePtrs &fp, int n, bool use_masters, 
     LAUNCH("sky_sub_stats", k_sky_sub_stats, dim3((g.W + SKY_W - 1) / SKY_W, (g.H + seg_h - 1) / seg_h, n), SKY_NT, kSkySmemBytes,
            w.gray, strideGray, w.med, w.strideLo, g.lw, c->ux, c->uy, w.stars, w.strideP, w.segmax, w.strideSeg, g.nseg,
            w.partials, w.stridePart, g, seg_h);
+    // the rest of the batch's detection (and whatever the caller queues next) goes to the pipeline's high-priority stream
+    CK(cudaEventRecord(c->pipes[c->cur].sky_done, c->stream));
+    c->stream = c->pipes[c->cur].chain_stream;
+    CK(cudaStreamWaitEvent(c->stream, c->pipes[c->cur].sky_done, 0));
     return run_detect_tail(c, n, threshold);
 }
 
@@ -732,10 +791,13 @@ int oss_reset_stack(oss_ctx *c)
     CK(cudaMemsetAsync(c->d_valid, 0, 16, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     c->has_ref = false;
+    c->prev_pipe = -1;
     c->ref_in_sum = true;
     c->nlights = 0;
     c->extra_valid = 0;
     c->ref_stars.clear();
+    c->ref_info = oss_detect_info{};
+    c->ref_host_valid = true;
     return OSS_OK;
 }
 
@@ -754,20 +816,40 @@ int oss_set_reference(oss_ctx *c, const void *frame, int mem, int threshold)
     rc = run_detect(c, fp, 1, true, threshold, set);
     if (rc) return rc;
     const long long PC = g.P * g.C;
-    LAUNCH("copy_reference", k_copy_f32, (unsigned)((PC + 1023) / 1024), 256, 0, w.cal, c->ref_cal, PC);
+    {   // bulk copy: on the pipeline's low-priority stream, ordered behind the calibration there
+        cudaStream_t chain = c->stream;
+        c->stream = c->pipes[c->cur].stream;
+        LAUNCH("copy_reference", k_copy_f32, (unsigned)((PC + 1023) / 1024), 256, 0, w.cal, c->ref_cal, PC);
+        c->stream = chain;
+    }
     int *xy_ref = c->d_xy + c->slots * 2 * OSS_NOBJS, *nxy_ref = c->d_nxy + c->slots;
     LAUNCH("pack_xy", k_pack_xy, 1, OSS_NOBJS, 0, w.star_out, w.ds, g.cap, xy_ref, nxy_ref);
     LAUNCH("build_ref_triangles", k_build_ref_triangles, 1, FOCAS_NT, 0, xy_ref, nxy_ref, c->d_ref);
-    DetectState d;
-    CK(cudaMemcpyAsync(&d, w.ds, sizeof d, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    fill_info(d, &c->ref_info);
-    if (d.overflow) return fail(c, OSS_E_CAPACITY, "reference frame: %d candidate pixels exceed the workspace (%d)", d.ncand, g.cap);
-    c->ref_stars.resize(d.nstars);
-    if (d.nstars) CK(cudaMemcpy(c->ref_stars.data(), w.star_out, (size_t)d.nstars * sizeof(oss_star), cudaMemcpyDeviceToHost));
+    CK(cudaEventRecord(c->ref_ready, c->stream));
+    // results stay on the device / go to pinned memory without blocking the caller (ref_host() pulls them on demand),
+    // so the first batch of lights can start while the reference's latency-bound detection tail is still running
+    CK(cudaMemcpyAsync(c->h_ref_ds, w.ds, sizeof(DetectState), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(c->d_ref_stars, w.star_out, (size_t)g.cap * sizeof(oss_star), cudaMemcpyDeviceToDevice, c->stream));
+    CK(cudaEventRecord(c->ref_copied, c->stream));
+    c->ref_host_valid = false;
     c->threshold = threshold;
     c->has_ref = true;
     c->ref_in_sum = true;
+    if (c->npipes > 1) c->light_batches = 1; // the first batch of lights goes to another pipeline than the reference's
+    return OSS_OK;
+}
+
+// host copies of the reference's detection results (and its deferred capacity error)
+static int ref_host(oss_ctx *c)
+{
+    if (c->ref_host_valid) return OSS_OK;
+    CK(cudaEventSynchronize(c->ref_copied));
+    const DetectState d = *c->h_ref_ds;
+    fill_info(d, &c->ref_info);
+    if (d.overflow) return fail(c, OSS_E_CAPACITY, "reference frame: %d candidate pixels exceed the workspace (%d)", d.ncand, c->g.cap);
+    c->ref_stars.resize(d.nstars);
+    if (d.nstars) CK(cudaMemcpy(c->ref_stars.data(), c->d_ref_stars, (size_t)d.nstars * sizeof(oss_star), cudaMemcpyDeviceToHost));
+    c->ref_host_valid = true;
     return OSS_OK;
 }
 
@@ -796,6 +878,10 @@ int oss_add_lights(oss_ctx *c, const void *const *frames, int n, int mem)
         int nb = n - b0 < c->slots ? n - b0 : c->slots;
         select_pipe(c, (int)(c->light_batches++ % c->npipes));
         Workspace &w = c->ws;
+        // this pipeline's previous batch must have been warped before its calibrated planes are overwritten
+        CK(cudaStreamWaitEvent(c->stream, c->pipes[c->cur].warp_done, 0));
+        if (c->stagger && c->prev_pipe >= 0 && c->prev_pipe != c->cur) CK(cudaStreamWaitEvent(c->stream, c->pipes[c->prev_pipe].sky_done, 0));
+        c->prev_pipe = c->cur;
         FramePtrs fp{};
         int set;
         rc = stage_frames(c, frames + b0, nb, mem, &fp, &set);
@@ -803,10 +889,14 @@ int oss_add_lights(oss_ctx *c, const void *const *frames, int n, int mem)
         rc = run_detect(c, fp, nb, true, c->threshold, set);
         if (rc) return rc;
         LAUNCH("pack_xy", k_pack_xy, nb, OSS_NOBJS, 0, w.star_out, w.ds, g.cap, c->d_xy, c->d_nxy);
+        CK(cudaStreamWaitEvent(c->stream, c->ref_ready, 0)); // the reference may still be in flight on pipeline 0
         LAUNCH("focas_match_fit", k_focas, nb, FOCAS_NT, sizeof(FocasSmem), c->d_ref, c->d_xy, c->d_nxy, w.align, c->d_valid,
                (int *)nullptr, (int *)nullptr, (long long *)nullptr);
-        // accumulate in batch order: wait for the previous batch's warp (it ran on another pipeline)
-        if (c->last_warp && c->npipes > 1) CK(cudaStreamWaitEvent(c->stream, c->last_warp, 0));
+        // warp + accumulate on the shared low-priority stream, in batch order
+        CK(cudaEventRecord(c->pipes[c->cur].detect_done, c->stream));
+        cudaStream_t pipe_stream = c->stream;
+        c->stream = c->warp_stream;
+        CK(cudaStreamWaitEvent(c->stream, c->pipes[c->cur].detect_done, 0));
         LAUNCH("warp_tables", k_warp_tables, dim3((g.W + g.H + 255) / 256, nb), 256, 0, w.align, w.warp_ab, (long long)g.W, w.warp_xy,
                (long long)g.H, g.W, g.H);
         const dim3 wgrid((g.W + WT_W - 1) / WT_W, (g.H + WT_H - 1) / WT_H);
@@ -818,7 +908,7 @@ int oss_add_lights(oss_ctx *c, const void *const *frames, int n, int mem)
                    (long long)g.W, w.warp_xy, (long long)g.H, c->sum, g.W, g.H);
         }
         CK(cudaEventRecord(c->pipes[c->cur].warp_done, c->stream));
-        c->last_warp = c->pipes[c->cur].warp_done;
+        c->stream = pipe_stream;
         // reports back to pinned host memory, asynchronously; a batch never straddles a chunk
         // boundary more than once
         int done = 0;
@@ -860,6 +950,7 @@ int oss_get_reference_stars(oss_ctx *c, oss_star *out, int cap, int *n, oss_dete
 {
     USE_PIPE0();
     if (!c->has_ref) return fail(c, OSS_E_ARG, "no reference");
+    { int rc = ref_host(c); if (rc) return rc; }
     int m = (int)c->ref_stars.size();
     if (n) *n = m;
     if (out) memcpy(out, c->ref_stars.data(), sizeof(oss_star) * (size_t)(m < cap ? m : cap));
@@ -888,6 +979,7 @@ int oss_finish(oss_ctx *c, float *out, int *tv)
 {
     USE_PIPE0();
     if (!c->has_ref) return fail(c, OSS_E_ARG, "no reference");
+    { int rc = ref_host(c); if (rc) return rc; } // a reference that overflowed the work space invalidates the stack
     CK(cudaStreamSynchronize(c->copy_stream));
     int v;
     int rc = total_valid(c, &v);
@@ -934,6 +1026,7 @@ int oss_detect_stars_batch(oss_ctx *c, const void *const *frames, int n, int mem
     std::vector<DetectState> d(c->slots);
     for (int b0 = 0; b0 < n; b0 += c->slots) {
         int nb = n - b0 < c->slots ? n - b0 : c->slots;
+        c->stream = c->pipes[c->cur].stream; // run_detect leaves the pipeline on its chain stream; the previous batch is complete
         FramePtrs fp{};
         int set;
         int rc = stage_frames(c, frames + b0, nb, mem, &fp, &set);
