@@ -187,7 +187,10 @@ def main():
     ap.add_argument("--height", type=int, default=4000)
     ap.add_argument("--lights", type=int, default=50)
     ap.add_argument("--ncal", type=int, default=10)
-    ap.add_argument("--slots", type=int, default=10)
+    ap.add_argument("--slots", type=int, default=25, help="frames in flight per pipeline, device-resident run")
+    ap.add_argument("--pipes", type=int, default=2, help="pipelines, device-resident run")
+    ap.add_argument("--e2e-slots", type=int, default=10, help="frames in flight for the host-fed run (shorter drain after the last H2D copy)")
+    ap.add_argument("--e2e-pipes", type=int, default=3)
     ap.add_argument("--cpu-lights", type=int, default=0, help="lights in the CPU sample (0 = host cores)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -201,7 +204,8 @@ def main():
     W, H, C = a.width, a.height, 3
     workload = f"{a.lights} x {W}x{H} RGB16 lights + {a.ncal} darks + {a.ncal} flats + {a.ncal} bias: full calibration + align + stack"
     config = {"workload": workload, "width": W, "height": H, "channels": C, "lights_per_gpu": a.lights,
-              "calibration_frames": 3 * a.ncal, "threshold": 20, "frames_in_flight": a.slots,
+              "calibration_frames": 3 * a.ncal, "threshold": 20, "frames_in_flight": a.slots, "pipelines": a.pipes,
+              "e2e_frames_in_flight": a.e2e_slots, "e2e_pipelines": a.e2e_pipes,
               "l2": "inputs (%.1f GB per step) are far larger than L2" % ((a.lights + 1 + 3 * a.ncal) * W * H * C * 2 / 1e9),
               "parallelism": f"frames sharded over {world} GPU(s), one ncclReduce of the f32 sum" if world > 1 else "1 GPU"}
 
@@ -246,6 +250,7 @@ def main():
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     eng = ob.Engine(local)
+    eng.set_pipelines(int(os.environ.get("OSS_B200_PIPES", a.pipes)))
     eng.set_geometry(W, H, C, np.uint16, a.slots)
     comm = None
     if world > 1:
@@ -317,6 +322,9 @@ def main():
         cal_h = (hp_arr(inp.bias), hp_arr(inp.darks), hp_arr(inp.flats))
         lights_h, _ = hp_arr(inp.lights)
         res_host = L.oss_host_alloc(W * H * C * 4) if rank == 0 else None
+        if (a.e2e_slots, a.e2e_pipes) != (a.slots, a.pipes):
+            eng.set_pipelines(a.e2e_pipes)
+            eng.set_geometry(W, H, C, np.uint16, a.e2e_slots)
         step_host = lambda: run_job(eng, B, cal_h, Ct.c_void_p(host[inp.ref]), lights_h, nl, B.HOST,
                                     Ct.c_void_p(res_host) if rank == 0 else None, comm, rank)
         timed(step_host, 1)

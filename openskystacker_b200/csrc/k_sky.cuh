@@ -174,6 +174,7 @@ struct SkySmem {
     ResizeTap tcol[SKY_UW];
     SkyRowTap trow[2][SKY_H];
     int blk_lo[2], blk_hi[2];
+    unsigned char mode[SKY_SEG_MAX / SKY_H]; // column-pass variant of every output block of the segment
     double red[2][SKY_NT / 32];
 };
 constexpr int kSkySmemBytes = (int)sizeof(SkySmem);
@@ -293,6 +294,7 @@ k_sky_sub_stats(const float *__restrict__ gray, long long strideGray, const floa
     int hr_lo = 0, hr_hi = -1; // low-res rows currently valid in the hrow ring (block-uniform)
     // horizontal lerp of the low-res rows block bb needs and the ring does not hold yet: warps 0..2, thread = column
     auto hrow_pass = [&](int bb) {
+        if (tid >= SKY_HLD) return; // warps 0..2 only (they all track the ring's valid range)
         const int lo = sm.blk_lo[bb & 1], hi = sm.blk_hi[bb & 1]; // hi - lo <= 32/8 + 2 < SKY_HRS (the scale is 8)
         int first;
         if (lo >= hr_lo && lo <= hr_hi + 1) { first = max(hr_hi + 1, lo); hr_hi = max(hr_hi, hi); }
@@ -334,35 +336,45 @@ k_sky_sub_stats(const float *__restrict__ gray, long long strideGray, const floa
             }
         }
     };
-    // gray tile of output block k -> sm.gray (asynchronously when rows are 16-byte aligned)
+    // gray tile of the next output block -> sm.gray (asynchronously when rows are 16-byte aligned); called once per
+    // output block, in order, so the source pointer and the row number just advance
     const bool vec_gray = (g.W & 3) == 0 && x0 + SKY_W <= g.W;
     const int pr = tid >> 4, pq = tid & 15;
-    const float *gp = G + (long long)(ya + pr) * g.W + x0 + 4 * pq; // this thread's chunk of row pr (and pr + SKY_H/2) of block 0
-    auto gray_prefetch = [&](int k) {
-        const int y0 = ya + SKY_H * k;
-        float *dst = sm.gray;
+    const float *gp = G + (long long)(ya + pr) * g.W + x0 + 4 * pq; // this thread's chunk of row pr (and pr + SKY_H/2)
+    int grow = ya + pr;
+    const unsigned gdst = (unsigned)__cvta_generic_to_shared(sm.gray + pr * SKY_W + 4 * pq);
+    auto gray_prefetch = [&]() {
         if (vec_gray) {
-            const float *src = gp + (long long)(SKY_H * k) * g.W;
-            const unsigned sa = (unsigned)__cvta_generic_to_shared(dst + pr * SKY_W + 4 * pq);
-            if (y0 + pr < g.H) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(src));
-            if (y0 + pr + SKY_H / 2 < g.H)
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa + (SKY_H / 2) * SKY_W * 4), "l"(src + (long long)(SKY_H / 2) * g.W));
+            if (grow < g.H) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(gdst), "l"(gp));
+            if (grow + SKY_H / 2 < g.H)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(gdst + (SKY_H / 2) * SKY_W * 4), "l"(gp + (long long)(SKY_H / 2) * g.W));
         } else {
+            const int y0 = grow - pr;
             for (int i = tid; i < SKY_H * SKY_W; i += SKY_NT) {
                 const int r = i >> 6, c = i & 63;
-                dst[i] = (y0 + r < g.H && x0 + c < g.W) ? __ldg(G + (long long)(y0 + r) * g.W + x0 + c) : 0.f;
+                sm.gray[i] = (y0 + r < g.H && x0 + c < g.W) ? __ldg(G + (long long)(y0 + r) * g.W + x0 + c) : 0.f;
             }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
+        gp += (long long)SKY_H * g.W;
+        grow += SKY_H;
     };
+
+    // column-pass variant per output block: 0 inside the image and inside the statistics ROI, 1 inside the image and
+    // outside the ROI, 2 anything else (per-pixel tests)
+    if (tid < nk) {
+        const int yblk = ya + SKY_H * tid;
+        const bool in_image = x0 + SKY_W <= g.W && yblk + SKY_H <= g.H && (g.W & 1) == 0;
+        const bool in_roi = x0 >= g.roi_x && x0 + SKY_W <= g.roi_x + g.roi_w && yblk >= g.roi_y && yblk + SKY_H <= g.roi_y + g.roi_h;
+        const bool off_roi = x0 >= g.roi_x + g.roi_w || x0 + SKY_W <= g.roi_x || yblk >= g.roi_y + g.roi_h || yblk + SKY_H <= g.roi_y;
+        sm.mode[tid] = (in_image && in_roi) ? 0 : (in_image && off_roi) ? 1 : 2;
+    }
 
     hrow_pass(0);
     __syncthreads();
     up_pass(0);
     if (wid == 0 && bmax >= 1) publish_row_taps(1, fetch_row_tap(1));
 
-    const bool strip_in_roi_x = x0 >= g.roi_x && x0 + SKY_W <= g.roi_x + g.roi_w;
-    const bool strip_off_roi_x = x0 >= g.roi_x + g.roi_w || x0 + SKY_W <= g.roi_x;
     double sum = 0.0, sq = 0.0;
     int slot = 0; // ring block that step b writes = b % SKY_NSLOT
 
@@ -370,7 +382,7 @@ k_sky_sub_stats(const float *__restrict__ gray, long long strideGray, const floa
     // output block b - SKY_LA, then (no barrier needed) up2 / row taps for the next step.
     for (int b = 0; b <= bmax; b++) {
         __syncthreads(); // B: up2(b), row taps of b+1 visible; everyone left the previous column pass
-        if (b >= SKY_LA) gray_prefetch(b - SKY_LA); // lands behind the row filter
+        if (b >= SKY_LA) gray_prefetch(); // tile of output block b - SKY_LA; lands behind the row filter
         ResizeTap tnext;
         const bool taps_due = wid == 0 && b + 2 <= bmax;
         if (taps_due) tnext = fetch_row_tap(b + 2); // lands behind the row filter
@@ -413,11 +425,9 @@ k_sky_sub_stats(const float *__restrict__ gray, long long strideGray, const floa
             const int yblk = ya + SKY_H * (b - SKY_LA);
             const int ring_row0 = (slot >= SKY_LA ? slot - SKY_LA : slot + SKY_NSLOT - SKY_LA) * SKY_H; // block b - SKY_LA
             const float *gtile = sm.gray;
-            const bool in_image = x0 + SKY_W <= g.W && yblk + SKY_H <= g.H && (g.W & 1) == 0;
-            const bool in_roi = strip_in_roi_x && yblk >= g.roi_y && yblk + SKY_H <= g.roi_y + g.roi_h;
-            const bool off_roi = strip_off_roi_x || yblk >= g.roi_y + g.roi_h || yblk + SKY_H <= g.roi_y;
-            if (in_image && in_roi) sky_column_pass<0>(sm, gtile, ring_row0, x0, yblk, tid, S, SM, nseg, g, sum, sq);
-            else if (in_image && off_roi) sky_column_pass<1>(sm, gtile, ring_row0, x0, yblk, tid, S, SM, nseg, g, sum, sq);
+            const int mode = sm.mode[b - SKY_LA];
+            if (mode == 0) sky_column_pass<0>(sm, gtile, ring_row0, x0, yblk, tid, S, SM, nseg, g, sum, sq);
+            else if (mode == 1) sky_column_pass<1>(sm, gtile, ring_row0, x0, yblk, tid, S, SM, nseg, g, sum, sq);
             else sky_column_pass<2>(sm, gtile, ring_row0, x0, yblk, tid, S, SM, nseg, g, sum, sq);
         }
         if (b < bmax) {
@@ -443,12 +453,27 @@ k_sky_sub_stats(const float *__restrict__ gray, long long strideGray, const floa
     }
 }
 
-// rows per segment of the marching kernel: as few segments as keep every one <= SKY_SEG_MAX rows
-static inline int sky_segment_rows(int H)
+// Rows per segment of the marching kernel.  Long segments amortise the warm-up rows (2 * 16 per segment); a launch of
+// few frames is cut into shorter ones so that the grid still fills the GPU a few times over (148 SMs x 4 CTAs).
+static inline int sky_segment_rows(int W, int H, int nframes)
 {
-    const int nseg = (H + SKY_SEG_MAX - 1) / SKY_SEG_MAX;
+    const int strips = (W + SKY_W - 1) / SKY_W;
+    const int want_ctas = 3 * 148 * SKY_CTAS;
+    int nseg = (H + SKY_SEG_MAX - 1) / SKY_SEG_MAX;
+    const int per_frame = strips * (nframes > 0 ? nframes : 1);
+    const int nseg_fill = (want_ctas + per_frame - 1) / per_frame;
+    if (nseg_fill > nseg) nseg = nseg_fill;
+    const int nseg_cap = (H + 4 * SKY_H - 1) / (4 * SKY_H); // segments of at least 4 steps
+    if (nseg > nseg_cap) nseg = nseg_cap;
+    if (nseg < 1) nseg = 1;
     const int rows = (H + nseg - 1) / nseg;
     return (rows + SKY_H - 1) / SKY_H * SKY_H;
+}
+// upper bound of the number of CTAs (= fp64 partial-sum pairs) per frame over all launch sizes
+static inline int sky_max_blocks(int W, int H)
+{
+    const int rows = sky_segment_rows(W, H, 1);
+    return ((W + SKY_W - 1) / SKY_W) * ((H + rows - 1) / rows);
 }
 
 // sigma, threshold = float(sigma*t*1.5), minPeak = float(sigma*t*2.0)  [stardetector.cpp:125-129]

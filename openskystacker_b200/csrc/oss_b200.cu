@@ -87,6 +87,7 @@ struct oss_ctx {
     // every warp + accumulate kernel runs on this one stream: accumulation order = batch order = frame order
     cudaStream_t warp_stream = nullptr;
     bool stagger = false;
+    int sky_blocks = 0; // CTAs per frame of the last sky_sub_stats launch (= partial sums finalize_stats adds up)
     int prev_pipe = -1;
     long long light_batches = 0;
     std::string err;
@@ -464,7 +465,7 @@ int oss_set_geometry(oss_ctx *c, int W, int H, int C, int sample, int slots)
         Workspace &w = pp.ws;
         w = Workspace{};
         w.strideP = pad64(g.P); w.stridePC = pad64(PC); w.strideLo = lo; w.strideSeg = nsegs;
-        w.stat_blocks = ((W + SKY_W - 1) / SKY_W) * ((H + sky_segment_rows(H) - 1) / sky_segment_rows(H));
+        w.stat_blocks = sky_max_blocks(W, H);
         w.stridePart = 2ll * w.stat_blocks;
         long long scan_max = nsegs + 1 > cap ? nsegs + 1 : cap;
         w.strideScan = (scan_max + SCAN_ITEMS - 1) / SCAN_ITEMS + 1;
@@ -635,7 +636,8 @@ static int run_detect(oss_ctx *c, const FramePtrs &fp, int n, bool use_masters, 
            c->dx, c->dy, w.lo, w.strideLo, g.lw, g.lh);
     LAUNCH("median5", k_median5, dim3((g.lw + 31) / 32, (g.lh + 7) / 8, n), 256, 0, w.lo, w.med, w.strideLo, g.lw, g.lh);
     const long long strideGray = g.C == 3 ? w.strideP : w.stridePC;
-    const int seg_h = sky_segment_rows(g.H);
+    const int seg_h = sky_segment_rows(g.W, g.H, n);
+    c->sky_blocks = ((g.W + SKY_W - 1) / SKY_W) * ((g.H + seg_h - 1) / seg_h);
     LAUNCH("sky_sub_stats", k_sky_sub_stats, dim3((g.W + SKY_W - 1) / SKY_W, (g.H + seg_h - 1) / seg_h, n), SKY_NT, kSkySmemBytes,
            w.gray, strideGray, w.med, w.strideLo, g.lw, c->ux, c->uy, w.stars, w.strideP, w.segmax, w.strideSeg, g.nseg,
            w.partials, w.stridePart, g, seg_h);
@@ -652,7 +654,7 @@ static int run_detect_tail(oss_ctx *c, int n, int threshold)
     Workspace &w = c->ws;
     const Geom &g = c->g;
     int r;
-    LAUNCH("finalize_stats", k_finalize_stats, n, 256, 0, w.partials, w.stridePart, w.stat_blocks, w.ds, threshold, g);
+    LAUNCH("finalize_stats", k_finalize_stats, n, 256, 0, w.partials, w.stridePart, c->sky_blocks, w.ds, threshold, g);
     const long long nsegs = w.strideSeg;
     const int segblocks = (int)((nsegs + 255) / 256);
     LAUNCH("segment_masks", k_segment_masks, dim3(segblocks, n), 256, 0, w.stars, w.strideP, w.segmax, w.strideSeg, w.segmask,
