@@ -61,14 +61,20 @@ static bool nccl_load(std::string *why)
     return true;
 }
 
-// One processing pipeline: its own stream, staging buffers and detection work space.
-// Batches of lights alternate between pipelines so that the FP32-bound kernels of one batch
-// (sky estimation, component walk, alignment) overlap the HBM-bound kernels of another
-// (calibration, warp + accumulate).  Only the accumulator is shared; the warp kernels are
-// chained by events in batch order, which keeps the summation order = frame order.
+// Scheduling.  Kernels fall in two classes: BULK kernels that fill the GPU (masters, calibration, sky, warp) and the
+// latency-bound detection TAIL of a batch (thresholding, scans, union-find, component walk, alignment: ~35 dependent
+// launches of a few CTAs each).  All bulk kernels go to ONE low-priority stream in a fixed order; the tail of each batch
+// runs on a high-priority stream of its own pipeline (= work space) and overlaps the bulk kernels of the following
+// batches.  The warp + accumulate of a batch is queued on the bulk stream only after the bulk kernels of the next
+// npipes - 1 batches, by which time its tail has finished, so the bulk stream never waits:
+//     cal+sky(0) cal+sky(1) cal+sky(2) warp(0) cal+sky(3) warp(1) ...      (bulk stream, 3 pipelines)
+//                tail(0)    tail(1)    tail(2)  ...                         (chain streams)
+// Accumulation order = batch order = frame order.  Co-running two bulk kernels from different streams was measured
+// slower than running them back to back (they evict each other's CTAs from the SMs), descending stream priorities
+// per pipeline likewise; the block scheduler serves equal-priority streams in launch order anyway.
 #define OSS_MAX_PIPES 4
 struct Pipe {
-    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaStream_t copy_stream = nullptr;  // H2D staging copies of this pipeline
     cudaStream_t chain_stream = nullptr; // high priority: the latency-bound detection tail + alignment of a batch
     Workspace ws{};
     int *d_xy = nullptr, *d_nxy = nullptr;
@@ -84,11 +90,10 @@ struct oss_ctx {
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     Pipe pipes[OSS_MAX_PIPES];
     int npipes = 3, want_pipes = 3, cur = 0;
-    // every warp + accumulate kernel runs on this one stream: accumulation order = batch order = frame order
-    cudaStream_t warp_stream = nullptr;
-    bool stagger = false;
+    cudaStream_t bulk = nullptr;         // the one low-priority stream of all bulk kernels
+    struct PendingWarp { int pipe, nb; };
+    std::vector<PendingWarp> pending_warps; // detected batches whose warp + accumulate is not queued yet, oldest first
     int sky_blocks = 0; // CTAs per frame of the last sky_sub_stats launch (= partial sums finalize_stats adds up)
-    int prev_pipe = -1;
     long long light_batches = 0;
     std::string err;
     Geom g{};
@@ -153,27 +158,32 @@ static int fail(oss_ctx *c, int code, const char *fmt, ...)
     return code;
 }
 
+// the stream a pipeline's bulk kernels (calibration, sky, copies; also the masters) go to
+static cudaStream_t bulk_of(oss_ctx *c, int) { return c->bulk; }
+
 static void select_pipe(oss_ctx *c, int p)
 {
     Pipe &o = c->pipes[c->cur];
     o.batch_counter = c->batch_counter;
     Pipe &n = c->pipes[p];
     c->cur = p;
-    c->stream = n.stream; c->copy_stream = n.copy_stream;
+    c->stream = bulk_of(c, p); c->copy_stream = n.copy_stream;
     c->ws = n.ws; c->d_xy = n.d_xy; c->d_nxy = n.d_nxy;
     for (int i = 0; i < 2; i++) { c->raw_stage[i] = n.raw_stage[i]; c->copy_done[i] = n.copy_done[i]; c->raw_free[i] = n.raw_free[i]; }
     c->batch_counter = n.batch_counter;
 }
 
+static int flush_warps(oss_ctx *c, size_t keep);
+
 static cudaError_t sync_all(oss_ctx *c)
 {
     cudaError_t e = cudaSuccess;
+    if (flush_warps(c, 0) != OSS_OK) e = cudaErrorLaunchFailure;
     for (int p = 0; p < OSS_MAX_PIPES; p++) {
         if (c->pipes[p].copy_stream) { cudaError_t r = cudaStreamSynchronize(c->pipes[p].copy_stream); if (r != cudaSuccess) e = r; }
-        if (c->pipes[p].stream) { cudaError_t r = cudaStreamSynchronize(c->pipes[p].stream); if (r != cudaSuccess) e = r; }
         if (c->pipes[p].chain_stream) { cudaError_t r = cudaStreamSynchronize(c->pipes[p].chain_stream); if (r != cudaSuccess) e = r; }
     }
-    if (c->warp_stream) { cudaError_t r = cudaStreamSynchronize(c->warp_stream); if (r != cudaSuccess) e = r; }
+    if (c->bulk) { cudaError_t r = cudaStreamSynchronize(c->bulk); if (r != cudaSuccess) e = r; }
     return e;
 }
 
@@ -281,7 +291,6 @@ static void free_geometry(oss_ctx *c)
         pp.batch_counter = 0;
     }
     c->light_batches = 0;
-    c->prev_pipe = -1;
     c->has_geom = false;
     c->has_ref = false;
     c->synth_plane = nullptr;
@@ -319,19 +328,12 @@ int oss_create(oss_ctx **out, int device)
     oss_ctx *c = new oss_ctx();
     c->device = device;
     bool ok = cudaSetDevice(device) == cudaSuccess;
-    // Two priority levels.  The block scheduler dispatches kernels of equal priority in launch order, so a small kernel
-    // queued behind another stream's 10^4-CTA kernel waits for that whole grid to be dispatched.  The latency-bound
-    // detection tail (thresholding, scans, components, alignment: dozens of dependent launches of a few CTAs each)
-    // therefore runs on a high-priority stream per pipeline and takes SM slots as they free up, while the bulk kernels
-    // (calibration, sky, warp, masters) of all pipelines share the low level.
-    int prio_least = 0, prio_greatest = 0;
-    ok = ok && cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest) == cudaSuccess; // numerically greatest <= least
-    if (const char *e = getenv("OSS_B200_CHAIN_PRIO")) if (atoi(e) == 0) prio_greatest = prio_least;
+    int prio_least = 0, prio_greatest = 0; // numerically greatest <= least
+    ok = ok && cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest) == cudaSuccess;
     for (int p = 0; ok && p < OSS_MAX_PIPES; p++)
-        ok = cudaStreamCreateWithPriority(&c->pipes[p].stream, cudaStreamNonBlocking, prio_least) == cudaSuccess &&
-             cudaStreamCreateWithPriority(&c->pipes[p].chain_stream, cudaStreamNonBlocking, prio_greatest) == cudaSuccess &&
+        ok = cudaStreamCreateWithPriority(&c->pipes[p].chain_stream, cudaStreamNonBlocking, prio_greatest) == cudaSuccess &&
              cudaStreamCreateWithPriority(&c->pipes[p].copy_stream, cudaStreamNonBlocking, prio_greatest) == cudaSuccess;
-    ok = ok && cudaStreamCreateWithPriority(&c->warp_stream, cudaStreamNonBlocking, prio_least) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithPriority(&c->bulk, cudaStreamNonBlocking, prio_least) == cudaSuccess;
     if (!ok) {
         delete c;
         return OSS_E_CUDA;
@@ -343,8 +345,7 @@ int oss_create(oss_ctx **out, int device)
         return OSS_E_CUDA;
     }
     if (const char *e = getenv("OSS_B200_PIPES")) c->want_pipes = atoi(e);
-    if (const char *e = getenv("OSS_B200_STAGGER")) c->stagger = atoi(e) != 0;
-    c->stream = c->pipes[0].stream;
+    c->stream = c->bulk;
     c->copy_stream = c->pipes[0].copy_stream;
     // constant tables
     float taps[31];
@@ -359,9 +360,9 @@ int oss_create(oss_ctx **out, int device)
         cudaFuncSetAttribute(k_focas, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FocasSmem)) != cudaSuccess ||
         cudaFuncSetAttribute(k_warp_accumulate_tiled<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, warp_tiled_smem<3>()) != cudaSuccess ||
         cudaFuncSetAttribute(k_warp_accumulate_tiled<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, warp_tiled_smem<1>()) != cudaSuccess) {
-        for (int p = 0; p < OSS_MAX_PIPES; p++) { cudaStreamDestroy(c->pipes[p].stream); cudaStreamDestroy(c->pipes[p].copy_stream); if (c->pipes[p].chain_stream) cudaStreamDestroy(c->pipes[p].chain_stream); }
-    cudaStreamDestroy(c->warp_stream);
-        cudaStreamDestroy(c->warp_stream);
+        for (int p = 0; p < OSS_MAX_PIPES; p++) { if (c->pipes[p].copy_stream) cudaStreamDestroy(c->pipes[p].copy_stream); if (c->pipes[p].chain_stream) cudaStreamDestroy(c->pipes[p].chain_stream); }
+    if (c->bulk) cudaStreamDestroy(c->bulk);
+        if (c->bulk) cudaStreamDestroy(c->bulk);
         delete c;
         return OSS_E_CUDA;
     }
@@ -381,8 +382,8 @@ void oss_destroy(oss_ctx *c)
     for (auto p : c->h_al_chunks) cudaFreeHost(p);
     prof_flush(c);
     for (auto e : c->event_pool) cudaEventDestroy(e);
-    for (int p = 0; p < OSS_MAX_PIPES; p++) { cudaStreamDestroy(c->pipes[p].stream); cudaStreamDestroy(c->pipes[p].copy_stream); if (c->pipes[p].chain_stream) cudaStreamDestroy(c->pipes[p].chain_stream); }
-    cudaStreamDestroy(c->warp_stream);
+    for (int p = 0; p < OSS_MAX_PIPES; p++) { if (c->pipes[p].copy_stream) cudaStreamDestroy(c->pipes[p].copy_stream); if (c->pipes[p].chain_stream) cudaStreamDestroy(c->pipes[p].chain_stream); }
+    if (c->bulk) cudaStreamDestroy(c->bulk);
     if (c->ref_ready) cudaEventDestroy(c->ref_ready);
     if (c->ref_copied) cudaEventDestroy(c->ref_copied);
     if (c->h_ref_ds) cudaFreeHost(c->h_ref_ds);
@@ -793,7 +794,6 @@ int oss_reset_stack(oss_ctx *c)
     CK(cudaMemsetAsync(c->d_valid, 0, 16, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     c->has_ref = false;
-    c->prev_pipe = -1;
     c->ref_in_sum = true;
     c->nlights = 0;
     c->extra_valid = 0;
@@ -817,10 +817,11 @@ int oss_set_reference(oss_ctx *c, const void *frame, int mem, int threshold)
     if (rc) return rc;
     rc = run_detect(c, fp, 1, true, threshold, set);
     if (rc) return rc;
+    if (set >= 0) CK(cudaEventSynchronize(c->copy_done[set])); // a host frame may be reused as soon as this call returns
     const long long PC = g.P * g.C;
     {   // bulk copy: on the pipeline's low-priority stream, ordered behind the calibration there
         cudaStream_t chain = c->stream;
-        c->stream = c->pipes[c->cur].stream;
+        c->stream = bulk_of(c, c->cur);
         LAUNCH("copy_reference", k_copy_f32, (unsigned)((PC + 1023) / 1024), 256, 0, w.cal, c->ref_cal, PC);
         c->stream = chain;
     }
@@ -868,6 +869,38 @@ static int ensure_report_room(oss_ctx *c, int upto)
     return OSS_OK;
 }
 
+} // extern "C"
+
+// queue the warp + accumulate kernels of the oldest pending batches until at most `keep` remain
+static int flush_warps(oss_ctx *c, size_t keep)
+{
+    const Geom &g = c->g;
+    while (c->pending_warps.size() > keep) {
+        const oss_ctx::PendingWarp pw = c->pending_warps.front();
+        c->pending_warps.erase(c->pending_warps.begin());
+        Pipe &pp = c->pipes[pw.pipe];
+        Workspace &w = pp.ws;
+        cudaStream_t saved = c->stream;
+        c->stream = c->bulk;
+        CK(cudaStreamWaitEvent(c->stream, pp.detect_done, 0));
+        LAUNCH("warp_tables", k_warp_tables, dim3((g.W + g.H + 255) / 256, pw.nb), 256, 0, w.align, w.warp_ab, (long long)g.W, w.warp_xy,
+               (long long)g.H, g.W, g.H);
+        const dim3 wgrid((g.W + WT_W - 1) / WT_W, (g.H + WT_H - 1) / WT_H);
+        if (g.C == 3) {
+            LAUNCH("warp_accumulate", k_warp_accumulate_tiled<3>, wgrid, 256, warp_tiled_smem<3>(), w.cal, w.stridePC, w.align, pw.nb,
+                   w.warp_ab, (long long)g.W, w.warp_xy, (long long)g.H, c->sum, g.W, g.H);
+        } else {
+            LAUNCH("warp_accumulate", k_warp_accumulate_tiled<1>, wgrid, 256, warp_tiled_smem<1>(), w.cal, w.stridePC, w.align, pw.nb,
+                   w.warp_ab, (long long)g.W, w.warp_xy, (long long)g.H, c->sum, g.W, g.H);
+        }
+        CK(cudaEventRecord(pp.warp_done, c->stream));
+        c->stream = saved;
+    }
+    return OSS_OK;
+}
+
+extern "C" {
+
 int oss_add_lights(oss_ctx *c, const void *const *frames, int n, int mem)
 {
     NEED_GEOM();
@@ -881,9 +914,13 @@ int oss_add_lights(oss_ctx *c, const void *const *frames, int n, int mem)
         select_pipe(c, (int)(c->light_batches++ % c->npipes));
         Workspace &w = c->ws;
         // this pipeline's previous batch must have been warped before its calibrated planes are overwritten
+        for (bool busy = true; busy;) {
+            busy = false;
+            for (const auto &pw : c->pending_warps) busy |= pw.pipe == c->cur;
+            if (busy) { rc = flush_warps(c, c->pending_warps.size() - 1); if (rc) return rc; }
+        }
         CK(cudaStreamWaitEvent(c->stream, c->pipes[c->cur].warp_done, 0));
-        if (c->stagger && c->prev_pipe >= 0 && c->prev_pipe != c->cur) CK(cudaStreamWaitEvent(c->stream, c->pipes[c->prev_pipe].sky_done, 0));
-        c->prev_pipe = c->cur;
+        CK(cudaStreamWaitEvent(c->stream, c->ref_copied, 0)); // ... and the reference's detection tail has left pipeline 0
         FramePtrs fp{};
         int set;
         rc = stage_frames(c, frames + b0, nb, mem, &fp, &set);
@@ -894,23 +931,6 @@ int oss_add_lights(oss_ctx *c, const void *const *frames, int n, int mem)
         CK(cudaStreamWaitEvent(c->stream, c->ref_ready, 0)); // the reference may still be in flight on pipeline 0
         LAUNCH("focas_match_fit", k_focas, nb, FOCAS_NT, sizeof(FocasSmem), c->d_ref, c->d_xy, c->d_nxy, w.align, c->d_valid,
                (int *)nullptr, (int *)nullptr, (long long *)nullptr);
-        // warp + accumulate on the shared low-priority stream, in batch order
-        CK(cudaEventRecord(c->pipes[c->cur].detect_done, c->stream));
-        cudaStream_t pipe_stream = c->stream;
-        c->stream = c->warp_stream;
-        CK(cudaStreamWaitEvent(c->stream, c->pipes[c->cur].detect_done, 0));
-        LAUNCH("warp_tables", k_warp_tables, dim3((g.W + g.H + 255) / 256, nb), 256, 0, w.align, w.warp_ab, (long long)g.W, w.warp_xy,
-               (long long)g.H, g.W, g.H);
-        const dim3 wgrid((g.W + WT_W - 1) / WT_W, (g.H + WT_H - 1) / WT_H);
-        if (g.C == 3) {
-            LAUNCH("warp_accumulate", k_warp_accumulate_tiled<3>, wgrid, 256, warp_tiled_smem<3>(), w.cal, w.stridePC, w.align, nb, w.warp_ab,
-                   (long long)g.W, w.warp_xy, (long long)g.H, c->sum, g.W, g.H);
-        } else {
-            LAUNCH("warp_accumulate", k_warp_accumulate_tiled<1>, wgrid, 256, warp_tiled_smem<1>(), w.cal, w.stridePC, w.align, nb, w.warp_ab,
-                   (long long)g.W, w.warp_xy, (long long)g.H, c->sum, g.W, g.H);
-        }
-        CK(cudaEventRecord(c->pipes[c->cur].warp_done, c->stream));
-        c->stream = pipe_stream;
         // reports back to pinned host memory, asynchronously; a batch never straddles a chunk
         // boundary more than once
         int done = 0;
@@ -921,6 +941,12 @@ int oss_add_lights(oss_ctx *c, const void *const *frames, int n, int mem)
             CK(cudaMemcpyAsync(c->h_al_chunks[ch] + off, w.align + done, sizeof(AlignOut) * m, cudaMemcpyDeviceToHost, c->stream));
             done += m;
         }
+        CK(cudaEventRecord(c->pipes[c->cur].detect_done, c->stream));
+        // warp + accumulate: queued in batch order, but only after the bulk kernels of the next npipes - 1
+        // batches, so that this batch's latency-bound tail has run by the time the bulk stream reaches its warp
+        c->pending_warps.push_back({c->cur, nb});
+        rc = flush_warps(c, (size_t)(c->npipes - 1));
+        if (rc) return rc;
         c->nlights += nb;
     }
     return OSS_OK;
@@ -1028,7 +1054,7 @@ int oss_detect_stars_batch(oss_ctx *c, const void *const *frames, int n, int mem
     std::vector<DetectState> d(c->slots);
     for (int b0 = 0; b0 < n; b0 += c->slots) {
         int nb = n - b0 < c->slots ? n - b0 : c->slots;
-        c->stream = c->pipes[c->cur].stream; // run_detect leaves the pipeline on its chain stream; the previous batch is complete
+        c->stream = bulk_of(c, c->cur); // run_detect leaves the pipeline on its chain stream; the previous batch is complete
         FramePtrs fp{};
         int set;
         int rc = stage_frames(c, frames + b0, nb, mem, &fp, &set);
