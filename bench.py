@@ -383,9 +383,9 @@ def main():
         name = max(hbm, key=lambda k: prof[k][0])
         k = kernels[name]
         # dram__bytes_read + dram__bytes_write per launch from the committed ncu --set full capture
-        # (profiles/r01_ncu_summary.md), valid for the default shape only: 24 MP RGB16, M = 3, 10 frames per launch
-        ncu_traffic = {"calibrate_gray": 2.307e9 + 3.782e9, "warp_accumulate": 3.183e9 + 0.292e9}
-        default_shape = (W, H, a.slots, a.lights) == (6000, 4000, 10, 50)
+        # (profiles/r01_ncu_summary.md), valid for the default shape only: 24 MP RGB16, M = 3, 17 frames per launch
+        ncu_traffic = {"calibrate_gray": 3.316e9 + 6.470e9, "warp_accumulate": 5.214e9 + 0.295e9}
+        default_shape = (W, H, a.slots, a.lights) == (6000, 4000, 17, 50)
         traffic = ncu_traffic.get(name) if default_shape else None
         roof = {"bound": "hbm", "kernel": name, "achieved": k["achieved_gbs"], "peak": peak, "unit": "GB/s",
                 "frac": k["hbm_frac"], "traffic": traffic, "peak_source": peak_src, "launches": k["launches"],

@@ -107,8 +107,9 @@ OSS_API int oss_memcpy_d2h(oss_ctx *ctx, void *dst_host, const void *src_dev, si
 OSS_API int oss_set_geometry(oss_ctx *ctx, int width, int height, int channels, int sample,
                              int frames_in_flight);
 /* Number of independent pipelines (streams + work spaces) that batches of lights alternate
- * between, so FP32-bound and HBM-bound kernels of different batches overlap; 1..4, default 2.
- * The accumulation order stays the frame order.  Takes effect at the next oss_set_geometry. */
+ * between: the latency-bound detection tail of one batch overlaps the bulk kernels of the next
+ * n - 1 batches; 1..4, default 3.  The accumulation order stays the frame order.  Takes effect at
+ * the next oss_set_geometry. */
 OSS_API int oss_set_pipelines(oss_ctx *ctx, int n);
 
 /* ---- master frames: stackBias / stackDarks / stackDarkFlats / stackFlats, util.cpp:584-722
@@ -125,7 +126,10 @@ OSS_API int oss_clear_masters(oss_ctx *ctx);
  * oss_set_reference: getCalibratedImage(ref) (util.cpp:266-274), workingImage = ref.clone()
  *   and totalValidImages = 1 (imagestacker.cpp:286-287,304); the reference stars are
  *   detected ONCE here and cached (the reference re-detects them for every light,
- *   util.cpp:559 — same values, no need to repeat).
+ *   util.cpp:559 — same values, no need to repeat).  Asynchronous like oss_add_lights: it
+ *   returns once the work is queued (a host frame has been copied by then and may be reused);
+ *   the detection runs while the first lights are being calibrated.  Its results and a
+ *   workspace overflow (OSS_E_CAPACITY) surface at oss_get_reference_stars / oss_finish.
  * oss_add_lights: the body of processConcurrent's loop (util.cpp:738-751) for n lights:
  *   calibrate, getStars, triangles, vote, HFTI fit, warpAffine, accumulate; lights whose
  *   alignment fails are skipped silently.  Asynchronous: it returns once the copies and
