@@ -292,6 +292,7 @@ bool writeTiff(const std::string &path, const T *px, int w, int h, int c, int fo
 
 bool probeImage(const std::string &path, ImageInfo *info, std::string *err)
 {
+    if (isFitsFile(path)) return probeFits(path, info, err);
     Reader r;
     Ifd d;
     return open(path, 1 << 16, &r, &d, info, err);
@@ -299,6 +300,7 @@ bool probeImage(const std::string &path, ImageInfo *info, std::string *err)
 
 bool readImageInto(const std::string &path, const ImageInfo &expect, void *dst, std::string *err)
 {
+    if (isFitsFile(path)) return readFitsInto(path, &expect, nullptr, dst, nullptr, err);
     Reader r;
     Ifd d;
     ImageInfo info;
@@ -310,6 +312,7 @@ bool readImageInto(const std::string &path, const ImageInfo &expect, void *dst, 
 
 bool readImage(const std::string &path, ImageInfo *info, std::vector<uint8_t> *pixels, std::string *err)
 {
+    if (isFitsFile(path)) return readFitsInto(path, nullptr, info, nullptr, pixels, err);
     Reader r;
     Ifd d;
     if (!open(path, 0, &r, &d, info, err)) return false;

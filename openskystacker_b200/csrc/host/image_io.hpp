@@ -1,8 +1,9 @@
 // Host-side image decode / encode for the ImageStacker facade (file codecs stay on the host,
 // as in the reference: readImage -> cv::imread, libstacker/src/util.cpp:277-298; cl/cl.cpp:205
-// cv::imwrite).  TIFF only: baseline strips, 8/16-bit unsigned or 32-bit float samples, 1 or 3
+// cv::imwrite).  TIFF: baseline strips, 8/16-bit unsigned or 32-bit float samples, 1 or 3
 // channels, uncompressed or LZW (+ horizontal predictor), either byte order.  Frames come back
-// interleaved HWC in cv::imread's channel order (B, G, R).
+// interleaved HWC in cv::imread's channel order (B, G, R).  FITS (fits_io.cpp): the primary HDU's first plane, BITPIX 8 / 16 /
+// -32 / -64, like fitsToMat (util.cpp:300-346); recognised by content ("SIMPLE  ="), so all three entry points take either.
 #pragma once
 #include <cstdint>
 #include <string>
@@ -25,6 +26,11 @@ bool readImageInto(const std::string &path, const ImageInfo &expect, void *dst, 
 bool readImage(const std::string &path, ImageInfo *info, std::vector<uint8_t> *pixels, std::string *err);
 // float32 / uint16 TIFF, channel order flipped back to RGB like cv::imwrite does
 bool writeTiffF32(const std::string &path, const float *hwc_bgr, int width, int height, int channels, std::string *err);
+// FITS primary HDU (fits_io.cpp)
+bool isFitsFile(const std::string &path);
+bool probeFits(const std::string &path, ImageInfo *info, std::string *err);
+bool readFitsInto(const std::string &path, const ImageInfo *expect, ImageInfo *info_out, void *dst, std::vector<uint8_t> *alloc,
+                  std::string *err);
 bool writeTiffU16(const std::string &path, const uint16_t *hwc_bgr, int width, int height, int channels, std::string *err);
 
 }  // namespace openskystacker

@@ -122,7 +122,8 @@ ImageRecord *getImageRecord(const std::string &filename)
     r->checked = true;
     ImageInfo info;
     std::string err;
-    if (getImageType(filename) == RGB_IMAGE && probeImage(filename, &info, &err)) { // util.cpp:134-143 without EXIF
+    // util.cpp:112-113 (FITS: axis(0) x axis(1)) and :134-143 (RGB, without EXIF)
+    if (getImageType(filename) != RAW_IMAGE && probeImage(filename, &info, &err)) {
         r->width = info.width;
         r->height = info.height;
     }

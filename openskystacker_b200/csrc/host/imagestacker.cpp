@@ -121,7 +121,7 @@ void ImageStacker::process(int tolerance, int threads)
     ImageType refType = getImageType(d->refImageFileName);
     for (const std::string &f : d->targetImageFileNames)
         if (getImageType(f) != refType) { error(oss_status_string(OSS_E_TYPE)); return; }
-    if (refType != RGB_IMAGE) { error("RAW and FITS decoding are not part of this build; convert the frames to 16-bit TIFF."); return; }
+    if (refType == RAW_IMAGE) { error("RAW decoding (LibRaw) is not part of this build; convert the frames to 16-bit TIFF or FITS."); return; }
 
     cancel = false;
     d->currentOperation = 1;

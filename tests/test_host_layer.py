@@ -173,3 +173,96 @@ def test_cli_end_to_end_matches_oracle(host, tmp_path):
     r = subprocess.run([CLI, "-f", lst, "-s", "-t", "20"], capture_output=True, text=True)
     nref = len(oracle.get_stars(oracle.u16_to_f32(ds["ref"]), 20)[0])
     assert r.returncode == 0 and r.stdout.strip().splitlines()[-1] == str(nref)
+
+
+# ---- FITS (fitsToMat, libstacker/src/util.cpp:300-346) -----------------------------------------------------------------
+def write_fits(path, data, bitpix, bzero=None, extra_axis=None):
+    """Minimal primary HDU: 80-byte cards, 2880-byte blocks, big-endian samples."""
+    h, w = data.shape[-2:]
+    cards = ["SIMPLE  = %20s" % "T", "BITPIX  = %20d" % bitpix, "NAXIS   = %20d" % (3 if extra_axis else 2),
+             "NAXIS1  = %20d" % w, "NAXIS2  = %20d" % h]
+    if extra_axis:
+        cards.append("NAXIS3  = %20d" % extra_axis)
+    if bzero is not None:
+        cards += ["BZERO   = %20.1f" % bzero, "BSCALE  = %20.1f" % 1.0]
+    cards += ["COMMENT made by the test-suite", "EXPTIME = %20.1f / seconds" % 30.0, "END"]
+    head = "".join(c.ljust(80) for c in cards).encode()
+    head += b" " * (-len(head) % 2880)
+    body = np.ascontiguousarray(data).astype({8: ">u1", 16: ">i2", 32: ">i4", -32: ">f4", -64: ">f8"}[bitpix]).tobytes()
+    body += b"\0" * (-len(body) % 2880)
+    with open(path, "wb") as f:
+        f.write(head + body)
+
+
+def test_fits_reader_follows_fitsToMat(host, tmp_path):
+    rng = np.random.default_rng(7)
+    h, w = 37, 53
+    u16 = rng.integers(0, 65536, (h, w)).astype(np.uint16)
+    # unsigned 16-bit the FITS way: BITPIX 16, BZERO 32768 (CFITSIO hands back unsigned shorts, util.cpp:316-321)
+    write_fits(tmp_path / "u16.fits", u16.astype(np.int32) - 32768, 16, bzero=32768.0)
+    got = read_tiff(host, str(tmp_path / "u16.fits"))
+    assert got.dtype == np.uint16 and np.array_equal(got, u16)          # no vertical flip: FITS row 0 = Mat row 0
+    # plain signed 16-bit: negative values saturate at 0 like CFITSIO's conversion to unsigned short
+    s16 = rng.integers(-200, 32768, (h, w)).astype(np.int16)
+    write_fits(tmp_path / "s16.fit", s16, 16)
+    assert np.array_equal(read_tiff(host, str(tmp_path / "s16.fit")), np.clip(s16, 0, None).astype(np.uint16))
+    u8 = rng.integers(0, 256, (h, w)).astype(np.uint8)
+    write_fits(tmp_path / "u8.fts", u8, 8)
+    got = read_tiff(host, str(tmp_path / "u8.fts"))
+    assert got.dtype == np.uint8 and np.array_equal(got, u8)
+    f32 = rng.random((h, w), dtype=np.float32)
+    write_fits(tmp_path / "f32.fits", f32, -32)
+    got = read_tiff(host, str(tmp_path / "f32.fits"))
+    assert got.dtype == np.float32 and np.array_equal(got, f32)
+    f64 = rng.random((h, w))
+    write_fits(tmp_path / "f64.fits", f64, -64)
+    assert np.array_equal(read_tiff(host, str(tmp_path / "f64.fits")), f64.astype(np.float32))   # convertTo(CV_32F), util.cpp:338
+    # a cube: the reference wraps only the first plane (rows x cols elements of the valarray)
+    cube = rng.integers(0, 65536, (3, h, w)).astype(np.uint16)
+    write_fits(tmp_path / "cube.fits", cube.astype(np.int32) - 32768, 16, bzero=32768.0, extra_axis=3)
+    assert np.array_equal(read_tiff(host, str(tmp_path / "cube.fits")), cube[0])
+    # BITPIX 32 is mis-read by the reference (8-byte unsigned long as CV_32SC1): refused, not imitated
+    write_fits(tmp_path / "i32.fits", rng.integers(0, 1000, (h, w)), 32)
+    whcs, err = (C.c_int * 4)(), C.create_string_buffer(256)
+    assert host.oss_host_probe_image(str(tmp_path / "i32.fits").encode(), whcs, err, 256) != 0 and b"BITPIX 32" in err.value
+    # truncated data must fail loudly
+    blob = (tmp_path / "u16.fits").read_bytes()
+    (tmp_path / "cut.fits").write_bytes(blob[:2880 + 100])
+    assert host.oss_host_probe_image(str(tmp_path / "cut.fits").encode(), whcs, err, 256) == 0
+    out = np.empty((h, w), np.uint16)
+    assert host.oss_host_read_image(str(tmp_path / "cut.fits").encode(), whcs, C.c_void_p(out.ctypes.data), err, 256) != 0
+    assert b"truncated" in err.value
+    # image list records carry the FITS geometry (util.cpp:112-113)
+    lst = write_list(tmp_path, [{"filename": "u16.fits", "type": "ref", "checked": True}])
+    buf = C.create_string_buffer(4096)
+    assert host.oss_host_load_image_list(lst.encode(), buf, 4096) == 0
+    assert f" {w} {h} " in buf.value.decode()
+
+
+@pytest.mark.gpu
+def test_cli_stacks_fits_like_the_oracle(host, tmp_path):
+    """Mono 16-bit FITS lights + darks through openskystacker-cl: same float32 stack as the oracle on the same arrays,
+    and -s counts the stars of the FITS reference (the reference's own testDetectStars case, test/testoss.cpp:37-39)."""
+    w, h = 1000, 700
+    ds = synth.dataset(w, h, 3, 1, nstars=120, ndarks=2, seed=99)
+    entries = []
+
+    def put(name, frame, kind):
+        write_fits(tmp_path / name, frame.astype(np.int32) - 32768, 16, bzero=32768.0)
+        entries.append({"filename": name, "type": kind, "checked": True})
+    put("ref.fits", ds["ref"], "ref")
+    for i, f in enumerate(ds["lights"]):
+        put(f"light{i}.fits", f, "light")
+    for i, f in enumerate(ds["darks"]):
+        put(f"dark{i}.fits", f, "dark")
+    lst = write_list(tmp_path, entries)
+    out = str(tmp_path / "stack")
+    r = subprocess.run([CLI, "-f", lst, "-o", out, "-t", "20", "-j", "2"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    got = cv2.imread(out + ".tif", cv2.IMREAD_ANYDEPTH | cv2.IMREAD_ANYCOLOR)
+    want = oracle.stack(ds["ref"], ds["lights"], 20, dark_frames=ds["darks"])
+    assert want["total_valid"] == 4
+    assert got.shape == want["image"].shape and np.array_equal(got.view(np.uint32), want["image"].view(np.uint32))
+    r = subprocess.run([CLI, "-f", lst, "-s", "-t", "20"], capture_output=True, text=True)
+    nref = len(oracle.get_stars(oracle.u16_to_f32(ds["ref"]), 20)[0])
+    assert r.returncode == 0 and r.stdout.strip().splitlines()[-1] == str(nref)
