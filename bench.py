@@ -124,12 +124,14 @@ class Inputs:
 def run_job(eng, B, cal, ref, light_arr, nlights, mem, result_host, comm=None, rank=0):
     """One step.  cal = (bias_ptrs, dark_ptrs, flat_ptrs) as ctypes arrays + counts."""
     L, h = eng._L, eng._h
-    if rank == 0:
-        for kind, (arr, n) in zip((B.BIAS, B.DARK, B.FLAT), cal):
+    for kind, (arr, n) in zip((B.BIAS, B.DARK, B.FLAT), cal):
+        if rank == 0:
             eng._ck(L.oss_build_master(h, kind, arr, n, mem))
+        if comm:
+            eng.comm_broadcast_master(kind, 0)  # asynchronous: overlaps the next master and the reference on rank 0
+    if rank == 0:
         eng._ck(L.oss_set_reference(h, ref, mem, 20))
     if comm:
-        eng.comm_broadcast_masters(0)
         eng.comm_broadcast_reference(0)
     eng._ck(L.oss_add_lights(h, light_arr, nlights, mem))
     if comm:

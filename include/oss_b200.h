@@ -183,6 +183,10 @@ OSS_API int oss_warp_affine(oss_ctx *ctx, const float *src_host, float *dst_host
 OSS_API int oss_comm_unique_id(void *id128);
 OSS_API int oss_comm_init(oss_ctx *ctx, const void *id128, int rank, int nranks);
 OSS_API int oss_comm_broadcast_masters(oss_ctx *ctx, int root);
+/* one master (oss_master kind), asynchronously on a stream of its own: on the root it overlaps the building of the next
+ * master and the reference frame; calibration waits for it on the device.  Every rank calls it for the same kinds in the
+ * same order (the image list tells each rank which masters exist). */
+OSS_API int oss_comm_broadcast_master(oss_ctx *ctx, int kind, int root);
 /* ships the calibrated reference's star list + detection threshold; only `root` keeps the
  * reference frame inside its sum (imagestacker.cpp:287,304) */
 OSS_API int oss_comm_broadcast_reference(oss_ctx *ctx, int root);

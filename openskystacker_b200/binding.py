@@ -87,6 +87,7 @@ _SIGS = {
     "oss_comm_unique_id": (C.c_int, [C.c_void_p]),
     "oss_comm_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "oss_comm_broadcast_masters": (C.c_int, [C.c_void_p, C.c_int]),
+    "oss_comm_broadcast_master": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "oss_comm_broadcast_reference": (C.c_int, [C.c_void_p, C.c_int]),
     "oss_comm_reduce": (C.c_int, [C.c_void_p, C.c_int]),
     "oss_mark": (C.c_int, [C.c_void_p, C.c_int]),
@@ -327,6 +328,9 @@ class Engine:
 
     def comm_broadcast_masters(self, root=0):
         self._ck(self._L.oss_comm_broadcast_masters(self._h, root))
+
+    def comm_broadcast_master(self, kind, root=0):
+        self._ck(self._L.oss_comm_broadcast_master(self._h, kind, root))
 
     def comm_broadcast_reference(self, root=0):
         self._ck(self._L.oss_comm_broadcast_reference(self._h, root))

@@ -143,6 +143,8 @@ struct oss_ctx {
     // multi-GPU
     ncclComm_t comm = nullptr;
     int rank = 0, nranks = 1;
+    cudaStream_t comm_stream = nullptr;   // master broadcasts run here, beside the bulk stream
+    cudaEvent_t comm_fork = nullptr, masters_ready = nullptr;
 };
 
 static const int kChunk = 1024;
@@ -175,7 +177,7 @@ static void select_pipe(oss_ctx *c, int p)
 
 static int flush_warps(oss_ctx *c, size_t keep);
 
-static cudaError_t sync_all(oss_ctx *c)
+static cudaError_t sync_all(oss_ctx *c, bool with_comm = true)
 {
     cudaError_t e = cudaSuccess;
     if (flush_warps(c, 0) != OSS_OK) e = cudaErrorLaunchFailure;
@@ -184,6 +186,7 @@ static cudaError_t sync_all(oss_ctx *c)
         if (c->pipes[p].chain_stream) { cudaError_t r = cudaStreamSynchronize(c->pipes[p].chain_stream); if (r != cudaSuccess) e = r; }
     }
     if (c->bulk) { cudaError_t r = cudaStreamSynchronize(c->bulk); if (r != cudaSuccess) e = r; }
+    if (with_comm && c->comm_stream) { cudaError_t r = cudaStreamSynchronize(c->comm_stream); if (r != cudaSuccess) e = r; }
     return e;
 }
 
@@ -384,6 +387,9 @@ void oss_destroy(oss_ctx *c)
     for (auto e : c->event_pool) cudaEventDestroy(e);
     for (int p = 0; p < OSS_MAX_PIPES; p++) { if (c->pipes[p].copy_stream) cudaStreamDestroy(c->pipes[p].copy_stream); if (c->pipes[p].chain_stream) cudaStreamDestroy(c->pipes[p].chain_stream); }
     if (c->bulk) cudaStreamDestroy(c->bulk);
+    if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
+    if (c->comm_fork) cudaEventDestroy(c->comm_fork);
+    if (c->masters_ready) cudaEventDestroy(c->masters_ready);
     if (c->ref_ready) cudaEventDestroy(c->ref_ready);
     if (c->ref_copied) cudaEventDestroy(c->ref_copied);
     if (c->h_ref_ds) cudaFreeHost(c->h_ref_ds);
@@ -630,6 +636,7 @@ static int run_detect(oss_ctx *c, const FramePtrs &fp, int n, bool use_masters, 
 {
     Workspace &w = c->ws;
     const Geom &g = c->g;
+    if (use_masters && c->masters_ready) CK(cudaStreamWaitEvent(c->stream, c->masters_ready, 0)); // broadcasts in flight
     int r = dispatch_calibrate(c, fp, n, use_masters);
     if (r) return r;
     if (stage_set >= 0) CK(cudaEventRecord(c->raw_free[stage_set], c->stream));
@@ -712,12 +719,23 @@ static int need_geom(oss_ctx *c)
         select_pipe(c, 0);                                                                     \
     } while (0)
 
+// same, but master broadcasts in flight on the comm stream (oss_comm_broadcast_master) keep running: for the calls that
+// only touch this rank's own bulk work (building masters, the reference)
+#define USE_PIPE0_LOCAL()                                                                      \
+    do {                                                                                       \
+        int r_ = need_geom(c);                                                                 \
+        if (r_) return r_;                                                                     \
+        cudaError_t e_ = sync_all(c, false);                                                   \
+        if (e_ != cudaSuccess) return fail(c, OSS_E_CUDA, "stream sync failed: %s", cudaGetErrorString(e_)); \
+        select_pipe(c, 0);                                                                     \
+    } while (0)
+
 extern "C" {
 
 // ---- masters ---------------------------------------------------------------------------
 int oss_build_master(oss_ctx *c, int kind, const void *const *frames, int n, int mem)
 {
-    USE_PIPE0();
+    USE_PIPE0_LOCAL();
     if (kind < 0 || kind > 3 || n < 1 || !frames) return fail(c, OSS_E_ARG, "bad master arguments");
     const Geom &g = c->g;
     const long long count = g.P * g.C;
@@ -789,7 +807,7 @@ int oss_clear_masters(oss_ctx *c)
 // ---- stacking --------------------------------------------------------------------------
 int oss_reset_stack(oss_ctx *c)
 {
-    USE_PIPE0();
+    USE_PIPE0_LOCAL();
     CK(cudaMemsetAsync(c->sum, 0, (size_t)c->g.P * c->g.C * sizeof(float), c->stream));
     CK(cudaMemsetAsync(c->d_valid, 0, 16, c->stream));
     CK(cudaStreamSynchronize(c->stream));
@@ -805,7 +823,7 @@ int oss_reset_stack(oss_ctx *c)
 
 int oss_set_reference(oss_ctx *c, const void *frame, int mem, int threshold)
 {
-    USE_PIPE0();
+    USE_PIPE0_LOCAL();
     if (!frame) return fail(c, OSS_E_ARG, "null reference frame");
     int rc = oss_reset_stack(c);
     if (rc) return rc;
@@ -1204,6 +1222,31 @@ int oss_comm_broadcast_masters(oss_ctx *c, int root)
         NK(g_nccl.Broadcast(c->master[k], c->master[k], (size_t)count, ncclFloat32, root, c->comm, c->stream));
     }
     CK(cudaStreamSynchronize(c->stream));
+    return OSS_OK;
+}
+
+// One master, asynchronously: the broadcast runs on its own stream behind whatever produced the master, so on the root
+// it overlaps the building of the next master and the reference frame; calibration kernels wait for it on the device.
+// Every rank calls it for the same kinds in the same order.
+int oss_comm_broadcast_master(oss_ctx *c, int kind, int root)
+{
+    NEED_GEOM();
+    if (!c->comm) return fail(c, OSS_E_ARG, "oss_comm_init has not been called");
+    if (kind < 0 || kind > 3) return fail(c, OSS_E_ARG, "bad master kind");
+    if (c->rank == root && !c->master[kind]) return fail(c, OSS_E_ARG, "the root has not built master %d", kind);
+    const long long count = c->g.P * c->g.C;
+    if (!c->master[kind]) DA(c->master[kind], count);
+    if (!c->comm_stream) {
+        int lo = 0, hi = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CK(cudaStreamCreateWithPriority(&c->comm_stream, cudaStreamNonBlocking, hi));
+        CK(cudaEventCreateWithFlags(&c->comm_fork, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&c->masters_ready, cudaEventDisableTiming));
+    }
+    CK(cudaEventRecord(c->comm_fork, c->bulk)); // after the kernels that wrote (root) or still read (others) this master
+    CK(cudaStreamWaitEvent(c->comm_stream, c->comm_fork, 0));
+    NK(g_nccl.Broadcast(c->master[kind], c->master[kind], (size_t)count, ncclFloat32, root, c->comm, c->comm_stream));
+    CK(cudaEventRecord(c->masters_ready, c->comm_stream));
     return OSS_OK;
 }
 

@@ -28,14 +28,18 @@ def sharded_stack(eng, dist, ref, lights, threshold, calib=None, mem=B.HOST, wan
     shard); `ref` and `calib` (dict kind -> frames) are only read on rank 0.  Returns
     (image, total_valid) on rank 0 and (None, 0) elsewhere."""
     rank, world = dist.get_rank(), dist.get_world_size()
+    kinds = [[k for k in (B.BIAS, B.DARK, B.DARKFLAT, B.FLAT) if calib and calib.get(k)] if rank == 0 else None]
+    if world > 1:
+        dist.broadcast_object_list(kinds, src=0)     # which masters exist (every rank of a real job reads it off the image list)
+    eng.clear_masters()
+    for kind in kinds[0]:                            # imagestacker.cpp:262-281 order
+        if rank == 0:
+            eng.build_master(kind, calib[kind], mem)
+        if world > 1:
+            eng.comm_broadcast_master(kind, 0)       # asynchronous: overlaps the next master and the reference on rank 0
     if rank == 0:
-        eng.clear_masters()
-        for kind in (B.BIAS, B.DARK, B.DARKFLAT, B.FLAT):   # imagestacker.cpp:262-281 order
-            if calib and calib.get(kind):
-                eng.build_master(kind, calib[kind], mem)
         eng.set_reference(ref, threshold, mem)
     if world > 1:
-        eng.comm_broadcast_masters(0)
         eng.comm_broadcast_reference(0)
     mine = [lights[i] for i in light_shard(len(lights), rank, world)]
     if mine:
