@@ -298,8 +298,13 @@ def main():
     if rank == 0:
         sampler.start()
     l0 = eng.launch_count()
+    if os.environ.get("OSS_B200_TIMELINE"):   # dev aid: per-launch events (and the timeline dump) in the timed region too
+        eng.profile(True)
     t_dev = timed(step_dev, a.steps)  # no per-launch events in here: they cost ~2 us of host and GPU time per launch
     launches = eng.launch_count() - l0
+    if os.environ.get("OSS_B200_TIMELINE"):
+        eng.profile(False)
+        eng.profile_table()
     clocks = sampler.finish() if rank == 0 else None
     frames_total = world * a.lights + 1
     dev_s = float(np.mean([t[0] for t in t_dev]))

@@ -344,3 +344,41 @@ def test_full_size_61mp_mono_star_heavy(eng):
     assert len(want) > 3000
     assert np.float32(info.threshold) == np.float32(oinfo.threshold) and info.ncomponents == oinfo.ncomponents
     same_stars(got, want)
+
+
+def test_many_small_batches_over_three_pipelines(eng):
+    """23 lights, up to 20 per launch, handed over in two calls: batches of 20 + 3 (> 16 frames in one launch), then 5 + 5 + 5 +
+    5 + 3 over three pipelines with deferred warps (the warp of a batch is queued behind the bulk kernels of the next two
+    batches) — bit-equal to the oracle and to each other."""
+    w, h = 640, 480
+    ds = synth.dataset(w, h, 23, 1, nstars=80, ndarks=2)     # a few of the lights fail to align (err -1): skipped, in order
+    eng.set_pipelines(3)
+    want = check_stack(eng, ds, w, h, 1, 20, slots=20)
+    eng.set_geometry(w, h, 1, np.uint16, 5)
+    eng.build_master(B.DARK, ds["darks"])
+    eng.set_reference(ds["ref"], 20)
+    eng.add_lights(ds["lights"][:12])     # 5 + 5 + 2
+    eng.add_lights(ds["lights"][12:])     # 5 + 5 + 1
+    img, tv = eng.finish()
+    assert tv == want["total_valid"] and np.array_equal(bits(img), bits(want["image"]))
+    assert [(r.nstars, r.k, r.err) for r in eng.reports()] == [(o.nstars, o.k, o.err) for o in want["reports"]]
+
+
+def test_reference_overflow_surfaces_at_the_next_synchronising_call(eng):
+    """oss_set_reference is asynchronous: a reference whose candidate pixels exceed the work space is reported by
+    oss_get_reference_stars / oss_finish (OSS_E_CAPACITY), not silently stacked."""
+    w, h = 1000, 700
+    rng = np.random.default_rng(5)
+    noisy = np.where(rng.random((h, w)) < 0.2, 65535, 0).astype(np.uint16)   # salt noise: a fifth of the pixels are candidates at t = 1
+    eng.set_geometry(w, h, 1, np.uint16, 2)
+    eng.set_reference(noisy, 1)
+    with pytest.raises(ob.OssError) as e:
+        eng.reference_stars()
+    assert e.value.status == -7
+    eng.add_lights([noisy])
+    with pytest.raises(ob.OssError) as e:
+        eng.finish()
+    assert e.value.status == -7
+    # the context stays usable
+    ds = synth.dataset(w, h, 2, 1, nstars=80, seed=11)
+    check_stack(eng, ds, w, h, 1, 20, slots=2)
