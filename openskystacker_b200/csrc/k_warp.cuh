@@ -165,6 +165,29 @@ k_warp_accumulate_tiled(const float *__restrict__ cal, long long strideCal, cons
         }
         const float *tile = tiles + buf * (WT_ROWS * ROWF);
         const int2 *rowxy = sxy + buf * WT_H;
+        if (t.fits && t.interior && (W & 3) == 0 && y0 + WT_H <= H) {
+            // fastest path (the usual one): every tap is inside the frame and inside the staged tile, all 8 rows of the
+            // thread exist, and with W % 4 == 0 every staged row starts at the same phase (cx0 & 3) of its 16-byte chunk,
+            // so one base pointer serves both tap rows: tap(sy, sx) = tb + sy * ROWF + sx * C
+            const float *tb = tile + ((t.cx0 & 3) - t.cx0) * C - t.cy0 * ROWF;
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const int2 b = rowxy[ty + 4 * k];
+                const int X = (b.x + abx.x) >> 5, Y = (b.y + abx.y) >> 5;
+                const float fx = (float)(X & 31) * (1.f / 32), fy = (float)(Y & 31) * (1.f / 32);
+                const float ix = 1.f - fx, iy = 1.f - fy;
+                const float w00 = iy * ix, w01 = iy * fx, w10 = fy * ix, w11 = fy * fx; // exact: multiples of 1/1024
+                const float *p0 = tb + (Y >> 5) * ROWF + (X >> 5) * C;
+                const float *p1 = p0 + ROWF;
+#pragma unroll
+                for (int ch = 0; ch < C; ch++) {
+                    float val = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(p0[ch], w00), __fmul_rn(p0[C + ch], w01)), __fmul_rn(p1[ch], w10)),
+                                          __fmul_rn(p1[C + ch], w11));
+                    acc[k][ch] = __fadd_rn(acc[k][ch], val);
+                }
+            }
+            continue;
+        }
         if (t.fits && t.interior) {
             // fast path: every tap is inside the frame and inside the staged tile
             const int w4 = W & 3, cxa = t.cx0 & 3;
