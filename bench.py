@@ -29,7 +29,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "24MP frames/sec (calibrate+align+stack)"
+METRIC = "24MP frames/sec (calibrate+align+stack)"  # (other --width/--height: same pipeline, that frame size)
 UNIT = "frames/s"
 
 
@@ -97,11 +97,11 @@ def star_motion(field, index, w, h):
 class Inputs:
     """Seeded synthetic stack rendered directly in HBM (oss_synth_*), SURVEY.md §8(d) spec."""
 
-    def __init__(self, eng, w, h, nlights, ncal, first_light=1):
+    def __init__(self, eng, w, h, nlights, ncal, first_light=1, nstars=0):
         from openskystacker_b200 import synth
         self.eng, self.w, self.h = eng, w, h
         nb = eng.frame_bytes()
-        field = synth.Field(w, h, max(60, int(600 * w * h / 24e6)), 1234)
+        field = synth.Field(w, h, nstars or max(60, int(600 * w * h / 24e6)), 1234)
         mk = lambda: eng.device_alloc(nb)
         self.bias, self.darks, self.flats = [mk() for _ in range(ncal)], [mk() for _ in range(ncal)], [mk() for _ in range(ncal)]
         for i, p in enumerate(self.bias):
@@ -121,16 +121,18 @@ class Inputs:
         return self.bias + self.darks + self.flats + [self.ref] + self.lights
 
 
-def run_job(eng, B, cal, ref, light_arr, nlights, mem, result_host, comm=None, rank=0):
+def run_job(eng, B, cal, ref, light_arr, nlights, mem, result_host, comm=None, rank=0, threshold=20, ncal=1):
     """One step.  cal = (bias_ptrs, dark_ptrs, flat_ptrs) as ctypes arrays + counts."""
     L, h = eng._L, eng._h
     for kind, (arr, n) in zip((B.BIAS, B.DARK, B.FLAT), cal):
+        if not ncal:
+            break
         if rank == 0:
             eng._ck(L.oss_build_master(h, kind, arr, n, mem))
         if comm:
             eng.comm_broadcast_master(kind, 0)  # asynchronous: overlaps the next master and the reference on rank 0
     if rank == 0:
-        eng._ck(L.oss_set_reference(h, ref, mem, 20))
+        eng._ck(L.oss_set_reference(h, ref, mem, threshold))
     if comm:
         eng.comm_broadcast_reference(0)
     eng._ck(L.oss_add_lights(h, light_arr, nlights, mem))
@@ -145,7 +147,7 @@ def run_job(eng, B, cal, ref, light_arr, nlights, mem, result_host, comm=None, r
     return 0
 
 
-def cpu_baseline(raw_lights, ref_raw, cal_frames, threads, steps=1, warmup=0):
+def cpu_baseline(raw_lights, ref_raw, cal_frames, threads, steps=1, warmup=0, threshold=20):
     """The reference's CPU path on this box (all in host memory).  Returns (fps, kind, note, times)."""
     import oracle
     from oracle import cv2_pipeline as cvp
@@ -159,14 +161,14 @@ def cpu_baseline(raw_lights, ref_raw, cal_frames, threads, steps=1, warmup=0):
     for it in range(warmup + steps):
         t0 = time.perf_counter()
         if use_cv:
-            cvp.stack_lights(raw_lights, (bias, dark, flat), 20, ref_cal, threads)
+            cvp.stack_lights(raw_lights, (bias, dark, flat), threshold, ref_cal, threads)
         else:
             from concurrent.futures import ThreadPoolExecutor
 
             def worker(i):
                 part = np.zeros_like(ref_cal)
                 for k in range(i, len(raw_lights), threads):
-                    oracle.process_light(raw_lights[k], bias, dark, flat, 20, ref_cal, None, part)
+                    oracle.process_light(raw_lights[k], bias, dark, flat, threshold, ref_cal, None, part)
                 return part
             with ThreadPoolExecutor(threads) as ex:
                 list(ex.map(worker, range(threads)))
@@ -188,10 +190,13 @@ def main():
     ap.add_argument("--width", type=int, default=6000)
     ap.add_argument("--height", type=int, default=4000)
     ap.add_argument("--lights", type=int, default=50)
-    ap.add_argument("--ncal", type=int, default=10)
+    ap.add_argument("--ncal", type=int, default=10, help="darks = flats = bias frames (0: no calibration, like configs 4/5)")
+    ap.add_argument("--channels", type=int, default=3, choices=(1, 3))
+    ap.add_argument("--threshold", type=int, default=20)
+    ap.add_argument("--stars", type=int, default=0, help="stars in the synthetic field (0: 600 per 24 MP)")
     ap.add_argument("--slots", type=int, default=17, help="frames in flight per pipeline, device-resident run")
     ap.add_argument("--pipes", type=int, default=3, help="pipelines, device-resident run")
-    ap.add_argument("--e2e-slots", type=int, default=10, help="frames in flight for the host-fed run (shorter drain after the last H2D copy)")
+    ap.add_argument("--e2e-slots", type=int, default=5, help="frames in flight for the host-fed run (shorter drain after the last H2D copy)")
     ap.add_argument("--e2e-pipes", type=int, default=3)
     ap.add_argument("--cpu-lights", type=int, default=0, help="lights in the CPU sample (0 = host cores)")
     ap.add_argument("--no-cpu", action="store_true")
@@ -203,10 +208,12 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     cores = os.cpu_count() or 1
-    W, H, C = a.width, a.height, 3
-    workload = f"{a.lights} x {W}x{H} RGB16 lights + {a.ncal} darks + {a.ncal} flats + {a.ncal} bias: full calibration + align + stack"
+    W, H, C = a.width, a.height, a.channels
+    kind = "RGB16" if C == 3 else "mono16"
+    workload = (f"{a.lights} x {W}x{H} {kind} lights + {a.ncal} darks + {a.ncal} flats + {a.ncal} bias: full calibration + align + stack"
+                if a.ncal else f"{a.lights} x {W}x{H} {kind} lights, no calibration frames: detect + align + stack at threshold {a.threshold}")
     config = {"workload": workload, "width": W, "height": H, "channels": C, "lights_per_gpu": a.lights,
-              "calibration_frames": 3 * a.ncal, "threshold": 20, "frames_in_flight": a.slots, "pipelines": a.pipes,
+              "calibration_frames": 3 * a.ncal, "threshold": a.threshold, "frames_in_flight": a.slots, "pipelines": a.pipes,
               "e2e_frames_in_flight": a.e2e_slots, "e2e_pipelines": a.e2e_pipes,
               "l2": "inputs (%.1f GB per step) are far larger than L2" % ((a.lights + 1 + 3 * a.ncal) * W * H * C * 2 / 1e9),
               "parallelism": f"frames sharded over {world} GPU(s), one ncclReduce of the f32 sum" if world > 1 else "1 GPU"}
@@ -223,7 +230,7 @@ def main():
         try:
             eng = ob.Engine(local)
             eng.set_geometry(W, H, C, np.uint16, 1)
-            inp = Inputs(eng, W, H, nl, a.ncal)
+            inp = Inputs(eng, W, H, nl, a.ncal, nstars=a.stars)
             shape = (H, W, C)
             pull = lambda p: eng.from_device(p, shape, np.uint16)
             cal = ([pull(p) for p in inp.bias], [pull(p) for p in inp.darks], [pull(p) for p in inp.flats])
@@ -234,7 +241,7 @@ def main():
             ds = synth.dataset(W, H, nl, C, ndarks=a.ncal, nflats=a.ncal, nbias=a.ncal)
             cal, ref, lights = (ds["bias"], ds["darks"], ds["flats"]), ds["ref"], ds["lights"]
             data = "synthetic (numpy)"
-        fps, kind, note, times = cpu_baseline(lights, ref, cal, cores, a.steps, a.warmup)
+        fps, kind, note, times = cpu_baseline(lights, ref, cal, cores, a.steps, a.warmup, a.threshold)
         sample = f"{nl} of {a.lights} lights per step against a prebuilt reference + masters, {cores} worker threads; {note}"
         print(json.dumps({"impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
                           "warmup": a.warmup, "ms_per_step": 1e3 * float(np.mean(times)), "higher_is_better": True,
@@ -261,7 +268,7 @@ def main():
         eng.comm_init(box[0], rank, world)
         comm = True
 
-    inp = Inputs(eng, W, H, a.lights, a.ncal if rank == 0 else 0, first_light=1 + rank * a.lights)
+    inp = Inputs(eng, W, H, a.lights, a.ncal if rank == 0 else 0, first_light=1 + rank * a.lights, nstars=a.stars)
     arr = lambda ps: ((Ct.c_void_p * len(ps))(*ps), len(ps))
     cal_d = (arr(inp.bias), arr(inp.darks), arr(inp.flats))
     lights_d, nl = arr(inp.lights)
@@ -292,7 +299,7 @@ def main():
             out = [tuple(x) for x in t.cpu().tolist()]
         return out
 
-    step_dev = lambda: run_job(eng, B, cal_d, Ct.c_void_p(inp.ref), lights_d, nl, B.DEVICE, None, comm, rank)
+    step_dev = lambda: run_job(eng, B, cal_d, Ct.c_void_p(inp.ref), lights_d, nl, B.DEVICE, None, comm, rank, a.threshold, a.ncal)
     timed(step_dev, a.warmup)
     sampler = ClockSampler(local)
     if rank == 0:
@@ -329,7 +336,7 @@ def main():
             eng.set_pipelines(a.e2e_pipes)
             eng.set_geometry(W, H, C, np.uint16, a.e2e_slots)
         step_host = lambda: run_job(eng, B, cal_h, Ct.c_void_p(host[inp.ref]), lights_h, nl, B.HOST,
-                                    Ct.c_void_p(res_host) if rank == 0 else None, comm, rank)
+                                    Ct.c_void_p(res_host) if rank == 0 else None, comm, rank, a.threshold, a.ncal)
         timed(step_host, 1)
         t_host = timed(step_host, max(1, min(a.steps, 3)))
         wall_s = float(np.mean([t[1] for t in t_host]))
@@ -349,23 +356,24 @@ def main():
     # run on ONE pipeline (kernels strictly serial), still inside this bench run, same inputs.
     peak, peak_src = peaks()
     P = W * H
-    M = 3
+    M = 3 if a.ncal else 0
+    B_frame = 2 * C + 4 * C * M + 4 * C + (4 if C > 1 else 0) + 4 + 4 + 4 * C + 8 * C  # SURVEY.md section 8(d), bytes per pixel
     eng.set_pipelines(1)
     eng.set_geometry(W, H, C, np.uint16, a.slots)
     if comm:
         comm = None  # rank 0 alone: the serial attribution pass is single-GPU
-    run_job(eng, B, cal_d, Ct.c_void_p(inp.ref), lights_d, nl, B.DEVICE, None, None, 0)
+    run_job(eng, B, cal_d, Ct.c_void_p(inp.ref), lights_d, nl, B.DEVICE, None, None, 0, a.threshold, a.ncal)
     eng.profile_reset()
     eng.profile(True)
     eng.mark(0)
-    run_job(eng, B, cal_d, Ct.c_void_p(inp.ref), lights_d, nl, B.DEVICE, None, None, 0)
+    run_job(eng, B, cal_d, Ct.c_void_p(inp.ref), lights_d, nl, B.DEVICE, None, None, 0, a.threshold, a.ncal)
     eng.mark(1)
     serial_ms = eng.elapsed_ms()
     eng.profile(False)
     prof = eng.profile_table()
     fp32_peak = 148 * 128 * 1.965e9 / 1e12          # non-fused fp32 op/s (no FMA allowed on this path), TFLOP/s
     per_frame = {  # algorithmic bytes per light frame, SURVEY.md section 8(d)
-        "calibrate_gray": P * (2 * C + 4 * C * M + 4 * C + 4),
+        "calibrate_gray": P * (2 * C + 4 * C * M + 4 * C + (4 if C > 1 else 0)),
         "warp_accumulate": P * (12 * C),
         "sky_sub_stats": P * (4 + 4),
     }
@@ -392,7 +400,7 @@ def main():
         # dram__bytes_read + dram__bytes_write per launch from the committed ncu --set full capture
         # (profiles/r01_ncu_summary.md), valid for the default shape only: 24 MP RGB16, M = 3, 17 frames per launch
         ncu_traffic = {"calibrate_gray": 3.316e9 + 6.470e9, "warp_accumulate": 5.214e9 + 0.295e9}
-        default_shape = (W, H, a.slots, a.lights) == (6000, 4000, 17, 50)
+        default_shape = (W, H, C, a.ncal, a.slots, a.lights) == (6000, 4000, 3, 10, 17, 50)
         traffic = ncu_traffic.get(name) if default_shape else None
         roof = {"bound": "hbm", "kernel": name, "achieved": k["achieved_gbs"], "peak": peak, "unit": "GB/s",
                 "frac": k["hbm_frac"], "traffic": traffic, "peak_source": peak_src, "launches": k["launches"],
@@ -404,9 +412,9 @@ def main():
                 "measured": "CUDA events around every launch on the launching stream, one extra serial step (1 pipeline) of the "
                             "same job inside this run; in the timed region detection tails overlap bulk kernels",
                 "kernels": kernels, "kernel_time_shares_serial": shares, "serial_step_ms": serial_ms,
-                "whole_pipeline": {"algorithmic_bytes_per_frame": P * 102,
-                                   "achieved_gbs": P * 102 * (a.lights + 1) / dev_s / 1e9,
-                                   "frac": P * 102 * (a.lights + 1) / dev_s / 1e9 / peak}}
+                "whole_pipeline": {"algorithmic_bytes_per_frame": P * B_frame,
+                                   "achieved_gbs": P * B_frame * (a.lights + 1) / dev_s / 1e9,
+                                   "frac": P * B_frame * (a.lights + 1) / dev_s / 1e9 / peak}}
 
     # ------------------------------------------------------------------ CPU baseline beside it (N = 1 only)
     cpu = None
@@ -415,7 +423,7 @@ def main():
         shape = (H, W, C)
         pull = lambda p: eng.from_device(p, shape, np.uint16)
         cal = ([pull(p) for p in inp.bias], [pull(p) for p in inp.darks], [pull(p) for p in inp.flats])
-        fps, kind, note, times = cpu_baseline([pull(p) for p in inp.lights[:ncpu]], pull(inp.ref), cal, cores)
+        fps, kind, note, times = cpu_baseline([pull(p) for p in inp.lights[:ncpu]], pull(inp.ref), cal, cores, threshold=a.threshold)
         cpu = {"value": fps, "unit": UNIT, "cores": cores, "kind": kind,
                "sample": f"{min(ncpu, a.lights)} of the {a.lights} lights (same bytes as the GPU run) against prebuilt masters + reference, "
                          f"{cores} worker threads, {times[0]:.1f} s; {note}"}
