@@ -276,6 +276,7 @@ static int dalloc(oss_ctx *c, T **p, size_t count, bool geom_scoped = true)
 static void free_geometry(oss_ctx *c)
 {
     cudaDeviceSynchronize();
+    c->pending_warps.clear(); // batches detected but never finished belong to the work spaces freed below
     for (void *p : c->allocs) cudaFree(p);
     c->allocs.clear();
     for (int i = 0; i < 4; i++) c->master[i] = nullptr;
