@@ -1226,6 +1226,17 @@ int oss_comm_broadcast_masters(oss_ctx *c, int root)
     return OSS_OK;
 }
 
+static int ensure_comm_stream(oss_ctx *c)
+{
+    if (c->comm_stream) return OSS_OK;
+    int lo = 0, hi = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CK(cudaStreamCreateWithPriority(&c->comm_stream, cudaStreamNonBlocking, hi));
+    CK(cudaEventCreateWithFlags(&c->comm_fork, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->masters_ready, cudaEventDisableTiming));
+    return OSS_OK;
+}
+
 // One master, asynchronously: the broadcast runs on its own stream behind whatever produced the master, so on the root
 // it overlaps the building of the next master and the reference frame; calibration kernels wait for it on the device.
 // Every rank calls it for the same kinds in the same order.
@@ -1237,13 +1248,7 @@ int oss_comm_broadcast_master(oss_ctx *c, int kind, int root)
     if (c->rank == root && !c->master[kind]) return fail(c, OSS_E_ARG, "the root has not built master %d", kind);
     const long long count = c->g.P * c->g.C;
     if (!c->master[kind]) DA(c->master[kind], count);
-    if (!c->comm_stream) {
-        int lo = 0, hi = 0;
-        CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-        CK(cudaStreamCreateWithPriority(&c->comm_stream, cudaStreamNonBlocking, hi));
-        CK(cudaEventCreateWithFlags(&c->comm_fork, cudaEventDisableTiming));
-        CK(cudaEventCreateWithFlags(&c->masters_ready, cudaEventDisableTiming));
-    }
+    { int rc = ensure_comm_stream(c); if (rc) return rc; }
     CK(cudaEventRecord(c->comm_fork, c->bulk)); // after the kernels that wrote (root) or still read (others) this master
     CK(cudaStreamWaitEvent(c->comm_stream, c->comm_fork, 0));
     NK(g_nccl.Broadcast(c->master[kind], c->master[kind], (size_t)count, ncclFloat32, root, c->comm, c->comm_stream));
@@ -1253,21 +1258,35 @@ int oss_comm_broadcast_master(oss_ctx *c, int kind, int root)
 
 int oss_comm_broadcast_reference(oss_ctx *c, int root)
 {
-    USE_PIPE0();
+    NEED_GEOM();
     if (!c->comm) return fail(c, OSS_E_ARG, "oss_comm_init has not been called");
-    if (c->rank == root && !c->has_ref) return fail(c, OSS_E_ARG, "root has no reference");
-    if (c->rank != root) { int rc = oss_reset_stack(c); if (rc) return rc; }
-    int *xy_ref = c->d_xy + c->slots * 2 * OSS_NOBJS, *nxy_ref = c->d_nxy + c->slots;
-    NK(g_nccl.Broadcast(c->d_ref, c->d_ref, sizeof(RefTriangles), ncclUint8, root, c->comm, c->stream));
-    NK(g_nccl.Broadcast(xy_ref, xy_ref, 2 * OSS_NOBJS, ncclInt32, root, c->comm, c->stream));
-    NK(g_nccl.Broadcast(nxy_ref, nxy_ref, 1, ncclInt32, root, c->comm, c->stream));
+    { int rc = ensure_comm_stream(c); if (rc) return rc; }
+    const bool is_root = c->rank == root;
+    if (is_root) {
+        // the root does not wait on the host: the broadcasts are ordered on the device behind the reference's alignment
+        // data (its detection tail may still be running), and its own lights can be queued right away
+        if (!c->has_ref) return fail(c, OSS_E_ARG, "root has no reference");
+        CK(cudaStreamWaitEvent(c->comm_stream, c->ref_ready, 0));
+    } else {
+        cudaError_t e = sync_all(c);
+        if (e != cudaSuccess) return fail(c, OSS_E_CUDA, "stream sync failed: %s", cudaGetErrorString(e));
+        select_pipe(c, 0);
+        int rc = oss_reset_stack(c);
+        if (rc) return rc;
+    }
+    int *xy_ref = c->pipes[0].d_xy + c->slots * 2 * OSS_NOBJS, *nxy_ref = c->pipes[0].d_nxy + c->slots;
     int *d_th = c->d_valid + 2;
-    if (c->rank == root) CK(cudaMemcpyAsync(d_th, &c->threshold, sizeof(int), cudaMemcpyHostToDevice, c->stream));
-    NK(g_nccl.Broadcast(d_th, d_th, 1, ncclInt32, root, c->comm, c->stream));
-    CK(cudaMemcpyAsync(&c->threshold, d_th, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    c->has_ref = true;
-    c->ref_in_sum = c->rank == root; // imagestacker.cpp:287,304: the reference is counted once
+    if (is_root) CK(cudaMemcpyAsync(d_th, &c->threshold, sizeof(int), cudaMemcpyHostToDevice, c->comm_stream));
+    NK(g_nccl.Broadcast(c->d_ref, c->d_ref, sizeof(RefTriangles), ncclUint8, root, c->comm, c->comm_stream));
+    NK(g_nccl.Broadcast(xy_ref, xy_ref, 2 * OSS_NOBJS, ncclInt32, root, c->comm, c->comm_stream));
+    NK(g_nccl.Broadcast(nxy_ref, nxy_ref, 1, ncclInt32, root, c->comm, c->comm_stream));
+    NK(g_nccl.Broadcast(d_th, d_th, 1, ncclInt32, root, c->comm, c->comm_stream));
+    if (!is_root) {
+        CK(cudaMemcpyAsync(&c->threshold, d_th, sizeof(int), cudaMemcpyDeviceToHost, c->comm_stream));
+        CK(cudaStreamSynchronize(c->comm_stream)); // masters (if broadcast one by one) and the reference have arrived
+        c->has_ref = true;
+    }
+    c->ref_in_sum = is_root; // imagestacker.cpp:287,304: the reference is counted once
     return OSS_OK;
 }
 
