@@ -82,7 +82,7 @@ template <int C>
 __global__ void __launch_bounds__(256, 3)
 k_warp_accumulate_tiled(const float *__restrict__ cal, long long strideCal, const AlignOut *__restrict__ align, int nframes,
                         const int2 *__restrict__ ab, long long strideAB, const int2 *__restrict__ xy, long long strideXY,
-                        float *__restrict__ sum, int W, int H)
+                        float *__restrict__ sum, int W, int H, int ytile0)
 {
     constexpr int ROWF = WT_COLS * C;           // floats per staged row
     constexpr int CHUNKS = ROWF / 4;            // 16-byte chunks per staged row
@@ -92,7 +92,7 @@ k_warp_accumulate_tiled(const float *__restrict__ cal, long long strideCal, cons
     int *valid = (int *)(sxy + 2 * WT_H);                         // [OSS_MAX_BATCH + 1]
     __shared__ WarpFoot sfoot[OSS_MAX_BATCH];
     const int tid = threadIdx.x, tx = tid & 63, ty = tid >> 6, lane = tid & 31, wid = tid >> 5;
-    const int x0 = blockIdx.x * WT_W, y0 = blockIdx.y * WT_H;
+    const int x0 = blockIdx.x * WT_W, y0 = (blockIdx.y + ytile0) * WT_H; // ytile0: first tile row of a banded launch
     const int x = x0 + tx;
     const int xe = min(x0 + WT_W, W) - 1, ye = min(y0 + WT_H, H) - 1; // last pixel of the (possibly clipped) tile
     const bool col_ok = x < W;

@@ -145,6 +145,7 @@ struct oss_ctx {
     int rank = 0, nranks = 1;
     cudaStream_t comm_stream = nullptr;   // master broadcasts run here, beside the bulk stream
     cudaEvent_t comm_fork = nullptr, masters_ready = nullptr;
+    int reduce_root = 0;
 };
 
 static const int kChunk = 1024;
@@ -175,12 +176,12 @@ static void select_pipe(oss_ctx *c, int p)
     c->batch_counter = n.batch_counter;
 }
 
-static int flush_warps(oss_ctx *c, size_t keep);
+static int flush_warps(oss_ctx *c, size_t keep, int bands, int (*after_band)(oss_ctx *, int, int));
 
 static cudaError_t sync_all(oss_ctx *c, bool with_comm = true)
 {
     cudaError_t e = cudaSuccess;
-    if (flush_warps(c, 0) != OSS_OK) e = cudaErrorLaunchFailure;
+    if (flush_warps(c, 0, 1, nullptr) != OSS_OK) e = cudaErrorLaunchFailure;
     for (int p = 0; p < OSS_MAX_PIPES; p++) {
         if (c->pipes[p].copy_stream) { cudaError_t r = cudaStreamSynchronize(c->pipes[p].copy_stream); if (r != cudaSuccess) e = r; }
         if (c->pipes[p].chain_stream) { cudaError_t r = cudaStreamSynchronize(c->pipes[p].chain_stream); if (r != cudaSuccess) e = r; }
@@ -890,13 +891,17 @@ static int ensure_report_room(oss_ctx *c, int upto)
 
 } // extern "C"
 
-// queue the warp + accumulate kernels of the oldest pending batches until at most `keep` remain
-static int flush_warps(oss_ctx *c, size_t keep)
+// queue the warp + accumulate kernels of the oldest pending batches until at most `keep` remain.
+// bands > 1 (multi-GPU, the very last batch of a stack): that batch's warp is launched as `bands` kernels over horizontal
+// bands of tile rows, and after each one `after_band(c, first_row, rows)` runs (it queues the NCCL reduce of those rows of
+// the sum on the comm stream), so that the reduce of band k overlaps the warp of band k + 1.
+static int flush_warps(oss_ctx *c, size_t keep, int bands = 1, int (*after_band)(oss_ctx *, int, int) = nullptr)
 {
     const Geom &g = c->g;
     while (c->pending_warps.size() > keep) {
         const oss_ctx::PendingWarp pw = c->pending_warps.front();
         c->pending_warps.erase(c->pending_warps.begin());
+        const bool last = c->pending_warps.empty();
         Pipe &pp = c->pipes[pw.pipe];
         Workspace &w = pp.ws;
         cudaStream_t saved = c->stream;
@@ -904,13 +909,24 @@ static int flush_warps(oss_ctx *c, size_t keep)
         CK(cudaStreamWaitEvent(c->stream, pp.detect_done, 0));
         LAUNCH("warp_tables", k_warp_tables, dim3((g.W + g.H + 255) / 256, pw.nb), 256, 0, w.align, w.warp_ab, (long long)g.W, w.warp_xy,
                (long long)g.H, g.W, g.H);
-        const dim3 wgrid((g.W + WT_W - 1) / WT_W, (g.H + WT_H - 1) / WT_H);
-        if (g.C == 3) {
-            LAUNCH("warp_accumulate", k_warp_accumulate_tiled<3>, wgrid, 256, warp_tiled_smem<3>(), w.cal, w.stridePC, w.align, pw.nb,
-                   w.warp_ab, (long long)g.W, w.warp_xy, (long long)g.H, c->sum, g.W, g.H);
-        } else {
-            LAUNCH("warp_accumulate", k_warp_accumulate_tiled<1>, wgrid, 256, warp_tiled_smem<1>(), w.cal, w.stridePC, w.align, pw.nb,
-                   w.warp_ab, (long long)g.W, w.warp_xy, (long long)g.H, c->sum, g.W, g.H);
+        const int tiles_y = (g.H + WT_H - 1) / WT_H, nb = (last && bands > 1) ? bands : 1;
+        for (int b = 0; b < nb; b++) {
+            const int t0 = (int)((long long)tiles_y * b / nb), t1 = (int)((long long)tiles_y * (b + 1) / nb);
+            if (t1 > t0) {
+                const dim3 wgrid((g.W + WT_W - 1) / WT_W, t1 - t0);
+                if (g.C == 3) {
+                    LAUNCH("warp_accumulate", k_warp_accumulate_tiled<3>, wgrid, 256, warp_tiled_smem<3>(), w.cal, w.stridePC, w.align, pw.nb,
+                           w.warp_ab, (long long)g.W, w.warp_xy, (long long)g.H, c->sum, g.W, g.H, t0);
+                } else {
+                    LAUNCH("warp_accumulate", k_warp_accumulate_tiled<1>, wgrid, 256, warp_tiled_smem<1>(), w.cal, w.stridePC, w.align, pw.nb,
+                           w.warp_ab, (long long)g.W, w.warp_xy, (long long)g.H, c->sum, g.W, g.H, t0);
+                }
+            }
+            if (nb > 1 && after_band) {
+                const int r0 = t0 * WT_H, r1 = t1 * WT_H < g.H ? t1 * WT_H : g.H;
+                int rc = after_band(c, r0, r1 - r0);
+                if (rc) return rc;
+            }
         }
         CK(cudaEventRecord(pp.warp_done, c->stream));
         c->stream = saved;
@@ -1168,10 +1184,10 @@ int oss_warp_affine(oss_ctx *c, const float *src, float *dst, const float *M)
     const dim3 wgrid((g.W + WT_W - 1) / WT_W, (g.H + WT_H - 1) / WT_H);
     if (g.C == 3) {
         LAUNCH("warp_accumulate", k_warp_accumulate_tiled<3>, wgrid, 256, warp_tiled_smem<3>(), w.cal, w.stridePC, w.align, 1, w.warp_ab, (long long)g.W,
-               w.warp_xy, (long long)g.H, c->result, g.W, g.H);
+               w.warp_xy, (long long)g.H, c->result, g.W, g.H, 0);
     } else {
         LAUNCH("warp_accumulate", k_warp_accumulate_tiled<1>, wgrid, 256, warp_tiled_smem<1>(), w.cal, w.stridePC, w.align, 1, w.warp_ab, (long long)g.W,
-               w.warp_xy, (long long)g.H, c->result, g.W, g.H);
+               w.warp_xy, (long long)g.H, c->result, g.W, g.H, 0);
     }
     CK(cudaMemcpyAsync(dst, c->result, bytes, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
@@ -1290,15 +1306,46 @@ int oss_comm_broadcast_reference(oss_ctx *c, int root)
     return OSS_OK;
 }
 
+// NCCL reduce of rows [r0, r0 + rows) of the sum image on the comm stream, behind what the bulk stream has queued so far
+static int reduce_band(oss_ctx *c, int r0, int rows)
+{
+    if (rows <= 0) return OSS_OK;
+    const size_t row_floats = (size_t)c->g.W * c->g.C;
+    CK(cudaEventRecord(c->comm_fork, c->bulk));
+    CK(cudaStreamWaitEvent(c->comm_stream, c->comm_fork, 0));
+    float *p = c->sum + (size_t)r0 * row_floats;
+    NK(g_nccl.Reduce(p, p, (size_t)rows * row_floats, ncclFloat32, ncclSum, c->reduce_root, c->comm, c->comm_stream));
+    return OSS_OK;
+}
+
+// One reduce of the float32 sum image (+ the valid count) to `root`.  It is issued in OSS_REDUCE_BANDS row bands; when the
+// last batch's warp + accumulate is still pending (oss_add_lights defers it, no oss_sync in between) that warp is launched
+// band by band as well, and the reduce of a band overlaps the warp of the next one.  Every rank issues the same bands.
+#define OSS_REDUCE_BANDS 4
 int oss_comm_reduce(oss_ctx *c, int root)
 {
-    USE_PIPE0();
+    NEED_GEOM();
     if (!c->comm) return fail(c, OSS_E_ARG, "oss_comm_init has not been called");
-    const long long count = c->g.P * c->g.C;
-    CK(cudaStreamSynchronize(c->copy_stream));
-    NK(g_nccl.Reduce(c->sum, c->sum, (size_t)count, ncclFloat32, ncclSum, root, c->comm, c->stream));
-    NK(g_nccl.Reduce(c->d_valid, c->d_valid, 1, ncclInt32, ncclSum, root, c->comm, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
+    { int rc = ensure_comm_stream(c); if (rc) return rc; }
+    c->reduce_root = root;
+    const int tiles_y = (c->g.H + WT_H - 1) / WT_H;
+    if (!c->pending_warps.empty()) {
+        int rc = flush_warps(c, 0, OSS_REDUCE_BANDS, reduce_band);
+        if (rc) return rc;
+    } else {
+        for (int b = 0; b < OSS_REDUCE_BANDS; b++) { // same band boundaries as flush_warps
+            const int t0 = (int)((long long)tiles_y * b / OSS_REDUCE_BANDS), t1 = (int)((long long)tiles_y * (b + 1) / OSS_REDUCE_BANDS);
+            const int r0 = t0 * WT_H, r1 = t1 * WT_H < c->g.H ? t1 * WT_H : c->g.H;
+            int rc = reduce_band(c, r0, r1 - r0);
+            if (rc) return rc;
+        }
+    }
+    // the valid count: every alignment kernel has finished once the chain streams are drained
+    cudaError_t e = sync_all(c, false);
+    if (e != cudaSuccess) return fail(c, OSS_E_CUDA, "stream sync failed: %s", cudaGetErrorString(e));
+    select_pipe(c, 0);
+    NK(g_nccl.Reduce(c->d_valid, c->d_valid, 1, ncclInt32, ncclSum, root, c->comm, c->comm_stream));
+    CK(cudaStreamSynchronize(c->comm_stream));
     return OSS_OK;
 }
 
