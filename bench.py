@@ -408,6 +408,7 @@ def main():
                          "keeps the masters in registers across the frames of a launch and really moves `traffic` bytes, which is why "
                          "frac can exceed 1; traffic / launch time is the physical DRAM rate") if name == "calibrate_gray" else None,
                 "physical_gbs": (traffic / a.slots / (k["us_per_frame"] * 1e-6) / 1e9) if traffic else None,
+                "physical_frac": (traffic / a.slots / (k["us_per_frame"] * 1e-6) / 1e9 / peak) if traffic else None,
                 "avg_launch_ms": k["avg_launch_ms"], "algorithmic_bytes_per_launch": per_frame[name] * min(a.slots, a.lights),
                 "measured": "CUDA events around every launch on the launching stream, one extra serial step (1 pipeline) of the "
                             "same job inside this run; in the timed region detection tails overlap bulk kernels",
