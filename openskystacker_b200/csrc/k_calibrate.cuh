@@ -216,15 +216,27 @@ k_master_accumulate(const __grid_constant__ FramePtrs frames, int n, const float
         if (sub1) load_f32<N>(sub1 + i0, s1);
         if (sub2) load_f32<N>(sub2 + i0, s2);
         if (!first) load_f32<N>(acc + i0, a);
-        for (int f = 0; f < n; f++) {
-            load_samples<T, N>((const T *)frames.p[f] + i0, v);
+        auto add = [&](const float *x_, int f) { // frames are added in order (util.cpp:596-607)
 #pragma unroll
             for (int i = 0; i < N; i++) {
-                float x = v[i];
+                float x = x_[i];
                 if (sub1) x = __fsub_rn(x, s1[i]);
                 if (sub2) x = __fsub_rn(x, s2[i]);
                 a[i] = (first && f == 0) ? x : __fadd_rn(a[i], x);
             }
+        };
+        int f = 0;
+        for (; f + 4 <= n; f += 4) { // four frames' loads in flight per thread
+            float v1[N], v2[N], v3[N];
+            load_samples<T, N>((const T *)frames.p[f] + i0, v);
+            load_samples<T, N>((const T *)frames.p[f + 1] + i0, v1);
+            load_samples<T, N>((const T *)frames.p[f + 2] + i0, v2);
+            load_samples<T, N>((const T *)frames.p[f + 3] + i0, v3);
+            add(v, f); add(v1, f + 1); add(v2, f + 2); add(v3, f + 3);
+        }
+        for (; f < n; f++) {
+            load_samples<T, N>((const T *)frames.p[f] + i0, v);
+            add(v, f);
         }
         if (last) {
 #pragma unroll
