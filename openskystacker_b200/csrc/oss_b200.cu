@@ -80,7 +80,7 @@ struct Pipe {
     int *d_xy = nullptr, *d_nxy = nullptr;
     unsigned char *raw_stage[2] = {nullptr, nullptr};
     cudaEvent_t copy_done[2] = {nullptr, nullptr}, raw_free[2] = {nullptr, nullptr};
-    cudaEvent_t warp_done = nullptr, detect_done = nullptr, sky_done = nullptr;
+    cudaEvent_t warp_done = nullptr, detect_done = nullptr, sky_done = nullptr, cal_done = nullptr, med_done = nullptr;
     long long batch_counter = 0;
 };
 
@@ -291,6 +291,8 @@ static void free_geometry(oss_ctx *c)
         if (pp.warp_done) { cudaEventDestroy(pp.warp_done); pp.warp_done = nullptr; }
         if (pp.detect_done) { cudaEventDestroy(pp.detect_done); pp.detect_done = nullptr; }
         if (pp.sky_done) { cudaEventDestroy(pp.sky_done); pp.sky_done = nullptr; }
+        if (pp.cal_done) { cudaEventDestroy(pp.cal_done); pp.cal_done = nullptr; }
+        if (pp.med_done) { cudaEventDestroy(pp.med_done); pp.med_done = nullptr; }
         pp.ws = Workspace{};
         pp.d_xy = pp.d_nxy = nullptr;
         pp.batch_counter = 0;
@@ -504,6 +506,8 @@ int oss_set_geometry(oss_ctx *c, int W, int H, int C, int sample, int slots)
         CK(cudaEventCreateWithFlags(&pp.warp_done, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&pp.detect_done, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&pp.sky_done, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&pp.cal_done, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&pp.med_done, cudaEventDisableTiming));
         pp.batch_counter = 0;
     }
     c->cur = 0;
@@ -633,18 +637,42 @@ static int stage_frames(oss_ctx *c, const void *const *frames, int n, int mem, F
 
 static int run_detect_tail(oss_ctx *c, int n, int threshold);
 
-// calibrate (optional) + full star detection for n frames sitting in fp; results in ws slots 0..n-1
-static int run_detect(oss_ctx *c, const FramePtrs &fp, int n, bool use_masters, int threshold, int stage_set)
+// The detection of a batch in four pieces, so that oss_add_lights can interleave two batches (all on the selected pipeline):
+//   detect_calibrate  BULK stream: calibration + gray of the batch's frames
+//   detect_lowres     CHAIN stream: resize / 8 and median 5x5 of the gray planes — 1/64 of the pixels, two small kernels that
+//                     would leave the GPU mostly idle on the bulk stream; here they run beside the NEXT batch's calibration
+//   detect_sky        BULK stream (behind the low-res grid): sky background, subtraction, statistics
+//   run_detect_tail   CHAIN stream: thresholding ... star lists
+static int detect_calibrate(oss_ctx *c, const FramePtrs &fp, int n, bool use_masters, int stage_set)
 {
-    Workspace &w = c->ws;
-    const Geom &g = c->g;
     if (use_masters && c->masters_ready) CK(cudaStreamWaitEvent(c->stream, c->masters_ready, 0)); // broadcasts in flight
     int r = dispatch_calibrate(c, fp, n, use_masters);
     if (r) return r;
     if (stage_set >= 0) CK(cudaEventRecord(c->raw_free[stage_set], c->stream));
+    CK(cudaEventRecord(c->pipes[c->cur].cal_done, c->stream));
+    return OSS_OK;
+}
+
+static int detect_lowres(oss_ctx *c, int n)
+{
+    Workspace &w = c->ws;
+    const Geom &g = c->g;
+    cudaStream_t bulk = c->stream;
+    c->stream = c->pipes[c->cur].chain_stream;
+    CK(cudaStreamWaitEvent(c->stream, c->pipes[c->cur].cal_done, 0));
     LAUNCH("resize_down", k_resize_down, dim3((g.lw + 31) / 32, (g.lh + 7) / 8, n), 256, 0, w.gray, g.C == 3 ? w.strideP : w.stridePC, g.W,
            c->dx, c->dy, w.lo, w.strideLo, g.lw, g.lh);
     LAUNCH("median5", k_median5, dim3((g.lw + 31) / 32, (g.lh + 7) / 8, n), 256, 0, w.lo, w.med, w.strideLo, g.lw, g.lh);
+    CK(cudaEventRecord(c->pipes[c->cur].med_done, c->stream));
+    c->stream = bulk;
+    return OSS_OK;
+}
+
+static int detect_sky(oss_ctx *c, int n)
+{
+    Workspace &w = c->ws;
+    const Geom &g = c->g;
+    CK(cudaStreamWaitEvent(c->stream, c->pipes[c->cur].med_done, 0));
     const long long strideGray = g.C == 3 ? w.strideP : w.stridePC;
     const int seg_h = sky_segment_rows(g.W, g.H, n);
     c->sky_blocks = ((g.W + SKY_W - 1) / SKY_W) * ((g.H + seg_h - 1) / seg_h);
@@ -655,7 +683,16 @@ static int run_detect(oss_ctx *c, const FramePtrs &fp, int n, bool use_masters, 
     CK(cudaEventRecord(c->pipes[c->cur].sky_done, c->stream));
     c->stream = c->pipes[c->cur].chain_stream;
     CK(cudaStreamWaitEvent(c->stream, c->pipes[c->cur].sky_done, 0));
-    return run_detect_tail(c, n, threshold);
+    return OSS_OK;
+}
+
+// calibrate (optional) + full star detection for n frames sitting in fp; results in ws slots 0..n-1
+static int run_detect(oss_ctx *c, const FramePtrs &fp, int n, bool use_masters, int threshold, int stage_set)
+{
+    int r = detect_calibrate(c, fp, n, use_masters, stage_set);
+    if (!r) r = detect_lowres(c, n);
+    if (!r) r = detect_sky(c, n);
+    return r ? r : run_detect_tail(c, n, threshold);
 }
 
 // threshold -> candidates -> components -> stars, from the sky-subtracted planes already in the work space
@@ -944,23 +981,41 @@ int oss_add_lights(oss_ctx *c, const void *const *frames, int n, int mem)
     const Geom &g = c->g;
     int rc = ensure_report_room(c, c->nlights + n);
     if (rc) return rc;
-    for (int b0 = 0; b0 < n; b0 += c->slots) {
-        int nb = n - b0 < c->slots ? n - b0 : c->slots;
+    // Take the next pipeline for the frames [b0, b0 + nb): wait until its previous batch has been warped, stage the frames,
+    // calibrate them (bulk stream) and queue the low-res grid behind that (chain stream).
+    struct LightBatch { int pipe = -1, nb = 0; };
+    auto start_batch = [&](int b0, int nb, LightBatch *out) -> int {
         select_pipe(c, (int)(c->light_batches++ % c->npipes));
-        Workspace &w = c->ws;
-        // this pipeline's previous batch must have been warped before its calibrated planes are overwritten
-        for (bool busy = true; busy;) {
+        for (bool busy = true; busy;) { // its pending warp has to be queued before the calibrated planes are overwritten
             busy = false;
             for (const auto &pw : c->pending_warps) busy |= pw.pipe == c->cur;
-            if (busy) { rc = flush_warps(c, c->pending_warps.size() - 1); if (rc) return rc; }
+            if (busy) { int r = flush_warps(c, c->pending_warps.size() - 1, 1, nullptr); if (r) return r; }
         }
         CK(cudaStreamWaitEvent(c->stream, c->pipes[c->cur].warp_done, 0));
         CK(cudaStreamWaitEvent(c->stream, c->ref_copied, 0)); // ... and the reference's detection tail has left pipeline 0
         FramePtrs fp{};
         int set;
-        rc = stage_frames(c, frames + b0, nb, mem, &fp, &set);
-        if (rc) return rc;
-        rc = run_detect(c, fp, nb, true, c->threshold, set);
+        int r = stage_frames(c, frames + b0, nb, mem, &fp, &set);
+        if (!r) r = detect_calibrate(c, fp, nb, true, set);
+        if (!r) r = detect_lowres(c, nb);
+        out->pipe = c->cur;
+        out->nb = nb;
+        return r;
+    };
+    // Bulk stream order within one call: cal(0) cal(1) sky(0) cal(2) sky(1) ... — the calibration runs one batch ahead, so
+    // that the small resize / median kernels of a batch (chain stream) overlap the next batch's calibration instead of
+    // leaving the GPU idle between calibrate and sky.
+    LightBatch cur, nxt;
+    for (int b0 = 0; b0 < n; b0 += c->slots) {
+        const int nb = n - b0 < c->slots ? n - b0 : c->slots;
+        if (cur.pipe < 0) { rc = start_batch(b0, nb, &cur); if (rc) return rc; }
+        nxt = LightBatch{};
+        const int b1 = b0 + c->slots;
+        if (b1 < n && c->npipes > 2) { rc = start_batch(b1, n - b1 < c->slots ? n - b1 : c->slots, &nxt); if (rc) return rc; }
+        select_pipe(c, cur.pipe);
+        Workspace &w = c->ws;
+        rc = detect_sky(c, nb);
+        if (!rc) rc = run_detect_tail(c, nb, c->threshold);
         if (rc) return rc;
         LAUNCH("pack_xy", k_pack_xy, nb, OSS_NOBJS, 0, w.star_out, w.ds, g.cap, c->d_xy, c->d_nxy);
         CK(cudaStreamWaitEvent(c->stream, c->ref_ready, 0)); // the reference may still be in flight on pipeline 0
@@ -983,6 +1038,7 @@ int oss_add_lights(oss_ctx *c, const void *const *frames, int n, int mem)
         rc = flush_warps(c, (size_t)(c->npipes - 1));
         if (rc) return rc;
         c->nlights += nb;
+        cur = nxt; // pipe < 0: the next batch (if any) has not been started yet
     }
     return OSS_OK;
 }
