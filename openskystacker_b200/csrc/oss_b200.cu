@@ -67,8 +67,9 @@ static bool nccl_load(std::string *why)
 // runs on a high-priority stream of its own pipeline (= work space) and overlaps the bulk kernels of the following
 // batches.  The warp + accumulate of a batch is queued on the bulk stream only after the bulk kernels of the next
 // npipes - 1 batches, by which time its tail has finished, so the bulk stream never waits:
-//     cal+sky(0) cal+sky(1) cal+sky(2) warp(0) cal+sky(3) warp(1) ...      (bulk stream, 3 pipelines)
-//                tail(0)    tail(1)    tail(2)  ...                         (chain streams)
+//     cal(0) cal(1) sky(0) cal(2) sky(1) warp(0) cal(3) sky(2) warp(1) ...   (bulk stream, 3 pipelines)
+//            lowres(0)     lowres(1) tail(0)    lowres(2) tail(1) ...        (chain streams)
+// (calibration runs one batch ahead; lowres = the resize / median kernels, 1/64 of the pixels)
 // Accumulation order = batch order = frame order.  Co-running two bulk kernels from different streams was measured
 // slower than running them back to back (they evict each other's CTAs from the SMs), descending stream priorities
 // per pipeline likewise; the block scheduler serves equal-priority streams in launch order anyway.
