@@ -612,7 +612,8 @@ static int dispatch_calibrate(oss_ctx *c, const FramePtrs &fp, int n, bool use_m
 }
 
 // stage n host frames into raw_stage[set] (async on the copy stream) or pass device pointers through
-static int stage_frames(oss_ctx *c, const void *const *frames, int n, int mem, FramePtrs *fp, int *set_out)
+// wait == false: only queue the copies (prefetch of a later batch); the consumer calls stage_wait before its first kernel
+static int stage_frames(oss_ctx *c, const void *const *frames, int n, int mem, FramePtrs *fp, int *set_out, bool wait = true)
 {
     for (int i = 0; i < n; i++) {
         if (!frames[i]) return fail(c, OSS_E_ARG, "null frame pointer");
@@ -631,8 +632,14 @@ static int stage_frames(oss_ctx *c, const void *const *frames, int n, int mem, F
         fp->p[i] = dst;
     }
     CK(cudaEventRecord(c->copy_done[set], c->copy_stream));
-    CK(cudaStreamWaitEvent(c->stream, c->copy_done[set], 0));
+    if (wait) CK(cudaStreamWaitEvent(c->stream, c->copy_done[set], 0));
     *set_out = set;
+    return OSS_OK;
+}
+
+static int stage_wait(oss_ctx *c, int set)
+{
+    if (set >= 0) CK(cudaStreamWaitEvent(c->stream, c->copy_done[set], 0));
     return OSS_OK;
 }
 
@@ -1144,18 +1151,30 @@ int oss_detect_stars_batch(oss_ctx *c, const void *const *frames, int n, int mem
     USE_PIPE0();
     if (n < 0 || (n && (!frames || !counts))) return fail(c, OSS_E_ARG, "bad arguments");
     std::vector<DetectState> d(c->slots);
+    // host frames: the copies of batch b + 1 (other staging set) are queued before batch b is waited for, so the H2D
+    // transfer of one batch overlaps the detection of the previous one
+    FramePtrs fp{}, fp_next{};
+    int set = -1, set_next = -1;
+    if (n > 0) {
+        int rc = stage_frames(c, frames, n < c->slots ? n : c->slots, mem, &fp, &set, false);
+        if (rc) return rc;
+    }
     for (int b0 = 0; b0 < n; b0 += c->slots) {
-        int nb = n - b0 < c->slots ? n - b0 : c->slots;
+        const int nb = n - b0 < c->slots ? n - b0 : c->slots;
         c->stream = bulk_of(c, c->cur); // run_detect leaves the pipeline on its chain stream; the previous batch is complete
-        FramePtrs fp{};
-        int set;
-        int rc = stage_frames(c, frames + b0, nb, mem, &fp, &set);
+        int rc = stage_wait(c, set);
+        if (!rc) rc = run_detect(c, fp, nb, false, threshold, set);
         if (rc) return rc;
-        rc = run_detect(c, fp, nb, false, threshold, set);
-        if (rc) return rc;
+        const int b1 = b0 + c->slots;
+        if (b1 < n) {
+            rc = stage_frames(c, frames + b1, n - b1 < c->slots ? n - b1 : c->slots, mem, &fp_next, &set_next, false);
+            if (rc) return rc;
+        }
         CK(cudaMemcpyAsync(d.data(), c->ws.ds, sizeof(DetectState) * nb, cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
         for (int i = 0; i < nb; i++) counts[b0 + i] = d[i].overflow ? -1 : d[i].nstars;
+        fp = fp_next;
+        set = set_next;
     }
     return OSS_OK;
 }
