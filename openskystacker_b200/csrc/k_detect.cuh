@@ -55,28 +55,33 @@ __global__ void __launch_bounds__(1024)
 k_scan_phase1(const int *__restrict__ in, long long strideIn, int *__restrict__ out, long long strideOut,
               const int *__restrict__ n_dev, int n_dev_stride, int n_host, int *__restrict__ blocksum, long long strideBS)
 {
+    // grid.x is a small fixed number of CTAs per frame that stride over the 4096-item blocks actually present (n is usually
+    // a device-side count far below the capacity the grid used to be sized for: thousands of empty 1024-thread CTAs at high
+    // stream priority were displacing the bulk kernels' CTAs)
     const int f = blockIdx.y;
     const int n = n_dev ? n_dev[(long long)f * n_dev_stride] : n_host;
-    const long long base = (long long)blockIdx.x * SCAN_ITEMS;
-    if (base >= n) return;
     const int *src = in + f * strideIn;
     int *dst = out + f * strideOut;
-    int v[4], s = 0;
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        long long i = base + threadIdx.x * 4 + k;
-        v[k] = i < n ? src[i] : 0;
-        s += v[k];
-    }
     __shared__ int total;
-    int ex = block_exclusive_scan_1024(s, &total);
+    for (int blk = blockIdx.x; (long long)blk * SCAN_ITEMS < n; blk += gridDim.x) {
+        const long long base = (long long)blk * SCAN_ITEMS;
+        int v[4], s = 0;
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-        long long i = base + threadIdx.x * 4 + k;
-        if (i < n) dst[i] = ex;
-        ex += v[k];
+        for (int k = 0; k < 4; k++) {
+            long long i = base + threadIdx.x * 4 + k;
+            v[k] = i < n ? src[i] : 0;
+            s += v[k];
+        }
+        int ex = block_exclusive_scan_1024(s, &total);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            long long i = base + threadIdx.x * 4 + k;
+            if (i < n) dst[i] = ex;
+            ex += v[k];
+        }
+        if (threadIdx.x == 0) blocksum[f * strideBS + blk] = total;
+        __syncthreads(); // `total` is rewritten by the next block
     }
-    if (threadIdx.x == 0) blocksum[f * strideBS + blockIdx.x] = total;
 }
 
 // one block per frame: exclusive scan of the block sums, total to out[n] and *total_out
@@ -114,14 +119,16 @@ k_scan_phase3(int *__restrict__ out, long long strideOut, const int *__restrict_
 {
     const int f = blockIdx.y;
     const int n = n_dev ? n_dev[(long long)f * n_dev_stride] : n_host;
-    const long long base = (long long)blockIdx.x * SCAN_ITEMS;
-    if (base >= n || blockIdx.x == 0) return;
-    const int add = blocksum[f * strideBS + blockIdx.x];
     int *dst = out + f * strideOut;
+    for (int blk = blockIdx.x; (long long)blk * SCAN_ITEMS < n; blk += gridDim.x) {
+        if (blk == 0) continue;
+        const long long base = (long long)blk * SCAN_ITEMS;
+        const int add = blocksum[f * strideBS + blk];
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-        long long i = base + threadIdx.x * 4 + k;
-        if (i < n) dst[i] += add;
+        for (int k = 0; k < 4; k++) {
+            long long i = base + threadIdx.x * 4 + k;
+            if (i < n) dst[i] += add;
+        }
     }
 }
 

@@ -538,6 +538,9 @@ int oss_set_geometry(oss_ctx *c, int W, int H, int C, int sample, int slots)
 }  // extern "C"
 
 // ---- helpers ---------------------------------------------------------------------------
+static const int kScanGrid = 24;    // CTAs per frame of the scan phases
+static const int kSparseGrid = 74;  // CTAs (of 256 threads) per frame of the grid-stride kernels over candidate lists
+
 static int run_scan(oss_ctx *c, const int *in, long long strideIn, int *out, long long strideOut, const int *n_dev,
                     int n_dev_stride, int n_host_max, int nframes, int *total_out, int total_stride, int write_total_at_n = 0)
 {
@@ -545,12 +548,14 @@ static int run_scan(oss_ctx *c, const int *in, long long strideIn, int *out, lon
     int nb = (n_host_max + SCAN_ITEMS - 1) / SCAN_ITEMS;
     if (nb < 1) nb = 1;
     int n_host = n_dev ? 0 : n_host_max;
-    LAUNCH("scan", k_scan_phase1, dim3(nb, nframes), 1024, 0, in, strideIn, out, strideOut, n_dev, n_dev_stride, n_host,
+    // few CTAs per frame striding over the blocks: sized for the work usually there, not for the capacity (k_scan_phase1)
+    const int gx = nb < kScanGrid ? nb : kScanGrid;
+    LAUNCH("scan", k_scan_phase1, dim3(gx, nframes), 1024, 0, in, strideIn, out, strideOut, n_dev, n_dev_stride, n_host,
            w.blocksum, w.strideScan);
     LAUNCH("scan", k_scan_phase2, nframes, 1024, 0, w.blocksum, w.strideScan, n_dev, n_dev_stride, n_host, out, strideOut,
            write_total_at_n, total_out, total_stride);
     if (nb > 1)
-        LAUNCH("scan", k_scan_phase3, dim3(nb, nframes), 1024, 0, out, strideOut, n_dev, n_dev_stride, n_host, w.blocksum,
+        LAUNCH("scan", k_scan_phase3, dim3(gx, nframes), 1024, 0, out, strideOut, n_dev, n_dev_stride, n_host, w.blocksum,
                w.strideScan);
     return OSS_OK;
 }
@@ -719,7 +724,7 @@ static int run_detect_tail(oss_ctx *c, int n, int threshold)
     LAUNCH("compact_candidates", k_compact_candidates, dim3(segblocks, n), 256, 0, w.stars, w.strideP, w.segmask, w.strideSeg,
            w.segoff, w.cand_idx, w.cand_val, w.owner, w.ds, g);
     const int DS = (int)(sizeof(DetectState) / sizeof(int));
-    const int gs = 296;
+    const int gs = kSparseGrid;
     LAUNCH("links", k_links, dim3(gs, n), 256, 0, w.cand_idx, w.segmask, w.strideSeg, w.segoff, w.nbr, w.parent, w.comp_size,
            w.comp_peak, w.ds, g);
     LAUNCH("ccl_union", k_ccl_union, dim3(gs, n), 256, 0, w.nbr, w.parent, w.ds, g);
@@ -732,7 +737,7 @@ static int run_detect_tail(oss_ctx *c, int n, int threshold)
     r = run_scan(c, w.comp_staroff, g.cap, w.comp_staroff, g.cap, ncand, DS, g.cap, n, nullptr, 0);
     if (r) return r;
     LAUNCH("gather_roots", k_gather_roots, dim3(gs, n), 256, 0, w.flag, w.flagscan, w.comp_staroff, w.comp_root, w.comp_off, w.ds, g);
-    LAUNCH("components", k_components, dim3(592, n), 64, 0, w.cand_idx, w.cand_val, w.nbr, w.owner, w.comp_size, w.comp_root,
+    LAUNCH("components", k_components, dim3(4 * kSparseGrid, n), 64, 0, w.cand_idx, w.cand_val, w.nbr, w.owner, w.comp_size, w.comp_root,
            w.comp_off, w.comp_nstar, w.scratch, w.star_tmp, w.ds, g);
     r = run_scan(c, w.comp_nstar, g.cap, w.comp_staroff, g.cap, ncomp, DS, g.cap, n, nstars, DS);
     if (r) return r;
