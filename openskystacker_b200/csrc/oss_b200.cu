@@ -1348,6 +1348,8 @@ int oss_comm_broadcast_master(oss_ctx *c, int kind, int root)
     { int rc = ensure_comm_stream(c); if (rc) return rc; }
     CK(cudaEventRecord(c->comm_fork, c->bulk)); // after the kernels that wrote (root) or still read (others) this master
     CK(cudaStreamWaitEvent(c->comm_stream, c->comm_fork, 0));
+    // (a scatter of 1/N pieces followed by an all-gather was measured slower than NCCL's own broadcast at 4 ranks: 21.06 vs
+    // 20.10 ms per step)
     NK(g_nccl.Broadcast(c->master[kind], c->master[kind], (size_t)count, ncclFloat32, root, c->comm, c->comm_stream));
     CK(cudaEventRecord(c->masters_ready, c->comm_stream));
     return OSS_OK;

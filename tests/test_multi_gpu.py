@@ -111,17 +111,18 @@ def _nccl_worker(rank, world, port, out):
 
 
 @pytest.mark.gpu
-def test_two_nccl_ranks_match_single_gpu_and_oracle():
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+@pytest.mark.parametrize("world", [2, 4])
+def test_nccl_ranks_match_single_gpu_and_oracle(world):
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs (run with gpurun --gpus {world})")
     ds = dataset()
     want = oracle.stack(ds["ref"], ds["lights"], 20, dark_frames=ds["darks"])
     with mp.Manager() as m:
         out = m.dict()
-        mp.spawn(_nccl_worker, args=(2, free_port(), out), nprocs=2, join=True)
+        mp.spawn(_nccl_worker, args=(world, free_port(), out), nprocs=world, join=True)
         assert out["valid"] == want["total_valid"]
         assert np.max(np.abs(out["image"] - want["image"])) <= 1e-6
         per_rank = out["reports"]
-        for r in range(2):
-            idx = light_shard(len(ds["lights"]), r, 2)
+        for r in range(world):
+            idx = light_shard(len(ds["lights"]), r, world)
             assert per_rank[r] == [(want["reports"][i].nstars, want["reports"][i].k, want["reports"][i].err) for i in idx]
