@@ -103,22 +103,22 @@ static const uint32_t kGaussBits[16] = {
     0x3d88bfb5u, 0x3d972180u, 0x3da079edu, 0x3da3b7d6u};
 
 // ---------------------------------------------------------------------------------------
-// K3  sky_sub_stats, marching form.  One CTA owns a strip of SKY_W = 64 output columns and a
-// segment of rows [ya, yb) of one frame and walks down it in steps of SKY_H = 32 rows.  Per step b:
-//   phase 1  horizontal lerp of the low-res rows that are new for this step ("hrow" ring, keyed by
-//            low-res row & 15), read from the segment's low-res patch staged in shared memory once;
-//   phase 2  vertical lerp -> `up2`, the upsampled sky over the step's 32 rows x (64 + 2*15) columns,
-//            rows interleaved in pairs (operand layout of the packed row filter); the Gaussian's
-//            BORDER_REFLECT_101 is applied to the FULL-RES coordinates of rows and columns;
-//            meanwhile cp.async fetches the gray tile of the output block finished in phase 4 and
-//            warp 0 looks up the next step's row taps;
-//   phase 3  31-tap row filter, taps accumulated k = 0..30 in order; a thread makes 2 rows x 4
-//            columns from one 36-wide register window of row pairs; results go to a ring of
-//            3 x 32 row-filtered rows (+ a mirror of the first block so windows never wrap);
-//   phase 4  column filter (centre + 15 symmetric pairs) of the PREVIOUS block, whose 15-row lower
-//            apron has just been produced: 4 rows x 2 columns per thread from a 34-row window;
-//            subtract from gray; write; fp64 sum / sum of squares over the statistics ROI;
+// K3  sky_sub_stats, marching form.  One CTA (SKY_NT = 8 * SKY_H threads) owns a strip of SKY_W = 64 output columns and a
+// segment of rows [ya, yb) of one frame and walks down it in steps of SKY_H = 16 rows.  The pieces of step b:
+//   hrow     horizontal lerp of the low-res rows that are new for a block ("hrow" ring, keyed by low-res row & 15),
+//            read from the segment's low-res patch staged in shared memory once; done one block ahead;
+//   up       vertical lerp -> `up2`, the upsampled sky over the block's rows x (64 + 2*15) columns, rows interleaved
+//            in pairs (operand layout of the packed row filter); the Gaussian's BORDER_REFLECT_101 is applied to the
+//            FULL-RES coordinates of rows and columns; also one block ahead;
+//   row      31-tap row filter, taps accumulated k = 0..30 in order; a thread makes 2 rows x 4 columns from one 36-wide
+//            register window of row pairs; results go to a ring of SKY_NSLOT blocks of row-filtered rows (the first
+//            SKY_LA blocks are mirrored behind the ring so that 34-row windows never wrap);
+//   column   column filter (centre + 15 symmetric pairs) of the block whose 15-row lower apron has just been produced
+//            (SKY_LA blocks behind): 4 rows x 2 columns per thread from a 34-row window; subtract from the gray tile
+//            that cp.async fetched during the row filter; write; fp64 sum / sum of squares over the statistics ROI;
 //            per-32-px-segment maximum (lets the thresholding pass skip empty segments).
+// Order inside the loop: barrier B | row(b), hrow(b+1) | barrier C | column(b - SKY_LA), up(b+1), row taps of b+2.
+// Two barriers per step; every global load of the steady state is issued one phase before its use.
 // Marching removes the vertical apron of a tiled design (each row is upsampled and row-filtered
 // once per strip instead of 1.23x) and every dependent global load from the steady state.
 // HBM traffic: gray read once (4 B/px), stars written once (4 B/px).  About 112 non-fusable
