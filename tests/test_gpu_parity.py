@@ -86,7 +86,10 @@ def test_masters_and_calibration(eng, w, h, c, dt):
 
 
 # ------------------------------------------------------------------------------- K2 / K3
-@pytest.mark.parametrize("w,h", [(203, 165), (640, 480), (1197, 799), (333, 1064), (64, 64)])
+# odd sizes, strips / segments / steps that do not divide, a tall frame (several row segments, folded reflections at both
+# ends), frames smaller than one strip or one step, and the smallest geometry the engine takes (one low-res pixel)
+@pytest.mark.parametrize("w,h", [(203, 165), (640, 480), (1197, 799), (333, 1064), (64, 64), (8, 8), (17, 70), (70, 17), (130, 33),
+                                 (72, 2100)])
 def test_sky_subtraction_and_threshold(eng, w, h):
     eng.set_geometry(w, h, 1, np.float32, 2)
     g = blob_image(w, h, 20, seed=w * 3 + h)
