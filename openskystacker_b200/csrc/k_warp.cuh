@@ -8,6 +8,8 @@
 // cvRound = round-half-even), the blend is fp32 ((a*w00 + b*w01) + c*w10) + d*w11 without
 // FMA, taps outside the image read 0 (BORDER_CONSTANT) — SURVEY.md a-14 / Appendix B.7.
 #pragma once
+#include <cuda.h> // CUtensorMap
+
 #include "common.cuh"
 
 namespace oss {
@@ -295,6 +297,216 @@ k_finalize(const float *__restrict__ sum, const float *__restrict__ ref, float *
         ((float4 *)(out + i0))[0] = q;
     } else {
         for (long long i = i0; i < count; i++) out[i] = __fmul_rn(ref ? __fadd_rn(ref[i], sum[i]) : sum[i], r);
+    }
+}
+
+
+// =======================================================================================
+// K8c  warp + accumulate with TMA-staged tiles (the default for geometries whose rows are 16-byte multiples).
+//
+// Same arithmetic and the same 64x32 accumulator tile per CTA as k_warp_accumulate_tiled, but the source footprint of
+// every frame is fetched by ONE `cp.async.bulk.tensor` (3-D tensor map over [slot][row][column*channel] of the calibrated
+// planes, box = WT_ROWS x WT_COLS pixels) issued by one thread and completed on an mbarrier:
+//   - out-of-bounds parts of the box arrive as zeros, which IS cv::warpAffine's BORDER_CONSTANT 0: border tiles take the
+//     same fast path as interior ones (no per-tap bounds tests, no clamped footprint);
+//   - every staged row starts at the same pixel (the footprint's first column rounded down to 4 pixels, the 16-byte
+//     granularity of TMA coordinates): one base pointer serves all taps;
+//   - no `__syncthreads` in the frame loop: consumers wait on the "full" mbarrier of their stage, each warp arrives on the
+//     stage's "empty" mbarrier when it has read its taps, and only the producer thread waits for that before it overwrites
+//     the stage with the frame after next — warps drift apart by up to a frame instead of meeting at a barrier per frame
+//     (the largest stall of the cp.async version).
+// The per-row (X0, Y0) coordinate tables of all frames of the launch are staged once in the prologue.
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "MBAR_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra MBAR_DONE;\n"
+        "bra MBAR_WAIT;\n"
+        "MBAR_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *map, int x, int y, int z, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(smem_u32(smem_dst)),
+                 "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)) : "memory");
+}
+
+struct WarpFootT { int sx0, sy0; bool empty, fits; };
+
+template <int C>
+struct WarpTmaSmem {
+    float tiles[2][WT_ROWS * WT_COLS * C]; // TMA destinations: 128-byte aligned (WT_ROWS * WT_COLS * C * 4 is a multiple of 128)
+    int2 rowxy[OSS_MAX_BATCH][WT_H];
+    WarpFootT foot[OSS_MAX_BATCH];
+    int valid[OSS_MAX_BATCH + 1];
+    unsigned long long full[2], empty[2];
+};
+
+template <int C>
+__global__ void __launch_bounds__(256, 3)
+k_warp_accumulate_tma(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ cal, long long strideCal,
+                      const AlignOut *__restrict__ align, int nframes, const int2 *__restrict__ ab, long long strideAB,
+                      const int2 *__restrict__ xy, long long strideXY, float *__restrict__ sum, int W, int H, int ytile0)
+{
+    constexpr int ROWF = WT_COLS * C;
+    constexpr unsigned TILE_BYTES = WT_ROWS * ROWF * 4;
+    static_assert(TILE_BYTES % 128 == 0, "TMA destinations must stay 128-byte aligned");
+    extern __shared__ __align__(16) unsigned char wsm_tma[];
+    // TMA destinations need 128-byte alignment: round the dynamic window up (the launch asks for 128 bytes more)
+    WarpTmaSmem<C> &sm = *(WarpTmaSmem<C> *)(wsm_tma + ((128u - (smem_u32(wsm_tma) & 127u)) & 127u));
+    const int tid = threadIdx.x, tx = tid & 63, ty = tid >> 6, lane = tid & 31;
+    const int x0 = blockIdx.x * WT_W, y0 = (blockIdx.y + ytile0) * WT_H;
+    const int x = x0 + tx;
+    const int xe = min(x0 + WT_W, W) - 1, ye = min(y0 + WT_H, H) - 1;
+    const bool col_ok = x < W;
+    if (tid == 0) { // frames that aligned, in order (util.cpp:746-747 skips the others)
+        int n = 0;
+        for (int f = 0; f < nframes; f++)
+            if (align[f].err == 0) sm.valid[1 + n++] = f;
+        sm.valid[0] = n;
+        mbar_init(&sm.full[0], 1); mbar_init(&sm.full[1], 1);
+        mbar_init(&sm.empty[0], 8); mbar_init(&sm.empty[1], 8);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    float acc[8][C];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const int y = y0 + ty + 4 * k;
+#pragma unroll
+        for (int ch = 0; ch < C; ch++) acc[k][ch] = (col_ok && y < H) ? sum[((long long)y * W + x) * C + ch] : 0.f;
+    }
+    __syncthreads();
+    const int nvalid = sm.valid[0];
+    // footprints (unclamped: what falls outside the frame arrives as zeros) and the row tables of every frame
+    if (tid < nvalid) {
+        const int f = sm.valid[1 + tid];
+        const int2 *AB = ab + f * strideAB, *XY = xy + f * strideXY;
+        const int2 a0 = AB[x0], a1 = AB[xe], b0 = XY[y0], b1 = XY[ye];
+        const int Xlo = min(a0.x, a1.x) + min(b0.x, b1.x), Xhi = max(a0.x, a1.x) + max(b0.x, b1.x);
+        const int Ylo = min(a0.y, a1.y) + min(b0.y, b1.y), Yhi = max(a0.y, a1.y) + max(b0.y, b1.y);
+        const int sx_lo = Xlo >> 10, sx_hi = (Xhi >> 10) + 1, sy_lo = Ylo >> 10, sy_hi = (Yhi >> 10) + 1;
+        WarpFootT t;
+        t.sx0 = sx_lo & ~3; // the box must start at a 16-byte multiple of the row: 4 pixels (4 or 12 floats); floors negatives too
+        t.sy0 = sy_lo;
+        t.empty = sx_hi < 0 || sx_lo > W - 1 || sy_hi < 0 || sy_lo > H - 1; // the whole tile maps outside the frame
+        t.fits = (sy_hi - sy_lo + 1) <= WT_ROWS && (sx_hi - t.sx0 + 1) <= WT_COLS && sx_lo > -(1 << 20) && sx_lo < (1 << 20) &&
+                 sy_lo > -(1 << 20) && sy_lo < (1 << 20);
+        sm.foot[tid] = t;
+    }
+    for (int i = tid; i < nvalid * WT_H; i += 256) {
+        const int v = i / WT_H, r = i - v * WT_H;
+        sm.rowxy[v][r] = xy[sm.valid[1 + v] * strideXY + min(y0 + r, H - 1)];
+    }
+    __syncthreads();
+
+    // producer (thread 0): frame v -> stage v & 1
+    auto issue = [&](int v) {
+        const WarpFootT t = sm.foot[v];
+        const int s = v & 1;
+        if (t.fits && !t.empty) {
+            mbar_arrive_expect_tx(&sm.full[s], TILE_BYTES);
+            tma_load_3d(sm.tiles[s], &tmap, t.sx0 * C, t.sy0, sm.valid[1 + v], &sm.full[s]);
+        } else {
+            mbar_arrive(&sm.full[s]); // nothing to stage: the phase still completes
+        }
+    };
+    if (tid == 0 && nvalid > 0) issue(0);
+    int2 abx_next = make_int2(0, 0);
+    if (nvalid > 0 && col_ok) abx_next = ab[sm.valid[1] * strideAB + x];
+    for (int v = 0; v < nvalid; v++) {
+        const int f = sm.valid[1 + v], s = v & 1;
+        const int2 abx = abx_next;
+        if (v + 1 < nvalid) {
+            if (tid == 0) {
+                // stage (v + 1) & 1 was last read for frame v - 1: wait until all 8 warps have arrived for it
+                if (v >= 1) mbar_wait(&sm.empty[(v + 1) & 1], ((v - 1) >> 1) & 1);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                issue(v + 1);
+            }
+            if (col_ok) abx_next = ab[sm.valid[2 + v] * strideAB + x]; // consumed one frame later
+        }
+        mbar_wait(&sm.full[s], (v >> 1) & 1);
+        const WarpFootT t = sm.foot[v];
+        const int2 *rowxy = sm.rowxy[v];
+        if (col_ok) {
+            if (t.empty) { // warpAffine writes 0 there
+#pragma unroll
+                for (int k = 0; k < 8; k++)
+#pragma unroll
+                    for (int ch = 0; ch < C; ch++) acc[k][ch] = __fadd_rn(acc[k][ch], 0.f);
+            } else if (t.fits) {
+                // every tap is inside the staged box; taps outside the frame were filled with zeros by the TMA unit
+                const float *tb = sm.tiles[s] - t.sx0 * C - t.sy0 * ROWF;
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const int yy = ty + 4 * k;
+                    if (y0 + yy >= H) continue;
+                    const int2 b = rowxy[yy];
+                    const int X = (b.x + abx.x) >> 5, Y = (b.y + abx.y) >> 5;
+                    const float fx = (float)(X & 31) * (1.f / 32), fy = (float)(Y & 31) * (1.f / 32);
+                    const float ix = 1.f - fx, iy = 1.f - fy;
+                    const float w00 = iy * ix, w01 = iy * fx, w10 = fy * ix, w11 = fy * fx; // exact: multiples of 1/1024
+                    const float *p0 = tb + (Y >> 5) * ROWF + (X >> 5) * C;
+                    const float *p1 = p0 + ROWF;
+#pragma unroll
+                    for (int ch = 0; ch < C; ch++) {
+                        float val = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(p0[ch], w00), __fmul_rn(p0[C + ch], w01)), __fmul_rn(p1[ch], w10)),
+                                              __fmul_rn(p1[C + ch], w11));
+                        acc[k][ch] = __fadd_rn(acc[k][ch], val);
+                    }
+                }
+            } else { // footprint larger than the box (strong rotation / scale): direct gathers with bounds tests
+                const float *src = cal + f * strideCal;
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const int yy = ty + 4 * k;
+                    if (y0 + yy >= H) continue;
+                    const int2 b = rowxy[yy];
+                    const int X = (b.x + abx.x) >> 5, Y = (b.y + abx.y) >> 5;
+                    const int sx = min(max(X >> 5, -32768), 32767), sy = min(max(Y >> 5, -32768), 32767);
+                    const float fx = (float)(X & 31) * (1.f / 32), fy = (float)(Y & 31) * (1.f / 32);
+                    const float ix = 1.f - fx, iy = 1.f - fy;
+                    const float w00 = iy * ix, w01 = iy * fx, w10 = fy * ix, w11 = fy * fx;
+                    const bool xa = sx >= 0 && sx < W, xb = sx + 1 >= 0 && sx + 1 < W;
+                    const bool ya = sy >= 0 && sy < H, yb = sy + 1 >= 0 && sy + 1 < H;
+                    const float *p = src + ((long long)sy * W + sx) * C;
+#pragma unroll
+                    for (int ch = 0; ch < C; ch++) {
+                        const float s00 = (xa && ya) ? __ldg(p + ch) : 0.f, s01 = (xb && ya) ? __ldg(p + C + ch) : 0.f;
+                        const float s10 = (xa && yb) ? __ldg(p + (long long)W * C + ch) : 0.f;
+                        const float s11 = (xb && yb) ? __ldg(p + (long long)W * C + C + ch) : 0.f;
+                        float val = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(s00, w00), __fmul_rn(s01, w01)), __fmul_rn(s10, w10)), __fmul_rn(s11, w11));
+                        acc[k][ch] = __fadd_rn(acc[k][ch], val);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.empty[s]); // this warp has read its taps of stage s
+    }
+    if (!col_ok) return;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const int y = y0 + ty + 4 * k;
+        if (y >= H) continue;
+#pragma unroll
+        for (int ch = 0; ch < C; ch++) sum[((long long)y * W + x) * C + ch] = acc[k][ch];
     }
 }
 

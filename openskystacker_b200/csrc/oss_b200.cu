@@ -82,6 +82,8 @@ struct Pipe {
     unsigned char *raw_stage[2] = {nullptr, nullptr};
     cudaEvent_t copy_done[2] = {nullptr, nullptr}, raw_free[2] = {nullptr, nullptr};
     cudaEvent_t warp_done = nullptr, detect_done = nullptr, sky_done = nullptr, cal_done = nullptr, med_done = nullptr;
+    CUtensorMap cal_map;       // [slot][row][column * channel] view of ws.cal for the TMA warp kernel
+    bool has_cal_map = false;
     long long batch_counter = 0;
 };
 
@@ -367,7 +369,9 @@ int oss_create(oss_ctx **out, int device)
         cudaFuncSetAttribute(k_sky_sub_stats, cudaFuncAttributeMaxDynamicSharedMemorySize, kSkySmemBytes) != cudaSuccess ||
         cudaFuncSetAttribute(k_focas, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FocasSmem)) != cudaSuccess ||
         cudaFuncSetAttribute(k_warp_accumulate_tiled<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, warp_tiled_smem<3>()) != cudaSuccess ||
-        cudaFuncSetAttribute(k_warp_accumulate_tiled<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, warp_tiled_smem<1>()) != cudaSuccess) {
+        cudaFuncSetAttribute(k_warp_accumulate_tiled<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, warp_tiled_smem<1>()) != cudaSuccess ||
+        cudaFuncSetAttribute(k_warp_accumulate_tma<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WarpTmaSmem<3>) + 128) != cudaSuccess ||
+        cudaFuncSetAttribute(k_warp_accumulate_tma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WarpTmaSmem<1>) + 128) != cudaSuccess) {
         for (int p = 0; p < OSS_MAX_PIPES; p++) { if (c->pipes[p].copy_stream) cudaStreamDestroy(c->pipes[p].copy_stream); if (c->pipes[p].chain_stream) cudaStreamDestroy(c->pipes[p].chain_stream); }
     if (c->bulk) cudaStreamDestroy(c->bulk);
         if (c->bulk) cudaStreamDestroy(c->bulk);
@@ -442,6 +446,34 @@ int oss_memcpy_d2h(oss_ctx *c, void *d, const void *s, size_t n)
 }
 
 // ---- geometry --------------------------------------------------------------------------
+// 3-D tensor map over a pipeline's calibrated planes for k_warp_accumulate_tma; false (the cp.async kernel is used) when the
+// rows are not 16-byte multiples or the driver entry point is missing
+static bool make_cal_map(oss_ctx *c, Pipe &pp, int slots)
+{
+    typedef CUresult (*EncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                    const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeTiled encode = nullptr;
+    static bool looked = false;
+    if (!looked) {
+        looked = true;
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            encode = (EncodeTiled)fn;
+    }
+    if (getenv("OSS_B200_NO_TMA")) return false;
+    const Geom &g = c->g;
+    const long long rowf = (long long)g.W * g.C;
+    if (!encode || (rowf * 4) % 16 != 0 || (pp.ws.stridePC * 4) % 16 != 0 || ((uintptr_t)pp.ws.cal & 15)) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)rowf, (cuuint64_t)g.H, (cuuint64_t)slots};
+    const cuuint64_t strides[2] = {(cuuint64_t)rowf * 4, (cuuint64_t)pp.ws.stridePC * 4};
+    const cuuint32_t box[3] = {(cuuint32_t)(WT_COLS * g.C), (cuuint32_t)WT_ROWS, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return encode(&pp.cal_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, pp.ws.cal, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 int oss_set_geometry(oss_ctx *c, int W, int H, int C, int sample, int slots)
 {
     if (!c) return OSS_E_ARG;
@@ -509,6 +541,7 @@ int oss_set_geometry(oss_ctx *c, int W, int H, int C, int sample, int slots)
         CK(cudaEventCreateWithFlags(&pp.sky_done, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&pp.cal_done, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&pp.med_done, cudaEventDisableTiming));
+        pp.has_cal_map = make_cal_map(c, pp, slots);
         pp.batch_counter = 0;
     }
     c->cur = 0;
@@ -964,7 +997,13 @@ static int flush_warps(oss_ctx *c, size_t keep, int bands = 1, int (*after_band)
             const int t0 = (int)((long long)tiles_y * b / nb), t1 = (int)((long long)tiles_y * (b + 1) / nb);
             if (t1 > t0) {
                 const dim3 wgrid((g.W + WT_W - 1) / WT_W, t1 - t0);
-                if (g.C == 3) {
+                if (pp.has_cal_map && g.C == 3) {
+                    LAUNCH("warp_accumulate", k_warp_accumulate_tma<3>, wgrid, 256, sizeof(WarpTmaSmem<3>) + 128, pp.cal_map, w.cal, w.stridePC, w.align,
+                           pw.nb, w.warp_ab, (long long)g.W, w.warp_xy, (long long)g.H, c->sum, g.W, g.H, t0);
+                } else if (pp.has_cal_map) {
+                    LAUNCH("warp_accumulate", k_warp_accumulate_tma<1>, wgrid, 256, sizeof(WarpTmaSmem<1>) + 128, pp.cal_map, w.cal, w.stridePC, w.align,
+                           pw.nb, w.warp_ab, (long long)g.W, w.warp_xy, (long long)g.H, c->sum, g.W, g.H, t0);
+                } else if (g.C == 3) {
                     LAUNCH("warp_accumulate", k_warp_accumulate_tiled<3>, wgrid, 256, warp_tiled_smem<3>(), w.cal, w.stridePC, w.align, pw.nb,
                            w.warp_ab, (long long)g.W, w.warp_xy, (long long)g.H, c->sum, g.W, g.H, t0);
                 } else {
