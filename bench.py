@@ -399,7 +399,7 @@ def main():
         k = kernels[name]
         # dram__bytes_read + dram__bytes_write per launch from the committed ncu --set full capture
         # (profiles/r01_ncu_summary.md), valid for the default shape only: 24 MP RGB16, M = 3, 17 frames per launch
-        ncu_traffic = {"calibrate_gray": 3.316e9 + 6.470e9, "warp_accumulate": 5.214e9 + 0.295e9}
+        ncu_traffic = {"calibrate_gray": 3.316e9 + 6.470e9, "warp_accumulate": 5.223e9 + 0.283e9}
         default_shape = (W, H, C, a.ncal, a.slots, a.lights) == (6000, 4000, 3, 10, 17, 50)
         traffic = ncu_traffic.get(name) if default_shape else None
         roof = {"bound": "hbm", "kernel": name, "achieved": k["achieved_gbs"], "peak": peak, "unit": "GB/s",
