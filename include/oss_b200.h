@@ -111,6 +111,13 @@ OSS_API int oss_set_geometry(oss_ctx *ctx, int width, int height, int channels, 
  * n - 1 batches; 1..4, default 3.  The accumulation order stays the frame order.  Takes effect at
  * the next oss_set_geometry. */
 OSS_API int oss_set_pipelines(oss_ctx *ctx, int n);
+/* Detection work space: room for width*height / one_in candidate pixels (pixels above the detection threshold) per
+ * frame; 1..64, default 16 (6.25 %).  The reference has no such limit (stardetector.cpp:192-246 grows vectors); here a
+ * frame that exceeds it is NOT silently dropped: its report carries overflow != 0 and oss_finish / oss_sync return
+ * OSS_E_CAPACITY, upon which the caller raises the capacity and runs the stack again.  Threshold 1 (1.5 sigma: 6.7 % of
+ * pure-noise pixels) needs one_in <= 8; thresholds >= 2 fit the default on any star field.  Takes effect at the next
+ * oss_set_geometry. */
+OSS_API int oss_set_candidate_capacity(oss_ctx *ctx, int one_in);
 
 /* ---- master frames: stackBias / stackDarks / stackDarkFlats / stackFlats, util.cpp:584-722
  * Build order follows ImageStackerPrivate::process (imagestacker.cpp:262-281): bias first,
@@ -176,6 +183,14 @@ OSS_API int oss_align_lists(oss_ctx *ctx, const int32_t *xy_ref, int n_ref, cons
 
 /* ---- warp only: cv::warpAffine(INTER_LINEAR | WARP_INVERSE_MAP), util.cpp:579 ----------- */
 OSS_API int oss_warp_affine(oss_ctx *ctx, const float *src_host, float *dst_host, const float *M);
+/* The stacking path's warp + accumulate in isolation (util.cpp:579 + :749 for n frames): dst = sum over i, in order, of
+ * warpAffine(src[i], M + 6 i) for the frames whose err[i] == 0 (err may be NULL; util.cpp:746-747 skips the others),
+ * n <= frames_in_flight.  `which` selects the kernel — OSS_WARP_AUTO is what oss_add_lights runs for this geometry,
+ * OSS_WARP_TMA / OSS_WARP_TILED force the TMA-staged / cp.async-staged variant (OSS_E_ARG when the geometry cannot use
+ * it) — and `bands` >= 1 splits the launch into that many bands of tile rows like oss_comm_reduce does. */
+typedef enum { OSS_WARP_AUTO = 0, OSS_WARP_TMA = 1, OSS_WARP_TILED = 2 } oss_warp_kernel;
+OSS_API int oss_warp_accumulate(oss_ctx *ctx, const float *const *src_host, const float *M, const int32_t *err, int n,
+                                float *dst_host, int which, int bands);
 
 /* ---- multi-GPU: frames shard across ranks (the reference's -j decomposition, util.cpp:738;
  * combine = imagestacker.cpp:348-351).  One process per GPU; the caller distributes the

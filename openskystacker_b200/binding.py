@@ -10,6 +10,7 @@ CSRC = os.path.join(_HERE, "csrc")
 NOBJS, MAX_MATCH = 40, 120
 
 U8, U16, F32 = 0, 1, 2
+WARP_AUTO, WARP_TMA, WARP_TILED = 0, 1, 2
 HOST, DEVICE = 0, 1
 BIAS, DARK, DARKFLAT, FLAT = 0, 1, 2, 3
 _SAMPLE = {np.dtype(np.uint8): U8, np.dtype(np.uint16): U16, np.dtype(np.float32): F32}
@@ -84,6 +85,8 @@ _SIGS = {
     "oss_align_lists": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                   C.c_void_p, C.c_void_p, C.c_void_p]),
     "oss_warp_affine": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "oss_warp_accumulate": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int]),
+    "oss_set_candidate_capacity": (C.c_int, [C.c_void_p, C.c_int]),
     "oss_comm_unique_id": (C.c_int, [C.c_void_p]),
     "oss_comm_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "oss_comm_broadcast_masters": (C.c_int, [C.c_void_p, C.c_int]),
@@ -306,6 +309,20 @@ class Engine:
         out = np.empty_like(src)
         self._ck(self._L.oss_warp_affine(self._h, _ptr(src), _ptr(out), _ptr(M)))
         return out
+
+    def warp_accumulate(self, srcs, Ms, err=None, which=WARP_AUTO, bands=1):
+        """sum over the frames (in order, err == 0 only) of warpAffine(srcs[i], Ms[i]) through the stacking path's kernels."""
+        keep = [np.ascontiguousarray(s, np.float32) for s in srcs]
+        ptrs = (C.c_void_p * len(keep))(*[k.ctypes.data for k in keep])
+        Ms = np.ascontiguousarray(Ms, np.float32).reshape(len(keep), 6)
+        e = np.ascontiguousarray(err, np.int32) if err is not None else None
+        out = np.empty_like(keep[0])
+        self._ck(self._L.oss_warp_accumulate(self._h, ptrs, _ptr(Ms), _ptr(e) if e is not None else None, len(keep),
+                                             _ptr(out), which, bands))
+        return out
+
+    def set_candidate_capacity(self, one_in):
+        self._ck(self._L.oss_set_candidate_capacity(self._h, one_in))
 
     def debug_plane(self, what, slot=0):
         h, w, c, _ = self.geom

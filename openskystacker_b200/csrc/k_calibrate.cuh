@@ -28,6 +28,11 @@ template <> struct Sample<float> {
     __device__ static __forceinline__ float conv(float v) { return v; }
 };
 
+// cv::divide on CV_32F as OpenCV 3.3.0 (the reference's pinned version, Dockerfile:7) defines it: the quotient is 0 where
+// the divisor is 0 (OpenCV >= 4 returns inf/nan there).  A master-flat pixel that is exactly 0 (a stuck pixel equal in
+// flats and dark-flats) must not poison sigma and the stack with NaN.  util.cpp:271
+__device__ __forceinline__ float div_flat(float v, float m) { return m == 0.f ? 0.f : __fdiv_rn(v, m); }
+
 // streaming 16-byte load that does not allocate in L1 (each raw sample is read once)
 __device__ __forceinline__ uint4 ld_stream16(const void *p)
 {
@@ -99,7 +104,7 @@ k_calibrate_gray(const __grid_constant__ FramePtrs raws, const float *__restrict
         if (HAS_F) {
             load_f32<N>(flat + p0 * C, m);
 #pragma unroll
-            for (int i = 0; i < N; i++) v[i] = __fdiv_rn(v[i], m[i]);
+            for (int i = 0; i < N; i++) v[i] = div_flat(v[i], m[i]);
         }
         store_f32<N>(out, v);
         if (C == 3) {
@@ -118,7 +123,7 @@ k_calibrate_gray(const __grid_constant__ FramePtrs raws, const float *__restrict
                 float x = Sample<T>::conv(((const T *)raws.p[blockIdx.y])[i]);
                 if (HAS_B) x = __fsub_rn(x, bias[i]);
                 if (HAS_D) x = __fsub_rn(x, dark[i]);
-                if (HAS_F) x = __fdiv_rn(x, flat[i]);
+                if (HAS_F) x = div_flat(x, flat[i]);
                 cal[(long long)blockIdx.y * strideCal + i] = x;
                 c[ch] = x;
             }
@@ -171,7 +176,7 @@ k_calibrate_gray_batch(const __grid_constant__ FramePtrs raws, int nframes, cons
         for (int i = 0; i < N; i++) {
             if (HAS_B) v[i] = __fsub_rn(v[i], mb[i]);
             if (HAS_D) v[i] = __fsub_rn(v[i], md[i]);
-            if (HAS_F) v[i] = __fdiv_rn(v[i], mf[i]);
+            if (HAS_F) v[i] = div_flat(v[i], mf[i]);
         }
         store_f32<N>(cal + (long long)f * strideCal + p0 * C, v);
         if (C == 3) {

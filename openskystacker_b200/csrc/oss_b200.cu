@@ -93,6 +93,7 @@ struct oss_ctx {
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     Pipe pipes[OSS_MAX_PIPES];
     int npipes = 3, want_pipes = 3, cur = 0;
+    int cap_one_in = 16;                 // detection work space: P / cap_one_in candidate pixels per frame
     cudaStream_t bulk = nullptr;         // the one low-priority stream of all bulk kernels
     struct PendingWarp { int pipe, nb; };
     std::vector<PendingWarp> pending_warps; // detected batches whose warp + accumulate is not queued yet, oldest first
@@ -344,14 +345,11 @@ int oss_create(oss_ctx **out, int device)
         ok = cudaStreamCreateWithPriority(&c->pipes[p].chain_stream, cudaStreamNonBlocking, prio_greatest) == cudaSuccess &&
              cudaStreamCreateWithPriority(&c->pipes[p].copy_stream, cudaStreamNonBlocking, prio_greatest) == cudaSuccess;
     ok = ok && cudaStreamCreateWithPriority(&c->bulk, cudaStreamNonBlocking, prio_least) == cudaSuccess;
-    if (!ok) {
-        delete c;
-        return OSS_E_CUDA;
-    }
+    if (!ok) { oss_destroy(c); return OSS_E_CUDA; } // oss_destroy null-checks every member: fine on a partly built ctx
     if (cudaEventCreateWithFlags(&c->ref_ready, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ref_copied, cudaEventDisableTiming) != cudaSuccess ||
         cudaMallocHost((void **)&c->h_ref_ds, sizeof(DetectState)) != cudaSuccess) {
-        delete c;
+        oss_destroy(c);
         return OSS_E_CUDA;
     }
     if (const char *e = getenv("OSS_B200_PIPES")) c->want_pipes = atoi(e);
@@ -372,10 +370,7 @@ int oss_create(oss_ctx **out, int device)
         cudaFuncSetAttribute(k_warp_accumulate_tiled<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, warp_tiled_smem<1>()) != cudaSuccess ||
         cudaFuncSetAttribute(k_warp_accumulate_tma<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WarpTmaSmem<3>) + 128) != cudaSuccess ||
         cudaFuncSetAttribute(k_warp_accumulate_tma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WarpTmaSmem<1>) + 128) != cudaSuccess) {
-        for (int p = 0; p < OSS_MAX_PIPES; p++) { if (c->pipes[p].copy_stream) cudaStreamDestroy(c->pipes[p].copy_stream); if (c->pipes[p].chain_stream) cudaStreamDestroy(c->pipes[p].chain_stream); }
-    if (c->bulk) cudaStreamDestroy(c->bulk);
-        if (c->bulk) cudaStreamDestroy(c->bulk);
-        delete c;
+        oss_destroy(c);
         return OSS_E_CUDA;
     }
     *out = c;
@@ -491,8 +486,8 @@ int oss_set_geometry(oss_ctx *c, int W, int H, int C, int sample, int slots)
     g.roi_x = W / 20; g.roi_y = H / 20;
     g.roi_w = (int)(W * 0.9); g.roi_h = (int)(H * 0.9);
     g.P = (long long)W * H;
-    long long div = 16;
-    if (const char *e = getenv("OSS_B200_CAP_DIV")) div = atoll(e) > 0 ? atoll(e) : 16;
+    long long div = c->cap_one_in;
+    if (const char *e = getenv("OSS_B200_CAP_DIV")) div = atoll(e) > 0 ? atoll(e) : div;
     long long cap = g.P / div;
     if (cap < 65536) cap = g.P < 65536 ? g.P : 65536; // small frames: every pixel may be a candidate
     g.cap = (int)cap;
@@ -974,6 +969,46 @@ static int ensure_report_room(oss_ctx *c, int upto)
 
 } // extern "C"
 
+// a light whose candidate pixels exceeded the work space was left out of the stack (k_focas sees 0 stars): the reference
+// would have stacked it, so the stack is reported as failed instead of silently differing (streams must be drained)
+static int check_light_overflow(oss_ctx *c)
+{
+    for (int i = 0; i < c->nlights; i++) {
+        const DetectState &d = c->h_ds_chunks[i / kChunk][i % kChunk];
+        if (d.overflow)
+            return fail(c, OSS_E_CAPACITY, "light %d: %d candidate pixels exceed the detection work space (%d); raise it with "
+                        "oss_set_candidate_capacity and run the stack again", i, d.ncand, c->g.cap);
+    }
+    return OSS_OK;
+}
+
+// warp + accumulate of the first nb slots of a pipeline's calibrated planes into `dst`, tile rows [t0, t1).
+// which: OSS_WARP_AUTO = the TMA kernel where the pipeline has a tensor map (rows are 16-byte multiples), else the cp.async
+// one; OSS_WARP_TMA / OSS_WARP_TILED force one of them (tests).  Launches on c->stream.
+static int launch_warp(oss_ctx *c, Pipe &pp, int nb, int t0, int t1, float *dst, int which)
+{
+    const Geom &g = c->g;
+    Workspace &w = pp.ws;
+    if (which == OSS_WARP_TMA && !pp.has_cal_map)
+        return fail(c, OSS_E_ARG, "the TMA warp kernel needs rows of a multiple of 16 bytes (width * channels * 4)");
+    const bool tma = which == OSS_WARP_TMA || (which == OSS_WARP_AUTO && pp.has_cal_map);
+    const dim3 wgrid((g.W + WT_W - 1) / WT_W, t1 - t0);
+    if (tma && g.C == 3) {
+        LAUNCH("warp_accumulate", k_warp_accumulate_tma<3>, wgrid, 256, sizeof(WarpTmaSmem<3>) + 128, pp.cal_map, w.cal, w.stridePC, w.align,
+               nb, w.warp_ab, (long long)g.W, w.warp_xy, (long long)g.H, dst, g.W, g.H, t0);
+    } else if (tma) {
+        LAUNCH("warp_accumulate", k_warp_accumulate_tma<1>, wgrid, 256, sizeof(WarpTmaSmem<1>) + 128, pp.cal_map, w.cal, w.stridePC, w.align,
+               nb, w.warp_ab, (long long)g.W, w.warp_xy, (long long)g.H, dst, g.W, g.H, t0);
+    } else if (g.C == 3) {
+        LAUNCH("warp_accumulate", k_warp_accumulate_tiled<3>, wgrid, 256, warp_tiled_smem<3>(), w.cal, w.stridePC, w.align, nb,
+               w.warp_ab, (long long)g.W, w.warp_xy, (long long)g.H, dst, g.W, g.H, t0);
+    } else {
+        LAUNCH("warp_accumulate", k_warp_accumulate_tiled<1>, wgrid, 256, warp_tiled_smem<1>(), w.cal, w.stridePC, w.align, nb,
+               w.warp_ab, (long long)g.W, w.warp_xy, (long long)g.H, dst, g.W, g.H, t0);
+    }
+    return OSS_OK;
+}
+
 // queue the warp + accumulate kernels of the oldest pending batches until at most `keep` remain.
 // bands > 1 (multi-GPU, the very last batch of a stack): that batch's warp is launched as `bands` kernels over horizontal
 // bands of tile rows, and after each one `after_band(c, first_row, rows)` runs (it queues the NCCL reduce of those rows of
@@ -995,22 +1030,7 @@ static int flush_warps(oss_ctx *c, size_t keep, int bands = 1, int (*after_band)
         const int tiles_y = (g.H + WT_H - 1) / WT_H, nb = (last && bands > 1) ? bands : 1;
         for (int b = 0; b < nb; b++) {
             const int t0 = (int)((long long)tiles_y * b / nb), t1 = (int)((long long)tiles_y * (b + 1) / nb);
-            if (t1 > t0) {
-                const dim3 wgrid((g.W + WT_W - 1) / WT_W, t1 - t0);
-                if (pp.has_cal_map && g.C == 3) {
-                    LAUNCH("warp_accumulate", k_warp_accumulate_tma<3>, wgrid, 256, sizeof(WarpTmaSmem<3>) + 128, pp.cal_map, w.cal, w.stridePC, w.align,
-                           pw.nb, w.warp_ab, (long long)g.W, w.warp_xy, (long long)g.H, c->sum, g.W, g.H, t0);
-                } else if (pp.has_cal_map) {
-                    LAUNCH("warp_accumulate", k_warp_accumulate_tma<1>, wgrid, 256, sizeof(WarpTmaSmem<1>) + 128, pp.cal_map, w.cal, w.stridePC, w.align,
-                           pw.nb, w.warp_ab, (long long)g.W, w.warp_xy, (long long)g.H, c->sum, g.W, g.H, t0);
-                } else if (g.C == 3) {
-                    LAUNCH("warp_accumulate", k_warp_accumulate_tiled<3>, wgrid, 256, warp_tiled_smem<3>(), w.cal, w.stridePC, w.align, pw.nb,
-                           w.warp_ab, (long long)g.W, w.warp_xy, (long long)g.H, c->sum, g.W, g.H, t0);
-                } else {
-                    LAUNCH("warp_accumulate", k_warp_accumulate_tiled<1>, wgrid, 256, warp_tiled_smem<1>(), w.cal, w.stridePC, w.align, pw.nb,
-                           w.warp_ab, (long long)g.W, w.warp_xy, (long long)g.H, c->sum, g.W, g.H, t0);
-                }
-            }
+            if (t1 > t0) { int rc = launch_warp(c, pp, pw.nb, t0, t1, c->sum, OSS_WARP_AUTO); if (rc) return rc; }
             if (nb > 1 && after_band) {
                 const int r0 = t0 * WT_H, r1 = t1 * WT_H < g.H ? t1 * WT_H : g.H;
                 int rc = after_band(c, r0, r1 - r0);
@@ -1099,7 +1119,7 @@ int oss_sync(oss_ctx *c)
 {
     USE_PIPE0();
     CK(sync_all(c));
-    return OSS_OK;
+    return check_light_overflow(c);
 }
 
 int oss_num_reports(oss_ctx *c) { return c ? c->nlights : 0; }
@@ -1152,6 +1172,7 @@ int oss_finish(oss_ctx *c, float *out, int *tv)
     if (!c->has_ref) return fail(c, OSS_E_ARG, "no reference");
     { int rc = ref_host(c); if (rc) return rc; } // a reference that overflowed the work space invalidates the stack
     CK(cudaStreamSynchronize(c->copy_stream));
+    { int rc = check_light_overflow(c); if (rc) return rc; }
     int v;
     int rc = total_valid(c, &v);
     if (rc) return rc;
@@ -1285,33 +1306,43 @@ int oss_align_lists(oss_ctx *c, const int32_t *xy1, int n1, const int32_t *xy2, 
 }
 
 // ---- warp only -------------------------------------------------------------------------
-int oss_warp_affine(oss_ctx *c, const float *src, float *dst, const float *M)
+// n frames, each through its own matrix, summed in frame order onto a zeroed accumulator (0.f + v == v): the stacking
+// path's own coordinate tables and warp kernels, with the kernel and the band split selectable so that tests reach every
+// variant.  err (may be NULL): per-frame alignment status; frames with err != 0 are skipped like util.cpp:746-747.
+int oss_warp_accumulate(oss_ctx *c, const float *const *src, const float *M, const int32_t *err, int n, float *dst, int which, int bands)
 {
     USE_PIPE0();
-    if (!src || !dst || !M) return fail(c, OSS_E_ARG, "null argument");
+    if (!src || !dst || !M || n < 1 || n > c->slots) return fail(c, OSS_E_ARG, "bad warp arguments (1 <= n <= frames_in_flight)");
+    if (which < OSS_WARP_AUTO || which > OSS_WARP_TILED || bands < 1) return fail(c, OSS_E_ARG, "bad warp kernel selection");
     const Geom &g = c->g;
     const size_t bytes = (size_t)g.P * g.C * sizeof(float);
-    // same kernels as the stacking path (coordinate tables + tiled warp) onto a zeroed accumulator: 0.f + v == v
-    Workspace &w = c->ws;
-    AlignOut ao{};
-    ao.k = 0; ao.err = 0;
-    memcpy(ao.M, M, sizeof ao.M);
-    CK(cudaMemcpyAsync(w.cal, src, bytes, cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemcpyAsync(w.align, &ao, sizeof ao, cudaMemcpyHostToDevice, c->stream));
+    Pipe &pp = c->pipes[0];
+    Workspace &w = pp.ws;
+    std::vector<AlignOut> ao(n);
+    for (int i = 0; i < n; i++) {
+        if (!src[i]) return fail(c, OSS_E_ARG, "null frame");
+        ao[i] = AlignOut{};
+        ao[i].err = err ? err[i] : 0;
+        memcpy(ao[i].M, M + 6 * i, sizeof ao[i].M);
+        CK(cudaMemcpyAsync(w.cal + (size_t)i * w.stridePC, src[i], bytes, cudaMemcpyHostToDevice, c->stream));
+    }
+    CK(cudaMemcpyAsync(w.align, ao.data(), sizeof(AlignOut) * n, cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemsetAsync(c->result, 0, bytes, c->stream));
-    LAUNCH("warp_tables", k_warp_tables, dim3((g.W + g.H + 255) / 256, 1), 256, 0, w.align, w.warp_ab, (long long)g.W, w.warp_xy,
+    LAUNCH("warp_tables", k_warp_tables, dim3((g.W + g.H + 255) / 256, n), 256, 0, w.align, w.warp_ab, (long long)g.W, w.warp_xy,
            (long long)g.H, g.W, g.H);
-    const dim3 wgrid((g.W + WT_W - 1) / WT_W, (g.H + WT_H - 1) / WT_H);
-    if (g.C == 3) {
-        LAUNCH("warp_accumulate", k_warp_accumulate_tiled<3>, wgrid, 256, warp_tiled_smem<3>(), w.cal, w.stridePC, w.align, 1, w.warp_ab, (long long)g.W,
-               w.warp_xy, (long long)g.H, c->result, g.W, g.H, 0);
-    } else {
-        LAUNCH("warp_accumulate", k_warp_accumulate_tiled<1>, wgrid, 256, warp_tiled_smem<1>(), w.cal, w.stridePC, w.align, 1, w.warp_ab, (long long)g.W,
-               w.warp_xy, (long long)g.H, c->result, g.W, g.H, 0);
+    const int tiles_y = (g.H + WT_H - 1) / WT_H;
+    for (int b = 0; b < bands; b++) { // same band boundaries as flush_warps / oss_comm_reduce
+        const int t0 = (int)((long long)tiles_y * b / bands), t1 = (int)((long long)tiles_y * (b + 1) / bands);
+        if (t1 > t0) { int rc = launch_warp(c, pp, n, t0, t1, c->result, which); if (rc) return rc; }
     }
     CK(cudaMemcpyAsync(dst, c->result, bytes, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     return OSS_OK;
+}
+
+int oss_warp_affine(oss_ctx *c, const float *src, float *dst, const float *M)
+{
+    return oss_warp_accumulate(c, &src, M, nullptr, 1, dst, OSS_WARP_AUTO, 1);
 }
 
 // ---- multi-GPU -------------------------------------------------------------------------
@@ -1476,6 +1507,13 @@ int oss_set_pipelines(oss_ctx *c, int n)
 {
     if (!c || n < 1 || n > OSS_MAX_PIPES) return fail(c, OSS_E_ARG, "pipelines must be 1..%d", OSS_MAX_PIPES);
     c->want_pipes = n; // takes effect at the next oss_set_geometry
+    return OSS_OK;
+}
+
+int oss_set_candidate_capacity(oss_ctx *c, int one_in)
+{
+    if (!c || one_in < 1 || one_in > 64) return fail(c, OSS_E_ARG, "candidate capacity is width*height / (1..64)");
+    c->cap_one_in = one_in; // takes effect at the next oss_set_geometry
     return OSS_OK;
 }
 

@@ -66,7 +66,7 @@ void orc_calibrate(float *img, size_t count, const float *bias, const float *dar
         float v = img[i];
         if (bias) v = v - bias[i];
         if (dark) v = v - dark[i];
-        if (flat) v = v / flat[i];
+        if (flat) v = flat[i] == 0.0f ? 0.0f : v / flat[i]; /* cv::divide of OpenCV 3.3.0 (Dockerfile:7): x / 0 = 0 */
         img[i] = v;
     }
 }

@@ -67,3 +67,23 @@ def test_gray_and_masters():
     avg = np.float32(cv2.mean(want)[0])
     got = oracle.flat_normalize(want)
     assert same(got, want * np.float32(1.0 / np.float64(avg)))
+
+
+def test_calibration_divide_follows_opencv_3_3_on_zero_divisors():
+    """getCalibratedImage (util.cpp:269-271): subtract, subtract, divide.  Equal to cv2 wherever the flat is non-zero;
+    where it is exactly 0 (either sign) the quotient is 0 — cv::divide of OpenCV 3.3.0, the version the reference pins
+    (Dockerfile:7; arithm.cpp div_f: `denom != 0 ? src1 * scale / denom : 0`).  cv2 >= 4 returns inf/nan there, which
+    is the one place the oracle deliberately departs from the cv2 4.13 it is otherwise pinned to."""
+    rng = np.random.default_rng(10)
+    img = rng.random((40, 60, 3), dtype=np.float32)
+    bias = rng.random((40, 60, 3), dtype=np.float32) * 0.01
+    dark = rng.random((40, 60, 3), dtype=np.float32) * 0.02
+    flat = (0.5 + rng.random((40, 60, 3), dtype=np.float32)).astype(np.float32)
+    flat[3, 5, 1] = 0.0
+    flat[7, 9, 2] = -0.0
+    got = oracle.calibrate(img, bias, dark, flat)
+    want = cv2.divide(cv2.subtract(cv2.subtract(img, bias), dark), flat)
+    nz = flat != 0
+    assert same(got[nz], want[nz])
+    assert got[3, 5, 1] == 0.0 and got[7, 9, 2] == 0.0 and np.isfinite(got).all()
+    assert not np.isfinite(want[3, 5, 1])   # documents the cv2 >= 4 behaviour the reference never saw
