@@ -315,16 +315,21 @@ class Job:
             out = [tuple(x) for x in t.cpu().tolist()]
         return out
 
-    def expect_all_valid(self, what):
-        """Every timed step must have stacked every light (+ the reference): a run in which lights silently fail to
-        align skips their warps and would print a HIGHER frames/s."""
+    def expect_valid(self, what):
+        """Every step must have stacked the SAME number of frames, and nearly all of them: a run in which lights silently
+        fail to align skips their warps and would print a HIGHER frames/s.  (A few synthetic lights do fail in the
+        reference's algorithm itself — its clipping loop rejects them, focas.cpp:338-369 — on the GPU and in the oracle alike;
+        `checks` names them and compares one with the oracle.)  Returns (steps checked, totalValidImages)."""
         want = self.total_lights + 1
-        bad = [t for t in self.tv if t != want] if self.rank == 0 else []
-        if bad:
-            raise SystemExit(f"bench invalid ({what}): totalValidImages {bad[0]} != {want} (lights + reference) in {len(bad)} step(s)")
-        n = len(self.tv)
+        tv = self.tv
         self.tv = []
-        return n
+        if self.rank != 0:
+            return len(tv), 0
+        if len(set(tv)) > 1:
+            raise SystemExit(f"bench invalid ({what}): totalValidImages differs between steps: {sorted(set(tv))}")
+        if tv and tv[0] < 0.95 * want:
+            raise SystemExit(f"bench invalid ({what}): totalValidImages {tv[0]} of {want} (lights + reference)")
+        return len(tv), (tv[0] if tv else want)
 
 
 def detect_only_job(eng, B, cf, rank, world, dist, steps, warmup):
@@ -464,7 +469,7 @@ def main():
     inp, nl = job.inp, job.nl
     nb = eng.frame_bytes()
     job.timed(job.step, a.warmup)
-    job.expect_all_valid("warm-up")
+    job.expect_valid("warm-up")
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -477,7 +482,7 @@ def main():
         eng.profile(False)
         eng.profile_table()
     clocks = sampler.finish() if rank == 0 else None
-    steps_checked = job.expect_all_valid("timed region")
+    steps_checked, tv_timed = job.expect_valid("timed region")
     frames_total = job.total_lights + 1
     dev_s = float(np.mean([t[0] for t in t_dev]))
     value = frames_total / dev_s
@@ -507,7 +512,9 @@ def main():
         step_host = lambda: job.step(B.HOST, cal_h, Ct.c_void_p(host[inp.ref]), lights_h, Ct.c_void_p(res_host) if rank == 0 else None)
         job.timed(step_host, 1)
         t_host = job.timed(step_host, max(1, min(a.steps, 3)))
-        job.expect_all_valid("e2e")
+        _, tv_e2e = job.expect_valid("e2e")
+        if rank == 0 and tv_e2e != tv_timed:
+            raise SystemExit(f"bench invalid: host-fed run stacked {tv_e2e} frames, device-resident run {tv_timed}")
         wall_s = float(np.mean([t[1] for t in t_host]))
         h2d = (nl + (1 + ncal_total if rank == 0 else 0)) * nb
         e2e = {"value": frames_total / wall_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
@@ -599,9 +606,9 @@ def main():
                                    "frac": P * B_frame * (job.total_lights + 1) / dev_s / 1e9 / world / peak}}
 
     # ------------------------------------------------------------------ checks (outside every timed region)
-    checks = {"total_valid_every_step": frames_total, "steps_checked": steps_checked}
+    checks = {"total_valid_every_step": tv_timed, "frames_handed_in": frames_total, "steps_checked": steps_checked}
     if not a.no_checks:
-        checks.update(run_checks(eng, B, job, res_n, reports_n, shape, world))
+        checks.update(run_checks(eng, B, job, res_n, reports_n, tv_timed, world))
 
     # ------------------------------------------------------------------ CPU baseline beside it (N = 1 only)
     cpu = None
@@ -627,12 +634,11 @@ def main():
                 j2 = Job(eng, B, c2, 0, 1, None, None)
                 j2.timed(j2.step, 2)
                 t2 = j2.timed(j2.step, 3)
-                if k == 3:
-                    j2.expect_all_valid("config 3")
+                _, tv2 = j2.expect_valid(f"config {k}")
                 s2 = float(np.mean([t[0] for t in t2]))
                 also[f"config{k}"] = {"workload": workload_text(c2, 1, c2["lights"]), "value": (j2.total_lights + 1) / s2, "unit": UNIT,
-                                      "ms_per_step": 1e3 * s2, "total_valid": j2.tv[-1] if j2.tv else j2.total_lights + 1,
-                                      "frames": j2.total_lights + 1, "scaling": c2["scaling"]}
+                                      "ms_per_step": 1e3 * s2, "total_valid": tv2, "frames": j2.total_lights + 1, "scaling": c2["scaling"],
+                                      "failed_lights": [i + 1 for i, r in enumerate(eng.reports()) if r.err != 0]}
                 for p in j2.inp.all_ptrs():
                     eng.device_free(p)
             also["config5"] = detect_only_job(eng, B, dict(CONFIGS[5]), 0, 1, None, 3, 2)
@@ -650,7 +656,7 @@ def main():
 SKY_OPS_PER_PIXEL = 113.0
 
 
-def run_checks(eng, B, job, res_n, reports_n, shape, world):
+def run_checks(eng, B, job, res_n, reports_n, tv_n, world):
     """Correctness of what was just timed, on rank 0 after the other ranks have left.
     (1) N > 1: the reduced N-rank stack against the 1-rank stack of the SAME frames (this GPU re-renders every rank's
         lights and stacks them in rank order); differences are float reassociation only (imagestacker.cpp:348-351 has the
@@ -679,8 +685,8 @@ def run_checks(eng, B, job, res_n, reports_n, shape, world):
     if world > 1:
         d = np.abs(res_n - img1)
         out.update(nrank_vs_1rank_maxabs=float(d.max()), nrank_vs_1rank_max_rel=float(d.max() / max(float(np.abs(img1).max()), 1e-30)),
-                   nrank_vs_1rank_total_valid=[job.total_lights + 1, int(tv1)], nrank_vs_1rank_bound=1e-6,
-                   nrank_vs_1rank_ok=bool(d.max() <= 1e-6 and tv1 == job.total_lights + 1))
+                   nrank_vs_1rank_total_valid=[int(tv_n), int(tv1)], nrank_vs_1rank_bound=1e-6,
+                   nrank_vs_1rank_ok=bool(d.max() <= 1e-6 and tv1 == tv_n))
         # rank 0's own lights give the same reports whether it runs alone or as a rank
         out["rank0_reports_identical"] = reports_n is not None and reports_n[:len(reports_1)] == reports_1[:len(reports_n)]
     else:
@@ -690,7 +696,9 @@ def run_checks(eng, B, job, res_n, reports_n, shape, world):
         import oracle
         if world > 1:
             inp.render(job.pedestal, cf["nflats"] > 0, job.first, job.stride, with_ref=False)
-        idx = min(7, job.nl - 1)
+        failed = [i for i, x in enumerate(reports_1) if x[2] != 0]
+        out["rank0_failed_lights"] = [job.first + i * job.stride for i in failed]
+        idx = failed[0] if failed else min(7, job.nl - 1)   # a light the GPU skipped, when there is one: the oracle must skip it too
         hw = (cf["h"], cf["w"], cf["c"]) if cf["c"] == 3 else (cf["h"], cf["w"])
         raw = eng.from_device(inp.lights[idx], hw, np.uint16)
         ref_raw = eng.from_device(inp.ref, hw, np.uint16)

@@ -272,6 +272,7 @@ def test_zero_flat_pixel_gives_zero_not_nan(eng):
     put inf/NaN into the calibrated frame, sigma and the stack."""
     w, h = 640, 480
     ds = synth.dataset(w, h, 2, 3, nstars=80, nflats=2)
+    eng.set_pipelines(1)                # the lights' planes land in pipeline 0, where debug_plane looks
     eng.set_geometry(w, h, 3, np.uint16, 2)
     eng.build_master(B.FLAT, ds["flats"])
     flat = eng.get_master(B.FLAT)
@@ -288,6 +289,7 @@ def test_zero_flat_pixel_gives_zero_not_nan(eng):
     img, tv = eng.finish()
     assert np.isfinite(img).all() and tv == 3
     eng.clear_masters()
+    eng.set_pipelines(3)
 
 
 # ------------------------------------------------------------------------------- whole path
