@@ -158,18 +158,25 @@ class Inputs:
 
 
 def run_job(eng, B, cal, ref, light_arr, nlights, mem, result_host, comm=None, rank=0, threshold=20):
-    """One step.  cal = [(kind, ctypes pointer array, count)] in build order (bias, dark, flat).  Returns totalValidImages
-    on rank 0 (imagestacker.cpp:304,350), 0 elsewhere."""
+    """One step.  cal = [(kind, ctypes pointer array, count)] in build order (bias, dark, flat).  With N > 1 every rank holds
+    the calibration frames and accumulates ITS 1/N row slice of every master; the slices are exchanged over NVLink
+    (bit-identical masters, 1/N of the calibration bytes read per rank).  Returns totalValidImages on rank 0
+    (imagestacker.cpp:304,350), 0 elsewhere."""
     L, h = eng._L, eng._h
+    if comm:
+        row0, rows = eng.comm_master_slice()
     for kind, arr, n in cal:
-        if rank == 0:
-            eng._ck(L.oss_build_master(h, kind, arr, n, mem))
         if comm:
-            eng.comm_broadcast_master(kind, 0)  # asynchronous: overlaps the next master and the reference on rank 0
+            eng._ck(L.oss_master_begin(h, kind, n, row0, rows))
+            eng._ck(L.oss_master_add(h, arr, n, mem))
+            eng._ck(L.oss_master_end(h))
+            eng.comm_allgather_master(kind)  # asynchronous: overlaps the next master's slice and the reference
+        else:
+            eng._ck(L.oss_build_master(h, kind, arr, n, mem))
     if rank == 0:
         eng._ck(L.oss_set_reference(h, ref, mem, threshold))
     if comm:
-        eng.comm_broadcast_reference(0)
+        eng.comm_broadcast_reference(threshold, 0)
     eng._ck(L.oss_add_lights(h, light_arr, nlights, mem))
     if comm:
         eng.comm_reduce(0)
@@ -271,15 +278,12 @@ class Job:
             self.first, self.stride = 1 + rank * cf["lights"], 1
         self.nl = len(self.my)
         self.total_lights = cf["lights"] * world if cf["scaling"] == "weak" else cf["lights"]
-        own_cal = rank == 0
-        self.inp = Inputs(eng, W, H, self.nl, cf["nbias"] if own_cal else 0, cf["ndarks"] if own_cal else 0,
-                          cf["nflats"] if own_cal else 0, nstars=cf["stars"])
+        # every rank renders the (seeded, identical) calibration frames: each one accumulates its own row slice of the masters
+        self.inp = Inputs(eng, W, H, self.nl, cf["nbias"], cf["ndarks"], cf["nflats"], nstars=cf["stars"])
         self.pedestal = (100.0 if cf["nbias"] else 0.0) + (300.0 if cf["ndarks"] else 0.0)
         self.inp.render(self.pedestal, cf["nflats"] > 0, self.first, self.stride)
         arr = lambda ps: (Ct.c_void_p * len(ps))(*ps)
         self.cal = [(k, arr(ps), len(ps)) for k, ps in ((B.BIAS, self.inp.bias), (B.DARK, self.inp.darks), (B.FLAT, self.inp.flats)) if ps]
-        if rank != 0:   # the other ranks take part in the broadcast of every master the root builds
-            self.cal = [(k, None, 0) for k, n in ((B.BIAS, cf["nbias"]), (B.DARK, cf["ndarks"]), (B.FLAT, cf["nflats"])) if n]
         self.lights = arr(self.inp.lights)
         self.tv = []
 
@@ -430,7 +434,8 @@ def main():
               "frames_in_flight": cf["slots"], "pipelines": cf["pipes"],
               "e2e_frames_in_flight": a.e2e_slots, "e2e_pipelines": a.e2e_pipes,
               "l2": "inputs (%.1f GB per step) are far larger than L2" % ((lights_per_gpu + 1 + ncal_total) * W * H * C * 2 / 1e9),
-              "parallelism": f"frames sharded over {world} GPU(s), one ncclReduce of the f32 sum" if world > 1 else "1 GPU"}
+              "parallelism": (f"lights sharded over {world} GPUs, masters built in {world} row slices + NVLink all-gather, one ncclReduce of the "
+                              "f32 sum") if world > 1 else "1 GPU"}
 
     # ------------------------------------------------------------------ reference arm (CPU only, nothing of ours loaded)
     if a.impl == "reference":
@@ -503,7 +508,7 @@ def main():
             eng._ck(L.oss_memcpy_d2h(eng._h, hp, p, nb))
             host[p] = hp
         hp_arr = lambda ps: (Ct.c_void_p * len(ps))(*[host[p] for p in ps])
-        cal_h = [(k, hp_arr(ps), len(ps)) for k, ps in ((B.BIAS, inp.bias), (B.DARK, inp.darks), (B.FLAT, inp.flats)) if ps] if rank == 0 else job.cal
+        cal_h = [(k, hp_arr(ps), len(ps)) for k, ps in ((B.BIAS, inp.bias), (B.DARK, inp.darks), (B.FLAT, inp.flats)) if ps]
         lights_h = hp_arr(inp.lights)
         res_host = L.oss_host_alloc(W * H * C * 4) if rank == 0 else None
         if (a.e2e_slots, a.e2e_pipes) != (job.slots, job.pipes):
@@ -516,7 +521,7 @@ def main():
         if rank == 0 and tv_e2e != tv_timed:
             raise SystemExit(f"bench invalid: host-fed run stacked {tv_e2e} frames, device-resident run {tv_timed}")
         wall_s = float(np.mean([t[1] for t in t_host]))
-        h2d = (nl + (1 + ncal_total if rank == 0 else 0)) * nb
+        h2d = (nl + (1 if rank == 0 else 0) + ncal_total / world) * nb   # every rank uploads its 1/N row slice of each calibration frame
         e2e = {"value": frames_total / wall_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(W * H * C * 4), "ms_per_step": 1e3 * wall_s,
                "timing": "wall clock between stream syncs (covers H2D, kernels, D2H of the float32 stack)"}

@@ -111,6 +111,13 @@ OSS_API int oss_set_geometry(oss_ctx *ctx, int width, int height, int channels, 
  * n - 1 batches; 1..4, default 3.  The accumulation order stays the frame order.  Takes effect at
  * the next oss_set_geometry. */
 OSS_API int oss_set_pipelines(oss_ctx *ctx, int n);
+/* SM partition: the FP32-pipe-bound sky kernel (k_sky_sub_stats) gets a green context of `fp_sms` SMs (rounded up to the
+ * device's granularity, 8 on sm_100), the HBM-bound bulk kernels (masters, calibration, warp + accumulate) the remaining
+ * SMs, so the two classes run side by side on disjoint SMs instead of back to back; results are bit-identical (only the
+ * order in time changes, never the accumulation order).  0 = no partition.  Takes effect at the next oss_set_geometry;
+ * oss_get_sm_split returns what the driver granted (0, 0 when off).  Environment OSS_B200_SPLIT sets the default. */
+OSS_API int oss_set_sm_split(oss_ctx *ctx, int fp_sms);
+OSS_API int oss_get_sm_split(oss_ctx *ctx, int *fp_sms, int *hbm_sms);
 /* Detection work space: room for width*height / one_in candidate pixels (pixels above the detection threshold) per
  * frame; 1..64, default 16 (6.25 %).  The reference has no such limit (stardetector.cpp:192-246 grows vectors); here a
  * frame that exceeds it is NOT silently dropped: its report carries overflow != 0 and oss_finish / oss_sync return
@@ -125,6 +132,15 @@ OSS_API int oss_set_candidate_capacity(oss_ctx *ctx, int one_in);
  * dark-flat, divided by the mean of its channel 0).  A master that was never built is
  * "absent" exactly like an empty cv::Mat (util.cpp:269-271). */
 OSS_API int oss_build_master(oss_ctx *ctx, int kind, const void *const *frames, int n, int mem);
+/* The same build in pieces, for callers that decode calibration frames a few at a time (stackDarks' loop, util.cpp:596-607,
+ * reads one file per iteration) and for multi-GPU builds: oss_master_begin names the master, the total number of frames
+ * and the rows [row0, row0 + rows) of it that THIS context accumulates (rows <= 0: the whole frame; a slice starts on a
+ * multiple of 16 rows); oss_master_add hands in the next n FULL frames, in order (only the slice's bytes are copied /
+ * read; host frames may be reused when it returns); oss_master_end closes it (a whole flat is normalised here, a sliced
+ * one in oss_comm_allgather_master).  oss_build_master = begin(whole) + add + end. */
+OSS_API int oss_master_begin(oss_ctx *ctx, int kind, int n_total, int row0, int rows);
+OSS_API int oss_master_add(oss_ctx *ctx, const void *const *frames, int n, int mem);
+OSS_API int oss_master_end(oss_ctx *ctx);
 OSS_API int oss_set_master(oss_ctx *ctx, int kind, const float *data, int mem);
 OSS_API int oss_get_master(oss_ctx *ctx, int kind, float *out_host); /* OSS_E_ARG if absent */
 OSS_API int oss_clear_masters(oss_ctx *ctx);
@@ -202,10 +218,19 @@ OSS_API int oss_comm_broadcast_masters(oss_ctx *ctx, int root);
  * master and the reference frame; calibration waits for it on the device.  Every rank calls it for the same kinds in the
  * same order (the image list tells each rank which masters exist). */
 OSS_API int oss_comm_broadcast_master(oss_ctx *ctx, int kind, int root);
-/* ships the calibrated reference's star list + detection threshold; only `root` keeps the
- * reference frame inside its sum (imagestacker.cpp:287,304) */
-OSS_API int oss_comm_broadcast_reference(oss_ctx *ctx, int root);
-/* ncclReduce(sum) + count to root over NVLink; afterwards oss_finish on root gives the stack */
+/* Masters built cooperatively: rank r accumulates the rows oss_comm_master_slice returns (1/N of the frame) of EVERY
+ * calibration frame (oss_master_begin/add/end), then oss_comm_allgather_master exchanges the slices in place over NVLink on
+ * the comm stream (asynchronously: it overlaps the next master's slice and the reference; calibration waits for it on the
+ * device) and normalises a flat.  Per-pixel arithmetic is unchanged, so the masters are bit-identical to a 1-GPU build;
+ * each rank reads (and, from the host, uploads) 1/N of the calibration bytes. */
+OSS_API int oss_comm_master_slice(oss_ctx *ctx, int *row0, int *rows);
+OSS_API int oss_comm_allgather_master(oss_ctx *ctx, int kind);
+/* ships the calibrated reference's triangle and star lists; `threshold` is the detection threshold of the stack (the same
+ * on every rank: it is a command-line value); only `root` keeps the reference frame inside its sum
+ * (imagestacker.cpp:287,304).  No rank waits on the host: alignment kernels wait for the data on the device. */
+OSS_API int oss_comm_broadcast_reference(oss_ctx *ctx, int root, int threshold);
+/* ncclReduce(sum) + count to root over NVLink, queued behind this rank's last warp + accumulate (asynchronous); afterwards
+ * oss_finish on root gives the stack, oss_sync on the others drains their part */
 OSS_API int oss_comm_reduce(oss_ctx *ctx, int root);
 
 /* ---- bench utilities (no reference counterpart) -------------------------------------------

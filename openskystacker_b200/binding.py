@@ -87,11 +87,18 @@ _SIGS = {
     "oss_warp_affine": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "oss_warp_accumulate": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int]),
     "oss_set_candidate_capacity": (C.c_int, [C.c_void_p, C.c_int]),
+    "oss_set_sm_split": (C.c_int, [C.c_void_p, C.c_int]),
+    "oss_get_sm_split": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "oss_comm_unique_id": (C.c_int, [C.c_void_p]),
     "oss_comm_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "oss_comm_broadcast_masters": (C.c_int, [C.c_void_p, C.c_int]),
     "oss_comm_broadcast_master": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
-    "oss_comm_broadcast_reference": (C.c_int, [C.c_void_p, C.c_int]),
+    "oss_comm_broadcast_reference": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "oss_comm_master_slice": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "oss_comm_allgather_master": (C.c_int, [C.c_void_p, C.c_int]),
+    "oss_master_begin": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "oss_master_add": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_int]),
+    "oss_master_end": (C.c_int, [C.c_void_p]),
     "oss_comm_reduce": (C.c_int, [C.c_void_p, C.c_int]),
     "oss_mark": (C.c_int, [C.c_void_p, C.c_int]),
     "oss_elapsed_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
@@ -321,6 +328,14 @@ class Engine:
                                              _ptr(out), which, bands))
         return out
 
+    def set_sm_split(self, fp_sms):
+        self._ck(self._L.oss_set_sm_split(self._h, fp_sms))
+
+    def sm_split(self):
+        a, b = C.c_int(), C.c_int()
+        self._ck(self._L.oss_get_sm_split(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def set_candidate_capacity(self, one_in):
         self._ck(self._L.oss_set_candidate_capacity(self._h, one_in))
 
@@ -349,8 +364,28 @@ class Engine:
     def comm_broadcast_master(self, kind, root=0):
         self._ck(self._L.oss_comm_broadcast_master(self._h, kind, root))
 
-    def comm_broadcast_reference(self, root=0):
-        self._ck(self._L.oss_comm_broadcast_reference(self._h, root))
+    def comm_broadcast_reference(self, threshold, root=0):
+        self._ck(self._L.oss_comm_broadcast_reference(self._h, root, threshold))
+
+    def comm_master_slice(self):
+        a, b = C.c_int(), C.c_int()
+        self._ck(self._L.oss_comm_master_slice(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def comm_allgather_master(self, kind):
+        self._ck(self._L.oss_comm_allgather_master(self._h, kind))
+
+    def build_master_slice(self, kind, frames, row0, rows, mem=HOST, chunk=0):
+        """oss_master_begin / add / end over rows [row0, row0 + rows) (rows <= 0: whole), `chunk` frames per add (0: all)."""
+        ptrs, keep = self._ptrs(frames, mem)
+        n = len(frames)
+        self._ck(self._L.oss_master_begin(self._h, kind, n, row0, rows))
+        step = chunk or n
+        for i in range(0, n, step):
+            m = min(step, n - i)
+            sub = (C.c_void_p * m)(*[ptrs[j] for j in range(i, i + m)])
+            self._ck(self._L.oss_master_add(self._h, sub, m, mem))
+        self._ck(self._L.oss_master_end(self._h))
 
     def comm_reduce(self, root=0):
         self._ck(self._L.oss_comm_reduce(self._h, root))

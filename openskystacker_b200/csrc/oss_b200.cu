@@ -34,6 +34,8 @@ struct NcclApi {
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Reduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
 };
 
@@ -55,6 +57,8 @@ static bool nccl_load(std::string *why)
     SYM(CommDestroy, "ncclCommDestroy")
     SYM(Broadcast, "ncclBroadcast")
     SYM(Reduce, "ncclReduce")
+    SYM(GroupStart, "ncclGroupStart")
+    SYM(GroupEnd, "ncclGroupEnd")
     SYM(GetErrorString, "ncclGetErrorString")
 #undef SYM
     g_nccl.handle = h;
@@ -93,8 +97,16 @@ struct oss_ctx {
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     Pipe pipes[OSS_MAX_PIPES];
     int npipes = 3, want_pipes = 3, cur = 0;
+    struct MasterBuild { int kind = -1, n_total = 0, added = 0, row0 = 0, rows = 0; bool sliced = false; } mb;
+    int slice_row0[4] = {0, 0, 0, 0}, slice_rows[4] = {0, 0, 0, 0}; // rows of each master this rank built last (0 rows: whole)
     int cap_one_in = 16;                 // detection work space: P / cap_one_in candidate pixels per frame
     cudaStream_t bulk = nullptr;         // the one low-priority stream of all bulk kernels
+    // SM partition (green contexts): the FP32-bound sky kernel runs on `fp_stream`, which lives in a green context of
+    // split_fp SMs, while the HBM-bound bulk kernels (masters, calibration, warp) run on `bulk`, re-created in the green
+    // context of the remaining SMs — the two classes co-run on disjoint SMs at their own full residency.  0 = no split.
+    int split_fp = 0, split_fp_got = 0, split_hbm_got = 0;
+    cudaStream_t fp_stream = nullptr;
+    CUgreenCtx green_fp = nullptr, green_hbm = nullptr;
     struct PendingWarp { int pipe, nb; };
     std::vector<PendingWarp> pending_warps; // detected batches whose warp + accumulate is not queued yet, oldest first
     int sky_blocks = 0; // CTAs per frame of the last sky_sub_stats launch (= partial sums finalize_stats adds up)
@@ -191,6 +203,7 @@ static cudaError_t sync_all(oss_ctx *c, bool with_comm = true)
         if (c->pipes[p].chain_stream) { cudaError_t r = cudaStreamSynchronize(c->pipes[p].chain_stream); if (r != cudaSuccess) e = r; }
     }
     if (c->bulk) { cudaError_t r = cudaStreamSynchronize(c->bulk); if (r != cudaSuccess) e = r; }
+    if (c->fp_stream) { cudaError_t r = cudaStreamSynchronize(c->fp_stream); if (r != cudaSuccess) e = r; }
     if (with_comm && c->comm_stream) { cudaError_t r = cudaStreamSynchronize(c->comm_stream); if (r != cudaSuccess) e = r; }
     return e;
 }
@@ -308,6 +321,91 @@ static void free_geometry(oss_ctx *c)
     c->synth_stars = nullptr;
 }
 
+// ---- SM partition ----------------------------------------------------------------------
+struct GreenApi {
+    bool looked = false, ok = false;
+    CUresult (*DeviceGet)(CUdevice *, int) = nullptr;
+    CUresult (*DeviceGetDevResource)(CUdevice, CUdevResource *, CUdevResourceType) = nullptr;
+    CUresult (*DevSmResourceSplitByCount)(CUdevResource *, unsigned int *, const CUdevResource *, CUdevResource *, unsigned int, unsigned int) = nullptr;
+    CUresult (*DevResourceGenerateDesc)(CUdevResourceDesc *, CUdevResource *, unsigned int) = nullptr;
+    CUresult (*GreenCtxCreate)(CUgreenCtx *, CUdevResourceDesc, CUdevice, unsigned int) = nullptr;
+    CUresult (*GreenCtxDestroy)(CUgreenCtx) = nullptr;
+    CUresult (*GreenCtxStreamCreate)(CUstream *, CUgreenCtx, unsigned int, int) = nullptr;
+};
+static GreenApi g_green;
+
+static bool green_load()
+{
+    if (g_green.looked) return g_green.ok;
+    g_green.looked = true;
+    bool ok = true;
+    auto get = [&](const char *name, void **fn) {
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint(name, fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !*fn) ok = false;
+    };
+    get("cuDeviceGet", (void **)&g_green.DeviceGet);
+    get("cuDeviceGetDevResource", (void **)&g_green.DeviceGetDevResource);
+    get("cuDevSmResourceSplitByCount", (void **)&g_green.DevSmResourceSplitByCount);
+    get("cuDevResourceGenerateDesc", (void **)&g_green.DevResourceGenerateDesc);
+    get("cuGreenCtxCreate", (void **)&g_green.GreenCtxCreate);
+    get("cuGreenCtxDestroy", (void **)&g_green.GreenCtxDestroy);
+    get("cuGreenCtxStreamCreate", (void **)&g_green.GreenCtxStreamCreate);
+    g_green.ok = ok;
+    return ok;
+}
+
+static void split_teardown(oss_ctx *c)
+{
+    if (c->fp_stream) { cudaStreamDestroy(c->fp_stream); c->fp_stream = nullptr; }
+    if (c->green_fp || c->green_hbm) {
+        // the bulk stream lives in green_hbm: replace it by an ordinary low-priority stream first
+        if (c->bulk) cudaStreamDestroy(c->bulk);
+        c->bulk = nullptr;
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        cudaStreamCreateWithPriority(&c->bulk, cudaStreamNonBlocking, lo);
+        if (c->green_fp) g_green.GreenCtxDestroy(c->green_fp);
+        if (c->green_hbm) g_green.GreenCtxDestroy(c->green_hbm);
+        c->green_fp = c->green_hbm = nullptr;
+    }
+    c->split_fp_got = c->split_hbm_got = 0;
+}
+
+// (re)build the partition: `fp_sms` SMs (rounded up to the device's granularity, 8 on sm_100) for the sky kernel, the rest
+// for the HBM-bound bulk kernels.  Called with every stream idle.
+static int split_setup(oss_ctx *c, int fp_sms)
+{
+    split_teardown(c);
+    if (fp_sms <= 0) return OSS_OK;
+    if (!green_load()) return fail(c, OSS_E_CUDA, "this driver has no green-context entry points (SM partition unavailable)");
+    CUdevice dev;
+    CUdevResource all, grp, rest;
+    unsigned int n = 1;
+    CUdevResourceDesc d_fp, d_hbm;
+#define GK(call) do { CUresult r_ = (call); if (r_ != CUDA_SUCCESS) { split_teardown(c); return fail(c, OSS_E_CUDA, "%s failed (CUresult %d)", #call, (int)r_); } } while (0)
+    GK(g_green.DeviceGet(&dev, c->device));
+    GK(g_green.DeviceGetDevResource(dev, &all, CU_DEV_RESOURCE_TYPE_SM));
+    if (fp_sms >= (int)all.sm.smCount) return fail(c, OSS_E_ARG, "SM split %d leaves nothing of %u SMs for the HBM-bound kernels", fp_sms, all.sm.smCount);
+    GK(g_green.DevSmResourceSplitByCount(&grp, &n, &all, &rest, 0, (unsigned)fp_sms));
+    if (n < 1 || rest.sm.smCount == 0) return fail(c, OSS_E_ARG, "SM split %d not realisable on %u SMs", fp_sms, all.sm.smCount);
+    GK(g_green.DevResourceGenerateDesc(&d_fp, &grp, 1));
+    GK(g_green.DevResourceGenerateDesc(&d_hbm, &rest, 1));
+    GK(g_green.GreenCtxCreate(&c->green_fp, d_fp, dev, CU_GREEN_CTX_DEFAULT_STREAM));
+    GK(g_green.GreenCtxCreate(&c->green_hbm, d_hbm, dev, CU_GREEN_CTX_DEFAULT_STREAM));
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    CUstream s_fp = nullptr, s_hbm = nullptr;
+    GK(g_green.GreenCtxStreamCreate(&s_fp, c->green_fp, CU_STREAM_NON_BLOCKING, lo));
+    GK(g_green.GreenCtxStreamCreate(&s_hbm, c->green_hbm, CU_STREAM_NON_BLOCKING, lo));
+#undef GK
+    c->fp_stream = (cudaStream_t)s_fp;
+    if (c->bulk) cudaStreamDestroy(c->bulk);
+    c->bulk = (cudaStream_t)s_hbm;
+    c->split_fp_got = (int)grp.sm.smCount;
+    c->split_hbm_got = (int)rest.sm.smCount;
+    return OSS_OK;
+}
+
 // ---- exported: lifetime ----------------------------------------------------------------
 extern "C" {
 
@@ -353,6 +451,7 @@ int oss_create(oss_ctx **out, int device)
         return OSS_E_CUDA;
     }
     if (const char *e = getenv("OSS_B200_PIPES")) c->want_pipes = atoi(e);
+    if (const char *e = getenv("OSS_B200_SPLIT")) c->split_fp = atoi(e);
     c->stream = c->bulk;
     c->copy_stream = c->pipes[0].copy_stream;
     // constant tables
@@ -390,6 +489,7 @@ void oss_destroy(oss_ctx *c)
     prof_flush(c);
     for (auto e : c->event_pool) cudaEventDestroy(e);
     for (int p = 0; p < OSS_MAX_PIPES; p++) { if (c->pipes[p].copy_stream) cudaStreamDestroy(c->pipes[p].copy_stream); if (c->pipes[p].chain_stream) cudaStreamDestroy(c->pipes[p].chain_stream); }
+    split_teardown(c);
     if (c->bulk) cudaStreamDestroy(c->bulk);
     if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
     if (c->comm_fork) cudaEventDestroy(c->comm_fork);
@@ -479,6 +579,11 @@ int oss_set_geometry(oss_ctx *c, int W, int H, int C, int sample, int slots)
     if (slots > OSS_MAX_BATCH) slots = OSS_MAX_BATCH;
     CK(cudaSetDevice(c->device));
     free_geometry(c);
+    if ((c->split_fp > 0) != (c->fp_stream != nullptr) || (c->split_fp > 0 && c->split_fp_got < c->split_fp)) {
+        int r_ = split_setup(c, c->split_fp);
+        if (r_) return r_;
+        c->stream = c->bulk;
+    }
     Geom g{};
     g.W = W; g.H = H; g.C = C; g.sample = sample;
     g.lw = W / 8; g.lh = H / 8;
@@ -646,22 +751,24 @@ static int dispatch_calibrate(oss_ctx *c, const FramePtrs &fp, int n, bool use_m
 
 // stage n host frames into raw_stage[set] (async on the copy stream) or pass device pointers through
 // wait == false: only queue the copies (prefetch of a later batch); the consumer calls stage_wait before its first kernel
-static int stage_frames(oss_ctx *c, const void *const *frames, int n, int mem, FramePtrs *fp, int *set_out, bool wait = true)
+static int stage_frames(oss_ctx *c, const void *const *frames, int n, int mem, FramePtrs *fp, int *set_out, bool wait = true,
+                        size_t byte0 = 0, size_t nbytes = 0)
 {
+    if (!nbytes) nbytes = c->frame_bytes;
     for (int i = 0; i < n; i++) {
         if (!frames[i]) return fail(c, OSS_E_ARG, "null frame pointer");
         if (((uintptr_t)frames[i] & 15) && mem == OSS_MEM_DEVICE) return fail(c, OSS_E_ARG, "device frames must be 16-byte aligned");
     }
     *set_out = -1;
     if (mem == OSS_MEM_DEVICE) {
-        for (int i = 0; i < n; i++) fp->p[i] = frames[i];
+        for (int i = 0; i < n; i++) fp->p[i] = (const unsigned char *)frames[i] + byte0;
         return OSS_OK;
     }
     int set = (int)(c->batch_counter++ & 1);
     CK(cudaStreamWaitEvent(c->copy_stream, c->raw_free[set], 0));
     for (int i = 0; i < n; i++) {
         unsigned char *dst = c->raw_stage[set] + (size_t)i * c->stage_stride;
-        CK(cudaMemcpyAsync(dst, frames[i], c->frame_bytes, cudaMemcpyHostToDevice, c->copy_stream));
+        CK(cudaMemcpyAsync(dst, (const unsigned char *)frames[i] + byte0, nbytes, cudaMemcpyHostToDevice, c->copy_stream));
         fp->p[i] = dst;
     }
     CK(cudaEventRecord(c->copy_done[set], c->copy_stream));
@@ -713,6 +820,10 @@ static int detect_sky(oss_ctx *c, int n)
 {
     Workspace &w = c->ws;
     const Geom &g = c->g;
+    if (c->fp_stream) { // SM partition: the sky kernel runs beside the HBM-bound kernels, ordered by events only
+        c->stream = c->fp_stream;
+        CK(cudaStreamWaitEvent(c->stream, c->pipes[c->cur].cal_done, 0));
+    }
     CK(cudaStreamWaitEvent(c->stream, c->pipes[c->cur].med_done, 0));
     const long long strideGray = g.C == 3 ? w.strideP : w.stridePC;
     const int seg_h = sky_segment_rows(g.W, g.H, n);
@@ -812,42 +923,95 @@ static int need_geom(oss_ctx *c)
 
 extern "C" {
 
-// ---- masters ---------------------------------------------------------------------------
-int oss_build_master(oss_ctx *c, int kind, const void *const *frames, int n, int mem)
+// flat /= mean(channel 0) of the WHOLE master (util.cpp:686-688), on c->stream
+static int normalise_flat(oss_ctx *c)
 {
-    USE_PIPE0_LOCAL();
-    if (kind < 0 || kind > 3 || n < 1 || !frames) return fail(c, OSS_E_ARG, "bad master arguments");
     const Geom &g = c->g;
     const long long count = g.P * g.C;
-    if (!c->master[kind]) DA(c->master[kind], count);
-    float *acc = c->master[kind];
+    float *acc = c->master[OSS_MASTER_FLAT];
+    const int nblk = 592;
+    LAUNCH("flat_mean", k_channel0_partial, nblk, 256, 0, acc, g.P, g.C, c->d_flat_partial);
+    LAUNCH("flat_mean", k_flat_ratio, 1, 32, 0, c->d_flat_partial, nblk, g.P, c->d_flat_ratio);
+    LAUNCH("flat_scale", k_scale_by, (unsigned)((count + 1023) / 1024), 256, 0, acc, count, c->d_flat_ratio, 0.f);
+    return OSS_OK;
+}
+
+int oss_master_begin(oss_ctx *c, int kind, int n_total, int row0, int rows)
+{
+    USE_PIPE0_LOCAL();
+    if (kind < 0 || kind > 3 || n_total < 1) return fail(c, OSS_E_ARG, "bad master arguments");
+    const Geom &g = c->g;
+    const bool whole = rows <= 0 || (row0 == 0 && rows >= g.H);
+    if (whole) { row0 = 0; rows = g.H; }
+    // a slice starts on a multiple of 16 rows: every sample type then starts on a 16-byte boundary whatever the width
+    if (!whole && (row0 < 0 || row0 + rows > g.H || (row0 & 15))) return fail(c, OSS_E_ARG, "master slice [%d, %d) of %d rows: start must be a multiple of 16", row0, row0 + rows, g.H);
+    if (!c->master[kind]) DA(c->master[kind], g.P * g.C);
+    c->mb = oss_ctx::MasterBuild{};
+    c->mb.kind = kind; c->mb.n_total = n_total; c->mb.row0 = row0; c->mb.rows = rows; c->mb.sliced = !whole;
+    c->slice_row0[kind] = row0; c->slice_rows[kind] = whole ? 0 : rows;
+    return OSS_OK;
+}
+
+int oss_master_add(oss_ctx *c, const void *const *frames, int n, int mem)
+{
+    NEED_GEOM();
+    oss_ctx::MasterBuild &mb = c->mb;
+    if (mb.kind < 0) return fail(c, OSS_E_ARG, "oss_master_begin has not been called");
+    if (n < 1 || !frames || mb.added + n > mb.n_total) return fail(c, OSS_E_ARG, "master frames: %d given after %d of %d", n, mb.added, mb.n_total);
+    select_pipe(c, 0);
+    const Geom &g = c->g;
+    const int kind = mb.kind;
+    const long long off = (long long)mb.row0 * g.W * g.C, count = (long long)mb.rows * g.W * g.C; // this slice, in samples
+    const size_t ssz = g.sample == OSS_U8 ? 1 : (g.sample == OSS_U16 ? 2 : 4);
+    float *acc = c->master[kind] + off;
     const float *sub1 = nullptr, *sub2 = nullptr;
-    if (kind != OSS_MASTER_BIAS) sub1 = c->master[OSS_MASTER_BIAS];     // util.cpp:593,627,662
-    if (kind == OSS_MASTER_FLAT) sub2 = c->master[OSS_MASTER_DARKFLAT]; // util.cpp:663
-    const float r = (float)(1.0 / (double)n);
+    if (kind != OSS_MASTER_BIAS && c->master[OSS_MASTER_BIAS]) sub1 = c->master[OSS_MASTER_BIAS] + off;     // util.cpp:593,627,662
+    if (kind == OSS_MASTER_FLAT && c->master[OSS_MASTER_DARKFLAT]) sub2 = c->master[OSS_MASTER_DARKFLAT] + off; // util.cpp:663
+    const float r = (float)(1.0 / (double)mb.n_total);
     const int per = c->slots;
+    int last_set = -1;
     for (int b0 = 0; b0 < n; b0 += per) {
         int nb = n - b0 < per ? n - b0 : per;
         FramePtrs fp{};
         int set;
-        int rc = stage_frames(c, frames + b0, nb, mem, &fp, &set);
+        int rc = stage_frames(c, frames + b0, nb, mem, &fp, &set, true, (size_t)off * ssz, (size_t)count * ssz);
         if (rc) return rc;
-        int first = b0 == 0, last = b0 + nb == n;
+        int first = mb.added == 0, last = mb.added + nb == mb.n_total;
 #define ACC(T) { auto kf = k_master_accumulate<T>; LAUNCH("master_accumulate", kf, (unsigned)((count + 256ll * Sample<T>::PX - 1) / (256ll * Sample<T>::PX)), 256, 0, fp, nb, sub1, sub2, acc, first, last, r, count); }
         if (g.sample == OSS_U16) ACC(uint16_t)
         else if (g.sample == OSS_U8) ACC(uint8_t)
         else ACC(float)
 #undef ACC
-        if (set >= 0) CK(cudaEventRecord(c->raw_free[set], c->stream));
+        if (set >= 0) { CK(cudaEventRecord(c->raw_free[set], c->stream)); last_set = set; }
+        mb.added += nb;
     }
-    if (kind == OSS_MASTER_FLAT) { // util.cpp:686-688
-        const int nblk = 592;
-        LAUNCH("flat_mean", k_channel0_partial, nblk, 256, 0, acc, g.P, g.C, c->d_flat_partial);
-        LAUNCH("flat_mean", k_flat_ratio, 1, 32, 0, c->d_flat_partial, nblk, g.P, c->d_flat_ratio);
-        LAUNCH("flat_scale", k_scale_by, (unsigned)((count + 1023) / 1024), 256, 0, acc, count, c->d_flat_ratio, 0.f);
-    }
-    CK(cudaStreamSynchronize(c->stream));
+    // host frames may be reused as soon as this call returns (the copies are waited for; the kernels keep running)
+    if (last_set >= 0) CK(cudaStreamSynchronize(c->copy_stream));
     return OSS_OK;
+}
+
+int oss_master_end(oss_ctx *c)
+{
+    NEED_GEOM();
+    oss_ctx::MasterBuild &mb = c->mb;
+    if (mb.kind < 0) return fail(c, OSS_E_ARG, "oss_master_begin has not been called");
+    if (mb.added != mb.n_total) return fail(c, OSS_E_ARG, "master %d: %d of %d frames were added", mb.kind, mb.added, mb.n_total);
+    select_pipe(c, 0);
+    // a sliced flat is normalised once all slices are in place (oss_comm_allgather_master): the mean is over the whole frame
+    if (mb.kind == OSS_MASTER_FLAT && !mb.sliced) { int rc = normalise_flat(c); if (rc) return rc; }
+    mb.kind = -1;
+    return OSS_OK;
+}
+
+// ---- masters ---------------------------------------------------------------------------
+int oss_build_master(oss_ctx *c, int kind, const void *const *frames, int n, int mem)
+{
+    if (!c) return OSS_E_ARG;
+    if (kind < 0 || kind > 3 || n < 1 || !frames) return fail(c, OSS_E_ARG, "bad master arguments");
+    int rc = oss_master_begin(c, kind, n, 0, 0);
+    if (!rc) rc = oss_master_add(c, frames, n, mem);
+    if (!rc) rc = oss_master_end(c);
+    return rc;
 }
 
 int oss_set_master(oss_ctx *c, int kind, const float *data, int mem)
@@ -1064,7 +1228,7 @@ int oss_add_lights(oss_ctx *c, const void *const *frames, int n, int mem)
             if (busy) { int r = flush_warps(c, c->pending_warps.size() - 1, 1, nullptr); if (r) return r; }
         }
         CK(cudaStreamWaitEvent(c->stream, c->pipes[c->cur].warp_done, 0));
-        CK(cudaStreamWaitEvent(c->stream, c->ref_copied, 0)); // ... and the reference's detection tail has left pipeline 0
+        if (c->cur == 0) CK(cudaStreamWaitEvent(c->stream, c->ref_copied, 0)); // ... and the reference's detection tail has left pipeline 0
         FramePtrs fp{};
         int set;
         int r = stage_frames(c, frames + b0, nb, mem, &fp, &set);
@@ -1425,7 +1589,68 @@ int oss_comm_broadcast_master(oss_ctx *c, int kind, int root)
     return OSS_OK;
 }
 
-int oss_comm_broadcast_reference(oss_ctx *c, int root)
+// canonical row slice of rank r of n: starts on multiples of 16 rows
+static void master_slice(int H, int r, int n, int *row0, int *rows)
+{
+    auto start = [&](int k) { return k <= 0 ? 0 : (k >= n ? H : (int)(((long long)H * k / n) & ~15ll)); };
+    *row0 = start(r);
+    *rows = start(r + 1) - start(r);
+}
+
+int oss_comm_master_slice(oss_ctx *c, int *row0, int *rows)
+{
+    NEED_GEOM();
+    int a = 0, b = c->g.H;
+    if (c->comm && c->nranks > 1) master_slice(c->g.H, c->rank, c->nranks, &a, &b);
+    if (row0) *row0 = a;
+    if (rows) *rows = b;
+    return OSS_OK;
+}
+
+// Every rank has built ITS row slice of master `kind` (oss_master_begin with oss_comm_master_slice's rows ... oss_master_end):
+// the slices are exchanged in place (one broadcast per slice, grouped) on the comm stream, beside whatever the bulk stream
+// does next (the next master's slice, the reference); a flat is then normalised by the mean of its channel 0 over the
+// whole frame, by every rank alike.  Per-pixel arithmetic and its order are those of the single-GPU build: the masters are
+// bit-identical on every rank and to the 1-GPU ones.  Calibration kernels wait for it on the device.
+int oss_comm_allgather_master(oss_ctx *c, int kind)
+{
+    NEED_GEOM();
+    if (!c->comm) return fail(c, OSS_E_ARG, "oss_comm_init has not been called");
+    if (kind < 0 || kind > 3 || !c->master[kind]) return fail(c, OSS_E_ARG, "master %d has not been built on this rank", kind);
+    int row0, rows;
+    master_slice(c->g.H, c->rank, c->nranks, &row0, &rows);
+    if (c->nranks > 1 && (c->slice_row0[kind] != row0 || c->slice_rows[kind] != rows))
+        return fail(c, OSS_E_ARG, "master %d was not built over this rank's slice [%d, %d)", kind, row0, row0 + rows);
+    { int rc = ensure_comm_stream(c); if (rc) return rc; }
+    CK(cudaEventRecord(c->comm_fork, c->bulk)); // behind the kernels that wrote this rank's slice
+    CK(cudaStreamWaitEvent(c->comm_stream, c->comm_fork, 0));
+    const size_t row_floats = (size_t)c->g.W * c->g.C;
+    if (c->nranks > 1) {
+        NK(g_nccl.GroupStart());
+        for (int r = 0; r < c->nranks; r++) {
+            int a, n;
+            master_slice(c->g.H, r, c->nranks, &a, &n);
+            if (n <= 0) continue;
+            float *p = c->master[kind] + (size_t)a * row_floats;
+            NK(g_nccl.Broadcast(p, p, (size_t)n * row_floats, ncclFloat32, r, c->comm, c->comm_stream));
+        }
+        NK(g_nccl.GroupEnd());
+    }
+    if (kind == OSS_MASTER_FLAT) {
+        cudaStream_t saved = c->stream;
+        c->stream = c->comm_stream;
+        int rc = normalise_flat(c);
+        c->stream = saved;
+        if (rc) return rc;
+    }
+    c->slice_rows[kind] = 0; // whole again
+    CK(cudaEventRecord(c->masters_ready, c->comm_stream));
+    // later slices of other masters read this one's OWN slice only (bias / dark-flat rows of the same range), which the
+    // exchange does not write; kernels that need the whole master wait for masters_ready
+    return OSS_OK;
+}
+
+int oss_comm_broadcast_reference(oss_ctx *c, int root, int threshold)
 {
     NEED_GEOM();
     if (!c->comm) return fail(c, OSS_E_ARG, "oss_comm_init has not been called");
@@ -1435,24 +1660,27 @@ int oss_comm_broadcast_reference(oss_ctx *c, int root)
         // the root does not wait on the host: the broadcasts are ordered on the device behind the reference's alignment
         // data (its detection tail may still be running), and its own lights can be queued right away
         if (!c->has_ref) return fail(c, OSS_E_ARG, "root has no reference");
+        if (c->threshold != threshold) return fail(c, OSS_E_ARG, "threshold %d differs from the reference's (%d)", threshold, c->threshold);
         CK(cudaStreamWaitEvent(c->comm_stream, c->ref_ready, 0));
     } else {
-        cudaError_t e = sync_all(c);
+        // neither do the others: they reset their stack (master exchanges in flight keep running), queue the receive and
+        // go on to their lights; the alignment kernels wait for ref_ready on the device.  The threshold comes from the
+        // caller (every rank has the same command line), so nothing has to be read back.
+        cudaError_t e = sync_all(c, false);
         if (e != cudaSuccess) return fail(c, OSS_E_CUDA, "stream sync failed: %s", cudaGetErrorString(e));
         select_pipe(c, 0);
         int rc = oss_reset_stack(c);
         if (rc) return rc;
     }
     int *xy_ref = c->pipes[0].d_xy + c->slots * 2 * OSS_NOBJS, *nxy_ref = c->pipes[0].d_nxy + c->slots;
-    int *d_th = c->d_valid + 2;
-    if (is_root) CK(cudaMemcpyAsync(d_th, &c->threshold, sizeof(int), cudaMemcpyHostToDevice, c->comm_stream));
+    NK(g_nccl.GroupStart());
     NK(g_nccl.Broadcast(c->d_ref, c->d_ref, sizeof(RefTriangles), ncclUint8, root, c->comm, c->comm_stream));
     NK(g_nccl.Broadcast(xy_ref, xy_ref, 2 * OSS_NOBJS, ncclInt32, root, c->comm, c->comm_stream));
     NK(g_nccl.Broadcast(nxy_ref, nxy_ref, 1, ncclInt32, root, c->comm, c->comm_stream));
-    NK(g_nccl.Broadcast(d_th, d_th, 1, ncclInt32, root, c->comm, c->comm_stream));
+    NK(g_nccl.GroupEnd());
     if (!is_root) {
-        CK(cudaMemcpyAsync(&c->threshold, d_th, sizeof(int), cudaMemcpyDeviceToHost, c->comm_stream));
-        CK(cudaStreamSynchronize(c->comm_stream)); // masters (if broadcast one by one) and the reference have arrived
+        CK(cudaEventRecord(c->ref_ready, c->comm_stream));
+        c->threshold = threshold;
         c->has_ref = true;
     }
     c->ref_in_sum = is_root; // imagestacker.cpp:287,304: the reference is counted once
@@ -1493,13 +1721,14 @@ int oss_comm_reduce(oss_ctx *c, int root)
             if (rc) return rc;
         }
     }
-    // the valid count: every alignment kernel has finished once the chain streams are drained
-    cudaError_t e = sync_all(c, false);
-    if (e != cudaSuccess) return fail(c, OSS_E_CUDA, "stream sync failed: %s", cudaGetErrorString(e));
-    select_pipe(c, 0);
+    // the valid count rides behind the last band: every alignment kernel (they bump d_valid) has finished before the last
+    // batch's warp starts (it waits for detect_done), and the last band's reduce is ordered behind that warp — no host wait
+    CK(cudaEventRecord(c->comm_fork, c->bulk));
+    CK(cudaStreamWaitEvent(c->comm_stream, c->comm_fork, 0));
+    for (int p = 0; p < c->npipes; p++) // (a stack without any light: the chain streams may still hold the reference)
+        if (c->pipes[p].detect_done) CK(cudaStreamWaitEvent(c->comm_stream, c->pipes[p].detect_done, 0));
     NK(g_nccl.Reduce(c->d_valid, c->d_valid, 1, ncclInt32, ncclSum, root, c->comm, c->comm_stream));
-    CK(cudaStreamSynchronize(c->comm_stream));
-    return OSS_OK;
+    return OSS_OK; // oss_finish (root) / oss_sync (others) drain the comm stream
 }
 
 // ---- device timer + synthetic frames (bench utilities) ---------------------------------
@@ -1507,6 +1736,21 @@ int oss_set_pipelines(oss_ctx *c, int n)
 {
     if (!c || n < 1 || n > OSS_MAX_PIPES) return fail(c, OSS_E_ARG, "pipelines must be 1..%d", OSS_MAX_PIPES);
     c->want_pipes = n; // takes effect at the next oss_set_geometry
+    return OSS_OK;
+}
+
+int oss_set_sm_split(oss_ctx *c, int fp_sms)
+{
+    if (!c || fp_sms < 0) return fail(c, OSS_E_ARG, "SM split must be >= 0");
+    c->split_fp = fp_sms; // takes effect at the next oss_set_geometry
+    return OSS_OK;
+}
+
+int oss_get_sm_split(oss_ctx *c, int *fp_sms, int *hbm_sms)
+{
+    if (!c) return OSS_E_ARG;
+    if (fp_sms) *fp_sms = c->split_fp_got;
+    if (hbm_sms) *hbm_sms = c->split_hbm_got;
     return OSS_OK;
 }
 

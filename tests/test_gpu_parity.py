@@ -85,6 +85,34 @@ def test_masters_and_calibration(eng, w, h, c, dt):
     assert np.array_equal(bits(eng.debug_plane(0)), bits(conv(light)))
 
 
+def test_masters_in_pieces_and_row_slices(eng):
+    """oss_master_begin / add / end: (1) the whole master from chunks of frames equals oss_build_master's (the accumulation
+    order is the frame order either way); (2) built as row slices [0, a) and [a, H) one after the other — what the ranks of
+    a multi-GPU job do side by side — every pixel is the oracle's, for bias and for a dark that subtracts the bias slice."""
+    w, h, c = 333, 200, 3
+    rng = np.random.default_rng(12)
+    eng.set_geometry(w, h, c, np.uint16, 3)
+    bias = [rng.integers(300, 900, (h, w, c)).astype(np.uint16) for _ in range(4)]
+    dark = [rng.integers(900, 3000, (h, w, c)).astype(np.uint16) for _ in range(7)]
+    o_bias = oracle.stack_mean([oracle.u16_to_f32(f) for f in bias])
+    o_dark = oracle.stack_mean([oracle.u16_to_f32(f) for f in dark], o_bias)
+    eng.build_master_slice(B.BIAS, bias, 0, 0, chunk=3)          # 3 + 1 frames
+    eng.build_master_slice(B.DARK, dark, 0, 0, chunk=2)          # 2 + 2 + 2 + 1
+    assert np.array_equal(bits(eng.get_master(B.BIAS)), bits(o_bias))
+    assert np.array_equal(bits(eng.get_master(B.DARK)), bits(o_dark))
+    eng.clear_masters()
+    for row0, rows in ((0, 112), (112, h - 112)):
+        eng.build_master_slice(B.BIAS, bias, row0, rows)
+    for row0, rows in ((112, h - 112), (0, 112)):
+        eng.build_master_slice(B.DARK, dark, row0, rows, chunk=4)
+    assert np.array_equal(bits(eng.get_master(B.BIAS)), bits(o_bias))
+    assert np.array_equal(bits(eng.get_master(B.DARK)), bits(o_dark))
+    with pytest.raises(ob.OssError) as e:
+        eng.build_master_slice(B.BIAS, bias, 100, 50)            # a slice must start on a multiple of 16 rows
+    assert e.value.status == -2
+    eng.clear_masters()
+
+
 # ------------------------------------------------------------------------------- K2 / K3
 # odd sizes, strips / segments / steps that do not divide, a tall frame (several row segments, folded reflections at both
 # ends), frames smaller than one strip or one step, and the smallest geometry the engine takes (one low-res pixel)

@@ -26,7 +26,9 @@ def free_port():
     return p
 
 
-def dataset():
+def dataset(full_cal=False):
+    if full_cal:
+        return synth.dataset(W, H, 5, 1, nstars=120, ndarks=2, nflats=3, nbias=2, seed=1234)
     return synth.dataset(W, H, 5, 1, nstars=120, ndarks=2, seed=1234)
 
 
@@ -89,18 +91,27 @@ def test_two_gloo_ranks_reproduce_the_single_process_stack():
         assert np.max(np.abs(out["image"] - want["image"])) <= 1e-6
 
 
-def _nccl_worker(rank, world, port, out):
+def _nccl_worker(rank, world, port, out, shard_masters=True, full_cal=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     import openskystacker_b200 as ob
     from openskystacker_b200 import binding as B
     from openskystacker_b200.distributed import init_comm, sharded_stack
-    ds = dataset()
+    ds = dataset(full_cal)
     eng = ob.Engine(rank)
     eng.set_geometry(W, H, 1, np.uint16, 2)
     init_comm(eng, dist)
-    img, tv = sharded_stack(eng, dist, ds["ref"], ds["lights"], 20, {B.DARK: ds["darks"]})
+    calib = {B.DARK: ds["darks"]}
+    if full_cal:
+        calib.update({B.BIAS: ds["bias"], B.FLAT: ds["flats"]})
+    img, tv = sharded_stack(eng, dist, ds["ref"], ds["lights"], 20, calib, shard_masters=shard_masters)
+    dark = eng.get_master(B.FLAT if full_cal else B.DARK)
+    darks = [None] * world
+    dist.all_gather_object(darks, dark.tobytes())
+    if rank == 0:
+        out["darks_identical"] = all(d == darks[0] for d in darks)
+        out["dark"] = dark
     reps = [(r.nstars, r.k, r.err) for r in eng.reports()]
     gathered = [None] * world
     dist.all_gather_object(gathered, reps)
@@ -111,16 +122,20 @@ def _nccl_worker(rank, world, port, out):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("world", [2, 4])
-def test_nccl_ranks_match_single_gpu_and_oracle(world):
+@pytest.mark.parametrize("world,shard_masters,full_cal", [(2, True, False), (2, False, False), (2, True, True), (4, True, True)])
+def test_nccl_ranks_match_single_gpu_and_oracle(world, shard_masters, full_cal):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs (run with gpurun --gpus {world})")
-    ds = dataset()
-    want = oracle.stack(ds["ref"], ds["lights"], 20, dark_frames=ds["darks"])
+    ds = dataset(full_cal)
+    want = oracle.stack(ds["ref"], ds["lights"], 20, ds["bias"] or None, ds["darks"], None, ds["flats"] or None)
     with mp.Manager() as m:
         out = m.dict()
-        mp.spawn(_nccl_worker, args=(world, free_port(), out), nprocs=world, join=True)
+        mp.spawn(_nccl_worker, args=(world, free_port(), out, shard_masters, full_cal), nprocs=world, join=True)
         assert out["valid"] == want["total_valid"]
+        # masters built in row slices + all-gather (or built on the root + broadcast): the same bits on every rank and in the
+        # oracle — for the flat that includes the mean of channel 0 over the WHOLE frame, taken after the exchange
+        o_master = want["masters"]["flat" if full_cal else "dark"]
+        assert out["darks_identical"] and np.array_equal(out["dark"].view(np.uint32), o_master.view(np.uint32))
         assert np.max(np.abs(out["image"] - want["image"])) <= 1e-6
         per_rank = out["reports"]
         for r in range(world):
