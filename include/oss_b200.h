@@ -165,6 +165,10 @@ OSS_API int oss_clear_masters(oss_ctx *ctx);
 OSS_API int oss_set_reference(oss_ctx *ctx, const void *frame, int mem, int threshold);
 OSS_API int oss_add_lights(oss_ctx *ctx, const void *const *frames, int n, int mem);
 OSS_API int oss_sync(oss_ctx *ctx);
+/* Host pipelining: returns when the OSS_MEM_HOST frames of all oss_add_lights calls except the `keep_recent` most recent
+ * ones have been copied to the device, i.e. their buffers may be refilled (the worker threads of processConcurrent,
+ * util.cpp:738-751, decode the next frames meanwhile) — without waiting for the GPU work on them like oss_sync does. */
+OSS_API int oss_wait_host_frames(oss_ctx *ctx, int keep_recent);
 OSS_API int oss_finish(oss_ctx *ctx, float *out_host, int *total_valid);
 OSS_API int oss_reset_stack(oss_ctx *ctx); /* forget reference + lights, keep masters */
 

@@ -72,6 +72,7 @@ _SIGS = {
     "oss_set_reference": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "oss_add_lights": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_int]),
     "oss_sync": (C.c_int, [C.c_void_p]),
+    "oss_wait_host_frames": (C.c_int, [C.c_void_p, C.c_int]),
     "oss_finish": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]),
     "oss_reset_stack": (C.c_int, [C.c_void_p]),
     "oss_num_reports": (C.c_int, [C.c_void_p]),
@@ -242,6 +243,9 @@ class Engine:
 
     def sync(self):
         self._ck(self._L.oss_sync(self._h))
+
+    def wait_host_frames(self, keep_recent=0):
+        self._ck(self._L.oss_wait_host_frames(self._h, keep_recent))
 
     def finish(self, want_image=True):
         out = np.empty(self._shape(), np.float32) if want_image else None

@@ -97,6 +97,11 @@ struct oss_ctx {
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     Pipe pipes[OSS_MAX_PIPES];
     int npipes = 3, want_pipes = 3, cur = 0;
+    // host-frame tickets: one event per oss_add_lights call with OSS_MEM_HOST frames, completed when the call's frames have
+    // been copied to the device (oss_wait_host_frames)
+    cudaStream_t ticket_stream = nullptr;
+    cudaEvent_t tickets[16] = {};
+    long long ticket_count = 0;
     struct MasterBuild { int kind = -1, n_total = 0, added = 0, row0 = 0, rows = 0; bool sliced = false; } mb;
     int slice_row0[4] = {0, 0, 0, 0}, slice_rows[4] = {0, 0, 0, 0}; // rows of each master this rank built last (0 rows: whole)
     int cap_one_in = 16;                 // detection work space: P / cap_one_in candidate pixels per frame
@@ -490,6 +495,8 @@ void oss_destroy(oss_ctx *c)
     for (auto e : c->event_pool) cudaEventDestroy(e);
     for (int p = 0; p < OSS_MAX_PIPES; p++) { if (c->pipes[p].copy_stream) cudaStreamDestroy(c->pipes[p].copy_stream); if (c->pipes[p].chain_stream) cudaStreamDestroy(c->pipes[p].chain_stream); }
     split_teardown(c);
+    for (auto &t : c->tickets) if (t) cudaEventDestroy(t);
+    if (c->ticket_stream) cudaStreamDestroy(c->ticket_stream);
     if (c->bulk) cudaStreamDestroy(c->bulk);
     if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
     if (c->comm_fork) cudaEventDestroy(c->comm_fork);
@@ -1220,6 +1227,7 @@ int oss_add_lights(oss_ctx *c, const void *const *frames, int n, int mem)
     // Take the next pipeline for the frames [b0, b0 + nb): wait until its previous batch has been warped, stage the frames,
     // calibrate them (bulk stream) and queue the low-res grid behind that (chain stream).
     struct LightBatch { int pipe = -1, nb = 0; };
+    bool host_frames = false;
     auto start_batch = [&](int b0, int nb, LightBatch *out) -> int {
         select_pipe(c, (int)(c->light_batches++ % c->npipes));
         for (bool busy = true; busy;) { // its pending warp has to be queued before the calibrated planes are overwritten
@@ -1232,6 +1240,11 @@ int oss_add_lights(oss_ctx *c, const void *const *frames, int n, int mem)
         FramePtrs fp{};
         int set;
         int r = stage_frames(c, frames + b0, nb, mem, &fp, &set);
+        if (!r && set >= 0) {
+            if (!c->ticket_stream) CK(cudaStreamCreateWithFlags(&c->ticket_stream, cudaStreamNonBlocking));
+            CK(cudaStreamWaitEvent(c->ticket_stream, c->copy_done[set], 0));
+            host_frames = true;
+        }
         if (!r) r = detect_calibrate(c, fp, nb, true, set);
         if (!r) r = detect_lowres(c, nb);
         out->pipe = c->cur;
@@ -1276,6 +1289,26 @@ int oss_add_lights(oss_ctx *c, const void *const *frames, int n, int mem)
         c->nlights += nb;
         cur = nxt; // pipe < 0: the next batch (if any) has not been started yet
     }
+    if (host_frames) {
+        cudaEvent_t &t = c->tickets[c->ticket_count % 16];
+        if (!t) CK(cudaEventCreateWithFlags(&t, cudaEventDisableTiming));
+        CK(cudaEventRecord(t, c->ticket_stream));
+        c->ticket_count++;
+    }
+    return OSS_OK;
+}
+
+// Blocks until the OSS_MEM_HOST frames of every oss_add_lights call except the `keep_recent` most recent ones have been copied
+// to the device: those host buffers may be overwritten (the decode of the next batch) while the GPU is still working on
+// them and the copies of the most recent calls are still in flight.
+int oss_wait_host_frames(oss_ctx *c, int keep_recent)
+{
+    if (!c || keep_recent < 0) return OSS_E_ARG;
+    const long long idx = c->ticket_count - 1 - keep_recent;
+    if (idx < 0) return OSS_OK;
+    CK(cudaSetDevice(c->device));
+    // (a slot of the ring that has been re-used holds a LATER ticket of the same in-order stream: waiting for it is safe)
+    CK(cudaEventSynchronize(c->tickets[idx % 16]));
     return OSS_OK;
 }
 
