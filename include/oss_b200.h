@@ -91,6 +91,7 @@ OSS_API void oss_destroy(oss_ctx *ctx);
 OSS_API const char *oss_last_error(const oss_ctx *ctx);
 OSS_API const char *oss_status_string(int status); /* the reference's processingError texts */
 OSS_API const char *oss_version(void);
+OSS_API int oss_device_count(void); /* CUDA devices visible to this process (0: none, every other call fails with OSS_E_CUDA) */
 
 /* Pinned host memory for decoders to write into (optional; any host pointer works). */
 OSS_API void *oss_host_alloc(size_t bytes);

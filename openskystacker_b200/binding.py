@@ -57,6 +57,7 @@ _SIGS = {
     "oss_last_error": (C.c_char_p, [C.c_void_p]),
     "oss_status_string": (C.c_char_p, [C.c_int]),
     "oss_version": (C.c_char_p, []),
+    "oss_device_count": (C.c_int, []),
     "oss_host_alloc": (C.c_void_p, [C.c_size_t]),
     "oss_host_free": (None, [C.c_void_p]),
     "oss_device_alloc": (C.c_void_p, [C.c_void_p, C.c_size_t]),

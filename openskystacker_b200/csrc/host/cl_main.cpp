@@ -1,6 +1,8 @@
 // openskystacker-cl without Qt: same flags, same stdout as cl/cl.cpp:63-225.
 //   -f <list.json>  -s  -o <output>  -t <threshold 1-100, default 20>  -j <threads, default 1>  -v
-// Extra (not in the reference): --device N.
+// Extra (not in the reference): --device N, --devices a,b,c | all (the lights are sharded over these GPUs, light k -> GPU k % N like
+// the reference's -j workers, util.cpp:738; masters in row slices, one NCCL reduce), --mono16 (write a single-channel
+// result as 16-bit like the GUI does, openskystacker/ui/mainwindow.cpp:91-101).
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -23,15 +25,20 @@ static void usage(int code)
            "  -t <threshold>  Star detection threshold (1-100). Default: 20\n"
            "  -j <threads>    Number of processing threads. Default: 1\n"
            "  -v, --verbose   Verbose output.\n"
-           "  --device <n>    CUDA device to run on. Default: 0\n");
+           "  --device <n>    CUDA device to run on. Default: 0\n"
+           "  --devices <l>   Comma-separated CUDA devices (or 'all') to shard the\n"
+           "                  light frames over.\n"
+           "  --mono16        Write a single-channel result as a 16-bit TIFF, like\n"
+           "                  the GUI does.\n");
     exit(code);
 }
 
 int main(int argc, char **argv)
 {
     std::string listFile, output, thresholdArg = "20", threadsArg = "1";
-    bool detect = false, verbose = false, haveList = false, haveOutput = false;
+    bool detect = false, verbose = false, haveList = false, haveOutput = false, mono16 = false;
     int device = 0;
+    std::string devicesArg;
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i];
         auto value = [&]() -> std::string { if (i + 1 >= argc) usage(1); return argv[++i]; };
@@ -43,6 +50,8 @@ int main(int argc, char **argv)
         else if (a == "-j") threadsArg = value();
         else if (a == "-v" || a == "--verbose") verbose = true;
         else if (a == "--device") device = atoi(value().c_str());
+        else if (a == "--devices") devicesArg = value();
+        else if (a == "--mono16") mono16 = true;
         else { printf("Unknown option '%s'.\n", a.c_str()); usage(1); }
     }
     if (!haveList) { printf("Error: Must specify an image list\n\n"); usage(1); }
@@ -56,7 +65,25 @@ int main(int argc, char **argv)
     std::vector<ImageRecord *> records = loadImageList(listFile, &err);
     if (err) { printf("Error %d: Couldn't load image list\n", err); return 1; }
 
-    ImageStacker stacker(device);
+    std::vector<int> devices;
+    if (devicesArg == "all") {
+        int n = visibleDeviceCount();
+        for (int i = 0; i < n; i++) devices.push_back(i);
+    } else if (!devicesArg.empty()) {
+        size_t pos = 0;
+        while (pos <= devicesArg.size()) {
+            size_t comma = devicesArg.find(',', pos);
+            std::string tok = devicesArg.substr(pos, comma == std::string::npos ? std::string::npos : comma - pos);
+            char *e2 = nullptr;
+            long v = strtol(tok.c_str(), &e2, 10);
+            if (tok.empty() || *e2 || v < 0) { printf("Error: --devices takes a comma-separated list of device numbers or 'all'\n"); usage(1); }
+            devices.push_back((int)v);
+            if (comma == std::string::npos) break;
+            pos = comma + 1;
+        }
+    }
+    ImageStacker stacker(devices.empty() ? device : devices[0]);
+    if (!devices.empty()) stacker.setDevices(devices);
     std::string ref;
     std::vector<std::string> lights, darks, darkFlats, flats, bias;
     bool referenceSet = false;
@@ -116,7 +143,9 @@ int main(int argc, char **argv)
         printProgressBar(message, 100);
         printf("\n");
         std::string why;
-        if (!writeTiffF32(output, image.data.data(), image.width, image.height, image.channels, &why)) {
+        const bool ok = mono16 ? saveImageLikeGui(output, image, &why)
+                               : writeTiffF32(output, image.data.data(), image.width, image.height, image.channels, &why);
+        if (!ok) {
             printf("Error: Couldn't write resulting image\n");
             rc = 1;
             return;

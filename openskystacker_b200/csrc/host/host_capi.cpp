@@ -5,6 +5,7 @@
 
 #include "image_io.hpp"
 #include "imagelist.hpp"
+#include "imagestacker.hpp"
 
 using namespace openskystacker;
 
@@ -48,6 +49,16 @@ __attribute__((visibility("default"))) int oss_host_load_image_list(const char *
     }
     if (out && cap > 0) { strncpy(out, text.c_str(), cap - 1); out[cap - 1] = 0; }
     return err;
+}
+
+// the GUI's output path (mainwindow.cpp:91-101): single-channel float -> 16-bit TIFF, otherwise float32 TIFF
+__attribute__((visibility("default"))) int oss_host_save_like_gui(const char *path, const float *px, int w, int h, int c)
+{
+    Image img;
+    img.width = w; img.height = h; img.channels = c;
+    img.data.assign(px, px + (size_t)w * h * c);
+    std::string e;
+    return saveImageLikeGui(path, img, &e) ? 0 : -1;
 }
 
 __attribute__((visibility("default"))) void oss_host_time_string(int seconds, char *out, int cap)

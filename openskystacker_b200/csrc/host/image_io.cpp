@@ -1,5 +1,7 @@
 #include "image_io.hpp"
 
+#include <zlib.h>
+
 #include <cstdio>
 #include <cstring>
 #include <fstream>
@@ -106,7 +108,8 @@ bool describe(const Ifd &d, ImageInfo *info, std::string *err)
     else if (d.bps == 16 && d.format == 1) info->sample = SAMPLE_U16;
     else if (d.bps == 32 && d.format == 3) info->sample = SAMPLE_F32;
     else return fail(err, "unsupported TIFF sample format");
-    if (d.compression != 1 && d.compression != 5) return fail(err, "unsupported TIFF compression (only none / LZW)");
+    if (d.compression != 1 && d.compression != 5 && d.compression != 8 && d.compression != 32946)
+        return fail(err, "unsupported TIFF compression (only none / LZW / Deflate)");
     return true;
 }
 
@@ -201,6 +204,11 @@ bool decode(const Reader &r, const Ifd &d, const ImageInfo &info, void *dst, std
         if (d.compression == 5) {
             if (!lzwDecode(data, d.counts[s], &strip, want) || strip.size() < want) return fail(err, "corrupt LZW strip");
             data = strip.data();
+        } else if (d.compression == 8 || d.compression == 32946) { // Adobe / legacy Deflate: one zlib stream per strip
+            strip.resize(want);
+            uLongf got = (uLongf)want;
+            if (uncompress(strip.data(), &got, data, (uLong)d.counts[s]) != Z_OK || got < want) return fail(err, "corrupt Deflate strip");
+            data = strip.data();
         } else if (d.counts[s] < want) return fail(err, "short TIFF strip");
         if (d.predictor == 2) { // horizontal differencing, per sample, in the file's byte order
             if (data != strip.data()) { strip.assign(data, data + want); data = strip.data(); }
@@ -235,7 +243,7 @@ bool open(const std::string &path, size_t limit, Reader *r, Ifd *d, ImageInfo *i
     if (r->buf.size() < 8) return fail(err, path + ": not a TIFF file");
     if (r->buf[0] == 'I' && r->buf[1] == 'I') r->big = false;
     else if (r->buf[0] == 'M' && r->buf[1] == 'M') r->big = true;
-    else return fail(err, path + ": not a TIFF file (only TIFF input is supported by this build)");
+    else return fail(err, path + ": not a TIFF, PNG or FITS file (JPEG and camera RAW decoding are not part of this build)");
     if (!parseIfd(*r, d, err)) {
         if (limit) { // directory at the end of the file: read it all
             if (!loadFile(path, &r->buf, 0, err)) return false;
@@ -293,6 +301,7 @@ bool writeTiff(const std::string &path, const T *px, int w, int h, int c, int fo
 bool probeImage(const std::string &path, ImageInfo *info, std::string *err)
 {
     if (isFitsFile(path)) return probeFits(path, info, err);
+    if (isPngFile(path)) return probePng(path, info, err);
     Reader r;
     Ifd d;
     return open(path, 1 << 16, &r, &d, info, err);
@@ -301,6 +310,7 @@ bool probeImage(const std::string &path, ImageInfo *info, std::string *err)
 bool readImageInto(const std::string &path, const ImageInfo &expect, void *dst, std::string *err)
 {
     if (isFitsFile(path)) return readFitsInto(path, &expect, nullptr, dst, nullptr, err);
+    if (isPngFile(path)) return readPngInto(path, &expect, nullptr, dst, nullptr, err);
     Reader r;
     Ifd d;
     ImageInfo info;
@@ -313,6 +323,7 @@ bool readImageInto(const std::string &path, const ImageInfo &expect, void *dst, 
 bool readImage(const std::string &path, ImageInfo *info, std::vector<uint8_t> *pixels, std::string *err)
 {
     if (isFitsFile(path)) return readFitsInto(path, nullptr, info, nullptr, pixels, err);
+    if (isPngFile(path)) return readPngInto(path, nullptr, info, nullptr, pixels, err);
     Reader r;
     Ifd d;
     if (!open(path, 0, &r, &d, info, err)) return false;

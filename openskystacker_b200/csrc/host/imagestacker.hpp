@@ -31,6 +31,13 @@ struct Star {
     float peak = 0, radius = 0, value = 0;
 };
 
+// MainWindow::finishedStacking (openskystacker/ui/mainwindow.cpp:91-101): a single-channel result is converted to 16 bits
+// (`image.convertTo(converted, CV_16U, 65535)`: round-half-even of v * 65535, saturated) before imwrite, anything else is
+// written as float32 — the GUI's output path (the CLI always writes float32, cl/cl.cpp:205).
+bool saveImageLikeGui(const std::string &path, const Image &image, std::string *err);
+// CUDA devices visible to this process (0 without a driver)
+int visibleDeviceCount();
+
 class ImageStackerPrivate;
 
 class ImageStacker {
@@ -41,6 +48,11 @@ public:
     ImageStacker &operator=(const ImageStacker &) = delete;
 
     bool cancel = false; // never read by process(), like the reference (imagestacker.cpp:248)
+
+    // not in the reference: the GPUs process() shards the lights over (light k -> devices[k % N], the reference's own
+    // split over its -j worker threads, util.cpp:738); default: the constructor's device alone
+    void setDevices(const std::vector<int> &devices);
+    std::vector<int> getDevices() const;
 
     // get/set — imagestacker.h:38-78
     std::string getRefImageFileName() const;
@@ -84,7 +96,7 @@ public:
 
     // not in the reference: the star list behind doneDetectingStars, and per-light outcomes
     std::vector<Star> getStars(const std::string &filename, int threshold);
-    struct LightReport { int nstars, matches, err; float M[6]; };
+    struct LightReport { int nstars, matches, err; float M[6]; int overflow; };
     std::vector<LightReport> getLightReports() const;
 
 private:

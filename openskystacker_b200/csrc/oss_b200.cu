@@ -414,7 +414,13 @@ static int split_setup(oss_ctx *c, int fp_sms)
 // ---- exported: lifetime ----------------------------------------------------------------
 extern "C" {
 
-const char *oss_version(void) { return "oss-b200 0.1 (sm_100a)"; }
+const char *oss_version(void) { return "oss-b200 0.2 (sm_100a)"; }
+
+int oss_device_count(void)
+{
+    int n = 0;
+    return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0;
+}
 
 const char *oss_status_string(int s)
 {
@@ -457,6 +463,7 @@ int oss_create(oss_ctx **out, int device)
     }
     if (const char *e = getenv("OSS_B200_PIPES")) c->want_pipes = atoi(e);
     if (const char *e = getenv("OSS_B200_SPLIT")) c->split_fp = atoi(e);
+    if (const char *e = getenv("OSS_B200_CAP_DIV")) { int v = atoi(e); if (v >= 1 && v <= 64) c->cap_one_in = v; } // default only
     c->stream = c->bulk;
     c->copy_stream = c->pipes[0].copy_stream;
     // constant tables
@@ -599,7 +606,6 @@ int oss_set_geometry(oss_ctx *c, int W, int H, int C, int sample, int slots)
     g.roi_w = (int)(W * 0.9); g.roi_h = (int)(H * 0.9);
     g.P = (long long)W * H;
     long long div = c->cap_one_in;
-    if (const char *e = getenv("OSS_B200_CAP_DIV")) div = atoll(e) > 0 ? atoll(e) : div;
     long long cap = g.P / div;
     if (cap < 65536) cap = g.P < 65536 ? g.P : 65536; // small frames: every pixel may be a candidate
     g.cap = (int)cap;

@@ -36,7 +36,8 @@ def read_tiff(L, path):
 
 
 @pytest.mark.parametrize("dtype,channels,compression", [(np.uint16, 3, 5), (np.uint16, 1, 5), (np.uint8, 3, 5),
-                                                        (np.uint16, 3, 1), (np.float32, 1, 1), (np.uint16, 3, 32773)])
+                                                        (np.uint16, 3, 1), (np.float32, 1, 1), (np.uint16, 3, 32773),
+                                                        (np.uint16, 3, 8), (np.uint16, 1, 32946), (np.float32, 3, 8)])
 def test_tiff_reader_matches_imread(host, tmp_path, dtype, channels, compression):
     rng = np.random.default_rng(channels + compression)
     shape = (57, 83) if channels == 1 else (57, 83, channels)
@@ -68,6 +69,80 @@ def test_float_tiff_writer_round_trips_through_cv2(host, tmp_path):
         back = cv2.imread(path, cv2.IMREAD_ANYDEPTH | cv2.IMREAD_ANYCOLOR)
         assert back.dtype == np.float32 and np.array_equal(back, img)
         assert np.array_equal(read_tiff(host, path), img)
+
+
+def test_png_reader_matches_imread(host, tmp_path):
+    """The reference's RGB_IMAGE branch is cv::imread(ANYDEPTH | ANYCOLOR) (util.cpp:291-294): 16-bit PNG is the other
+    lossless input besides TIFF.  Every colour type / depth cv2 or PIL can write, against cv2.imread on the same file."""
+    rng = np.random.default_rng(17)
+    h, w = 41, 67
+    ramp = np.linspace(0, 1, w)[None, :]
+
+    def img(dtype, ch):
+        top = np.iinfo(dtype).max
+        base = np.broadcast_to(ramp * top * 0.7, (h, w))
+        if ch > 1:
+            base = np.stack([base * g for g in (1.0, 0.8, 0.6, 0.9)[:ch]], 2)
+        return (base + rng.integers(0, 40, base.shape)).astype(dtype)
+    cases = {"g8": img(np.uint8, 1), "g16": img(np.uint16, 1), "rgb8": img(np.uint8, 3), "rgb16": img(np.uint16, 3),
+             "rgba8": img(np.uint8, 4), "rgba16": img(np.uint16, 4)}
+    for name, a in cases.items():
+        path = str(tmp_path / f"{name}.png")
+        assert cv2.imwrite(path, a, [cv2.IMWRITE_PNG_COMPRESSION, 6])
+        want = cv2.imread(path, cv2.IMREAD_ANYDEPTH | cv2.IMREAD_ANYCOLOR)
+        got = read_tiff(host, path)
+        assert got.dtype == want.dtype and got.shape == want.shape and np.array_equal(got, want), name
+    try:
+        from PIL import Image
+    except Exception:
+        return
+    # palette, 1-bit, grey + alpha: colour types cv2 does not write
+    rgb = cases["rgb8"][:, :, ::-1].copy()
+    pil = {"pal": Image.fromarray(rgb).quantize(37), "bit1": Image.fromarray((cases["g8"] > 90).astype(np.uint8) * 255).convert("1"),
+           "ga8": Image.fromarray(np.stack([cases["g8"], 255 - cases["g8"]], 2), "LA")}
+    for name, im in pil.items():
+        path = str(tmp_path / f"{name}.png")
+        im.save(path)
+        want = cv2.imread(path, cv2.IMREAD_ANYDEPTH | cv2.IMREAD_ANYCOLOR)
+        got = read_tiff(host, path)
+        assert got.dtype == want.dtype and got.shape == want.shape and np.array_equal(got, want), name
+    # Adam7: interlace a file by hand (zlib + the seven passes, filter 0) and read it back
+    import struct
+    import zlib
+    a = cases["rgb16"]
+    be = a[:, :, ::-1].astype(">u2")            # file order RGB, big-endian
+    raw = b""
+    for x0, y0, dx, dy in ((0, 0, 8, 8), (4, 0, 8, 8), (0, 4, 4, 8), (2, 0, 4, 4), (0, 2, 2, 4), (1, 0, 2, 2), (0, 1, 1, 2)):
+        sub = be[y0::dy, x0::dx]
+        if sub.size:
+            raw += b"".join(b"\0" + sub[r].tobytes() for r in range(sub.shape[0]))
+    def chunk(t, d):
+        return struct.pack(">I", len(d)) + t + d + struct.pack(">I", zlib.crc32(t + d) & 0xffffffff)
+    png = b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 16, 2, 0, 0, 1)) + \
+        chunk(b"IDAT", zlib.compress(raw)[:1000]) + chunk(b"IDAT", zlib.compress(raw)[1000:]) + chunk(b"IEND", b"")
+    path = str(tmp_path / "adam7.png")
+    open(path, "wb").write(png)
+    want = cv2.imread(path, cv2.IMREAD_ANYDEPTH | cv2.IMREAD_ANYCOLOR)
+    assert np.array_equal(want, a)              # cv2 agrees that this is the image
+    assert np.array_equal(read_tiff(host, path), a)
+
+
+def test_gui_output_path_writes_mono_as_16_bit(host, tmp_path):
+    """MainWindow::finishedStacking (openskystacker/ui/mainwindow.cpp:91-101): a single-channel stack goes through
+    convertTo(CV_16U, 65535) before imwrite, a colour one is written as float32."""
+    rng = np.random.default_rng(4)
+    mono = rng.random((33, 47), dtype=np.float32) * 1.2 - 0.1       # values below 0 and above 1 saturate
+    mono[0, :4] = [0.5 / 65535, 1.5 / 65535, 2.5 / 65535, np.nan]    # ties round to even; NaN -> 0
+    path = str(tmp_path / "m.tif")
+    assert host.oss_host_save_like_gui(path.encode(), C.c_void_p(mono.ctypes.data), 47, 33, 1) == 0
+    back = cv2.imread(path, cv2.IMREAD_ANYDEPTH | cv2.IMREAD_ANYCOLOR)
+    v = np.nan_to_num(mono * np.float32(65535.0), nan=0.0)
+    want = np.clip(np.rint(v), 0, 65535).astype(np.uint16)
+    assert back.dtype == np.uint16 and np.array_equal(back, want) and list(back[0, :3]) == [0, 2, 2]
+    rgb = rng.random((12, 9, 3), dtype=np.float32)
+    assert host.oss_host_save_like_gui(path.encode(), C.c_void_p(rgb.ctypes.data), 9, 12, 3) == 0
+    back = cv2.imread(path, cv2.IMREAD_ANYDEPTH | cv2.IMREAD_ANYCOLOR)
+    assert back.dtype == np.float32 and np.array_equal(back, rgb)
 
 
 def write_list(tmp_path, entries):
@@ -173,6 +248,79 @@ def test_cli_end_to_end_matches_oracle(host, tmp_path):
     r = subprocess.run([CLI, "-f", lst, "-s", "-t", "20"], capture_output=True, text=True)
     nref = len(oracle.get_stars(oracle.u16_to_f32(ds["ref"]), 20)[0])
     assert r.returncode == 0 and r.stdout.strip().splitlines()[-1] == str(nref)
+
+
+def _write_stack(tmp_path, ds, ext, put_frame):
+    entries = []
+
+    def put(name, frame, kind):
+        put_frame(str(tmp_path / (name + ext)), frame)
+        entries.append({"filename": name + ext, "type": kind, "checked": True})
+    put("ref", ds["ref"], "ref")
+    for i, f in enumerate(ds["lights"]):
+        put(f"light{i}", f, "light")
+    for i, f in enumerate(ds["darks"]):
+        put(f"dark{i}", f, "dark")
+    for i, f in enumerate(ds["flats"]):
+        put(f"flat{i}", f, "flat")
+    for i, f in enumerate(ds["bias"]):
+        put(f"bias{i}", f, "bias")
+    return write_list(tmp_path, entries)
+
+
+@pytest.mark.gpu
+def test_cli_many_png_lights_pipelined_mono16_and_capacity_retry(host, tmp_path):
+    """40 mono 16-bit PNG lights of 640x480 = 3 batches of 16 through the two pinned sets (decode of batch b + 1 overlaps copy
+    and compute of batch b, handed back by oss_wait_host_frames), 7 darks streamed 16 at a time through oss_master_add;
+    --mono16 writes the GUI's 16-bit file.  Then the same stack starting from a detection work space that is too small
+    (test hook OSS_STACKER_CAPACITY=64 at threshold 2): the facade must notice OSS_E_CAPACITY, enlarge and re-run — same file."""
+    w, h = 640, 480
+    ds = synth.dataset(w, h, 40, 1, nstars=80, ndarks=7, seed=77)
+    lst = _write_stack(tmp_path, ds, ".png", lambda p, f: cv2.imwrite(p, f))
+    want = oracle.stack(ds["ref"], ds["lights"], 20, dark_frames=ds["darks"])
+    out = str(tmp_path / "stack")
+    r = subprocess.run([CLI, "-f", lst, "-o", out, "-t", "20", "-j", "6"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    got = cv2.imread(out + ".tif", cv2.IMREAD_ANYDEPTH | cv2.IMREAD_ANYCOLOR)
+    assert got.dtype == np.float32 and np.array_equal(got.view(np.uint32), want["image"].view(np.uint32))
+    r = subprocess.run([CLI, "-f", lst, "-o", out + "16", "-t", "20", "-j", "2", "--mono16"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    got16 = cv2.imread(out + "16.tif", cv2.IMREAD_ANYDEPTH | cv2.IMREAD_ANYCOLOR)
+    assert got16.dtype == np.uint16 and np.array_equal(got16, np.clip(np.rint(want["image"] * np.float32(65535)), 0, 65535).astype(np.uint16))
+    # threshold 2 on this sparse field: 3 sigma -> ~0.2 % of the pixels, above 1/64 only with the hook ... use threshold 1 (6.7 %)
+    want1 = oracle.stack(ds["ref"], ds["lights"][:6], 1, dark_frames=ds["darks"])
+    lst1 = _write_stack(tmp_path, dict(ds, lights=ds["lights"][:6]), ".png", lambda p, f: cv2.imwrite(p, f))
+    env = dict(os.environ, OSS_STACKER_CAPACITY="64")
+    r = subprocess.run([CLI, "-f", lst1, "-o", out + "t1", "-t", "1", "-j", "2"], capture_output=True, text=True, env=env)
+    if want1["total_valid"] < 2:
+        assert r.returncode == 1 and "No images could be aligned" in r.stdout
+    else:
+        assert r.returncode == 0, r.stdout + r.stderr
+        got1 = cv2.imread(out + "t1.tif", cv2.IMREAD_ANYDEPTH | cv2.IMREAD_ANYCOLOR)
+        assert np.array_equal(got1.view(np.uint32), want1["image"].view(np.uint32))
+
+
+@pytest.mark.gpu
+def test_cli_shards_the_lights_over_two_gpus(host, tmp_path):
+    """openskystacker-cl --devices 0,1: one host thread per GPU, light k -> GPU k % 2 (util.cpp:738), masters built in row
+    slices + NVLink exchange, one NCCL reduce.  Against the oracle within float reassociation (1e-6); identical reports."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    w, h = 1000, 700
+    ds = synth.dataset(w, h, 21, 3, nstars=120, ndarks=3, nflats=3, nbias=2, seed=1234)
+    lst = _write_stack(tmp_path, ds, ".tif", lambda p, f: cv2.imwrite(p, f))
+    want = oracle.stack(ds["ref"], ds["lights"], 20, ds["bias"], ds["darks"], None, ds["flats"])
+    out = str(tmp_path / "stack2")
+    r = subprocess.run([CLI, "-f", lst, "-o", out, "-t", "20", "-j", "8", "--devices", "0,1", "-v"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    got = cv2.imread(out + ".tif", cv2.IMREAD_ANYDEPTH | cv2.IMREAD_ANYCOLOR)
+    assert got.shape == want["image"].shape and float(np.max(np.abs(got - want["image"]))) <= 1e-6
+    one = str(tmp_path / "stack1")
+    r = subprocess.run([CLI, "-f", lst, "-o", one, "-t", "20", "-j", "8", "--devices", "all"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    got_all = cv2.imread(one + ".tif", cv2.IMREAD_ANYDEPTH | cv2.IMREAD_ANYCOLOR)
+    assert float(np.max(np.abs(got_all - want["image"]))) <= 1e-6
 
 
 # ---- FITS (fitsToMat, libstacker/src/util.cpp:300-346) -----------------------------------------------------------------
