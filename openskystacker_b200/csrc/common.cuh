@@ -55,6 +55,7 @@ struct Workspace {
     float *cal;     // [slots][P*C]  calibrated frame
     float *gray;    // [slots][P]    luminance (aliases cal when C == 1)
     float *stars;   // [slots][P]    gray - sky
+    float *rf;      // [slots][P]    row-filtered upsampled sky (between k_sky_rows and k_sky_cols)
     float *lo;      // [slots][lw*lh]
     float *med;     // [slots][lw*lh]
     float *segmax;  // [slots][H*nseg]

@@ -143,6 +143,11 @@ __device__ __forceinline__ f32x2_t add2(f32x2_t a, f32x2_t b)
 }
 __device__ __forceinline__ void unpack2(f32x2_t v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
 
+__device__ __forceinline__ void cp_async16_sky(void *smem, const void *gmem)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+
 #ifndef SKY_CTAS
 #define SKY_CTAS (512 / SKY_NT)      // 16 warps per SM at 128 registers
 #endif
@@ -192,13 +197,13 @@ __device__ __forceinline__ void reflect_range(int va, int vb, int n, int &lo, in
 // MODE 0: block inside the image and inside the statistics ROI; 1: inside the image, outside the ROI;
 // 2: anything else (per-pixel tests).
 template <int MODE>
-__device__ __forceinline__ void sky_column_pass(const SkySmem &sm, const float *__restrict__ gtile, int ring_row0, int x0, int yblk,
-                                                int tid, float *__restrict__ S, float *__restrict__ SM, int nseg, const Geom &g,
-                                                double &sum, double &sq)
+__device__ __forceinline__ void sky_column_pass(const float *__restrict__ ring, const float *__restrict__ gtile, int ring_row0, int x0,
+                                                int yblk, int tid, float *__restrict__ S, float *__restrict__ SM, int nseg,
+                                                const Geom &g, double &sum, double &sq)
 {
     const int gy = tid >> 5, cp = tid & 31, lane = cp;
     const int x = x0 + 2 * cp, y = yblk + 4 * gy;
-    const f32x2_t *q = (const f32x2_t *)(sm.rf + (ring_row0 + 4 * gy + 1) * SKY_W + 2 * cp);
+    const f32x2_t *q = (const f32x2_t *)(ring + (ring_row0 + 4 * gy + 1) * SKY_W + 2 * cp);
     f32x2_t w[34];
 #pragma unroll
     for (int j = 0; j < 34; j++) w[j] = q[j * (SKY_W / 2)];
@@ -426,9 +431,9 @@ k_sky_sub_stats(const float *__restrict__ gray, long long strideGray, const floa
             const int ring_row0 = (slot >= SKY_LA ? slot - SKY_LA : slot + SKY_NSLOT - SKY_LA) * SKY_H; // block b - SKY_LA
             const float *gtile = sm.gray;
             const int mode = sm.mode[b - SKY_LA];
-            if (mode == 0) sky_column_pass<0>(sm, gtile, ring_row0, x0, yblk, tid, S, SM, nseg, g, sum, sq);
-            else if (mode == 1) sky_column_pass<1>(sm, gtile, ring_row0, x0, yblk, tid, S, SM, nseg, g, sum, sq);
-            else sky_column_pass<2>(sm, gtile, ring_row0, x0, yblk, tid, S, SM, nseg, g, sum, sq);
+            if (mode == 0) sky_column_pass<0>(sm.rf, gtile, ring_row0, x0, yblk, tid, S, SM, nseg, g, sum, sq);
+            else if (mode == 1) sky_column_pass<1>(sm.rf, gtile, ring_row0, x0, yblk, tid, S, SM, nseg, g, sum, sq);
+            else sky_column_pass<2>(sm.rf, gtile, ring_row0, x0, yblk, tid, S, SM, nseg, g, sum, sq);
         }
         if (b < bmax) {
             up_pass(b + 1);
@@ -437,6 +442,313 @@ k_sky_sub_stats(const float *__restrict__ gray, long long strideGray, const floa
         slot = slot == SKY_NSLOT - 1 ? 0 : slot + 1;
     }
     // block reduction of the fp64 partial sums, fixed order
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    }
+    if (lane == 0) { sm.red[0][wid] = sum; sm.red[1][wid] = sq; }
+    __syncthreads();
+    if (tid == 0) {
+        double a = 0.0, b = 0.0;
+        for (int w = 0; w < SKY_NT / 32; w++) { a += sm.red[0][w]; b += sm.red[1][w]; }
+        const long long blk = (long long)blockIdx.y * gridDim.x + blockIdx.x;
+        partials[f * stridePart + 2 * blk] = a;
+        partials[f * stridePart + 2 * blk + 1] = b;
+    }
+}
+
+// =======================================================================================
+// K3 split in two (alternative to k_sky_sub_stats, OSS_B200_SKY_SPLIT=1): the same arithmetic, cut where the data flow is narrowest.
+//   k_sky_rows   upsample + 31-tap ROW filter of every image row -> `rf` plane in HBM (4 B/px written).  No vertical
+//                dependency at all: a CTA marches down a 64-column strip, one barrier per 16-row step (the upsampled
+//                block is double-buffered), FP32-pipe bound (61 + 4.4 non-fusable ops per pixel).
+//   k_sky_cols   COLUMN filter + subtraction + statistics + segment maxima: a CTA marches down a strip with a ring of rf
+//                rows that cp.async fills from HBM one block ahead (rows beyond the frame are BORDER_REFLECT_101 of rows the
+//                first kernel wrote: filtering a mirrored row gives the mirrored row's result), HBM bound: rf read 4 B/px +
+//                gray read 4 + stars written 4.
+// The fused kernel spends its time in phases (up, row, column, two barriers per step) whose different instruction mixes
+// four warps per scheduler cannot overlap well: 59 % FP32-pipe utilisation, while the row filter ALONE reaches 85 %
+// (tools/ubench/rowpass.cu).  Split, each kernel has one dense phase; the price is 8 B/px of extra HBM traffic that
+// neither kernel's bound notices.
+struct SkyRowsSmem {
+    float2 up2[2][(SKY_H / 2) * SKY_ULD];    // double-buffered upsampled block (row pairs interleaved)
+    float hr[SKY_HRS * SKY_HLD];
+    float lr[SKY_LRR * SKY_LRC];
+    ResizeTap tcol[SKY_UW];
+    SkyRowTap trow[4][SKY_H];
+    int blk_lo[4], blk_hi[4];
+};
+constexpr int kSkyRowsSmemBytes = (int)sizeof(SkyRowsSmem);
+
+__global__ void __launch_bounds__(SKY_NT, 4)
+k_sky_rows(const float *__restrict__ med, long long strideLo, int lw, const ResizeTap *__restrict__ ux,
+           const ResizeTap *__restrict__ uy, float *__restrict__ rf, long long strideRf, Geom g, int seg_h)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SkyRowsSmem &sm = *(SkyRowsSmem *)smem_raw;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int x0 = blockIdx.x * SKY_W, ya = blockIdx.y * seg_h, yb = min(ya + seg_h, g.H), f = blockIdx.z;
+    const int nb = (yb - ya + SKY_H - 1) / SKY_H; // blocks 0..nb-1; block j = rows ya + j*SKY_H ...
+    const float *L = med + f * strideLo;
+    float *R = rf + f * strideRf;
+
+    auto fetch_row_tap = [&](int bb) { return uy[min(ya + SKY_H * bb + (lane & (SKY_H - 1)), g.H - 1)]; };
+    auto publish_row_taps = [&](int bb, const ResizeTap &t) {
+        SkyRowTap r;
+        r.o0 = (t.i0 & (SKY_HRS - 1)) * SKY_HLD; r.o1 = (t.i1 & (SKY_HRS - 1)) * SKY_HLD; r.w0 = t.w0; r.w1 = t.w1;
+        if (lane < SKY_H) sm.trow[bb & 3][lane] = r;
+        const int lo = __reduce_min_sync(0xffffffffu, t.i0), hi = __reduce_max_sync(0xffffffffu, t.i1);
+        if (lane == 0) { sm.blk_lo[bb & 3] = lo; sm.blk_hi[bb & 3] = hi; }
+    };
+    // ---- prologue: column taps, row taps of blocks 0..2, the segment's low-res patch
+    for (int i = tid; i < SKY_UW; i += SKY_NT) sm.tcol[i] = ux[reflect101(x0 - SKY_R + i, g.W)];
+    if (wid == 0) {
+        publish_row_taps(0, fetch_row_tap(0));
+        if (nb > 1) publish_row_taps(1, fetch_row_tap(1));
+        if (nb > 2) publish_row_taps(2, fetch_row_tap(2));
+    }
+    int xlo, xhi;
+    reflect_range(x0 - SKY_R, x0 + SKY_W + SKY_R - 1, g.W, xlo, xhi);
+    const int pc0 = ux[xlo].i0, pc1 = ux[xhi].i1, pr0 = uy[ya].i0, pr1 = uy[min(ya + SKY_H * nb, g.H) - 1].i1; // taps are monotone
+    const bool patch_ok = pc1 - pc0 < SKY_LRC && pr1 - pr0 < SKY_LRR;
+    if (patch_ok) {
+        const int nrow = pr1 - pr0 + 1, ncol = pc1 - pc0 + 1;
+        for (int i = tid; i < nrow * SKY_LRC; i += SKY_NT) {
+            const int r = i >> 4, cc = i & 15;
+            if (cc < ncol) sm.lr[i] = __ldg(L + (long long)(pr0 + r) * lw + pc0 + cc);
+        }
+    }
+    __syncthreads();
+
+    int hr_lo = 0, hr_hi = -1; // low-res rows currently valid in the hrow ring (uniform over warps 0..2)
+    auto hrow_pass = [&](int bb) {
+        if (tid >= SKY_HLD) return;
+        const int lo = sm.blk_lo[bb & 3], hi = sm.blk_hi[bb & 3];
+        int first;
+        if (lo >= hr_lo && lo <= hr_hi + 1) { first = max(hr_hi + 1, lo); hr_hi = max(hr_hi, hi); }
+        else { first = lo; hr_lo = lo; hr_hi = hi; }
+        hr_lo = max(hr_lo, hr_hi - (SKY_HRS - 1));
+        if (tid < SKY_UW && first <= hi) {
+            const ResizeTap a = sm.tcol[tid];
+            if (patch_ok) {
+                const float *p0 = sm.lr + (first - pr0) * SKY_LRC - pc0;
+                for (int r = first; r <= hi; r++, p0 += SKY_LRC)
+                    sm.hr[(r & (SKY_HRS - 1)) * SKY_HLD + tid] = lerp2(p0[a.i0], a.w0, p0[a.i1], a.w1);
+            } else {
+                for (int r = first; r <= hi; r++) {
+                    const float *row = L + (long long)r * lw;
+                    sm.hr[(r & (SKY_HRS - 1)) * SKY_HLD + tid] = lerp2(__ldg(row + a.i0), a.w0, __ldg(row + a.i1), a.w1);
+                }
+            }
+        }
+    };
+    // this thread's items of the upsample pass (row pair, column pair) are the same in every step: resolved once
+    constexpr int UP_ITEMS = (SKY_H / 2) * (SKY_UW / 2), UP_ITERS = (UP_ITEMS + SKY_NT - 1) / SKY_NT;
+    int up_rp2[UP_ITERS], up_c[UP_ITERS], up_dst[UP_ITERS];
+#pragma unroll
+    for (int it = 0; it < UP_ITERS; it++) {
+        const int i = tid + SKY_NT * it, rp = i / (SKY_UW / 2), c = 2 * (i - rp * (SKY_UW / 2));
+        up_rp2[it] = i < UP_ITEMS ? 2 * rp : -1;
+        up_c[it] = c;
+        up_dst[it] = rp * SKY_ULD + c;
+    }
+    auto up_pass = [&](int bb) {
+        const SkyRowTap *tr = sm.trow[bb & 3];
+        float2 *up2 = sm.up2[bb & 1];
+#pragma unroll
+        for (int it = 0; it < UP_ITERS; it++) {
+            if (up_rp2[it] >= 0) {
+                const int c = up_c[it];
+                const SkyRowTap t0 = tr[up_rp2[it]], t1 = tr[up_rp2[it] + 1];
+                const f32x2_t h0 = *(const f32x2_t *)(sm.hr + t0.o0 + c), h1 = *(const f32x2_t *)(sm.hr + t0.o1 + c);
+                const f32x2_t g0 = *(const f32x2_t *)(sm.hr + t1.o0 + c), g1 = *(const f32x2_t *)(sm.hr + t1.o1 + c);
+                float a0, a1, b0, b1, c0, c1, d0, d1;
+                unpack2(mul2_bcast(t0.w0, h0), a0, a1);
+                unpack2(mul2_bcast(t0.w1, h1), b0, b1);
+                unpack2(mul2_bcast(t1.w0, g0), c0, c1);
+                unpack2(mul2_bcast(t1.w1, g1), d0, d1);
+                *(float4 *)(up2 + up_dst[it]) = make_float4(__fadd_rn(a0, b0), __fadd_rn(c0, d0), __fadd_rn(a1, b1), __fadd_rn(c1, d1));
+            }
+        }
+    };
+    hrow_pass(0);
+    if (nb > 1) hrow_pass(1); // rows of two consecutive blocks coexist in the ring: <= 2 * (16 / 8) + 3 <= SKY_HRS
+    __syncthreads();
+    up_pass(0);
+
+    const bool vec_out = (g.W & 3) == 0 && x0 + SKY_W <= g.W;
+    // this thread's output position (rows 2 rp, 2 rp + 1 of a block, 4 columns), advanced by one block per step
+    float *out_run = R + (long long)(ya + 2 * (2 * wid + ((lane >> 2) & 1))) * g.W + x0 + 4 * ((lane & 3) | ((lane >> 3) << 2));
+    // One barrier per step.  Phase b: row filter of block b (reads up2[b & 1]) | up of block b+1 (writes up2[(b+1) & 1], reads
+    // the hrow rows of block b+1) | hrow of block b+2 (other ring slots) | row taps of block b+3.
+    for (int b = 0; b < nb; b++) {
+        __syncthreads();
+        ResizeTap tnext;
+        const bool taps_due = wid == 0 && b + 3 < nb;
+        if (taps_due) tnext = fetch_row_tap(b + 3);
+        {
+            const int rp = 2 * wid + ((lane >> 2) & 1), gx = (lane & 3) | ((lane >> 3) << 2); // conflict-free LDS.128 (see above)
+            const ulonglong2 *src = (const ulonglong2 *)(sm.up2[b & 1] + rp * SKY_ULD + 4 * gx);
+            f32x2_t w[36];
+#pragma unroll
+            for (int q = 0; q < 18; q++) { ulonglong2 v = src[q]; w[2 * q] = v.x; w[2 * q + 1] = v.y; }
+            float o0[4], o1[4];
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                float a0, a1;
+                unpack2(mul2_bcast(c_gauss[0], w[e]), a0, a1);
+#pragma unroll
+                for (int j = 1; j < 31; j++) {
+                    float u, v;
+                    unpack2(mul2_bcast(c_gauss[j], w[e + j]), u, v);
+                    a0 = __fadd_rn(a0, u);
+                    a1 = __fadd_rn(a1, v);
+                }
+                o0[e] = a0; o1[e] = a1;
+            }
+            const int y = ya + SKY_H * b + 2 * rp, x = x0 + 4 * gx;
+            float *d0 = out_run;
+            out_run += (long long)SKY_H * g.W;
+            if (vec_out) {
+                if (y < yb) ((float4 *)d0)[0] = make_float4(o0[0], o0[1], o0[2], o0[3]);
+                if (y + 1 < yb) ((float4 *)(d0 + g.W))[0] = make_float4(o1[0], o1[1], o1[2], o1[3]);
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; e++)
+                    if (x + e < g.W) {
+                        if (y < yb) d0[e] = o0[e];
+                        if (y + 1 < yb) d0[g.W + e] = o1[e];
+                    }
+            }
+        }
+        if (b + 1 < nb) up_pass(b + 1);
+        if (b + 2 < nb) hrow_pass(b + 2);
+        if (taps_due) publish_row_taps(b + 3, tnext);
+    }
+}
+
+#define SKC_D 3                              // prefetch distance in steps: a step is < 1 us, an HBM round trip under load is not
+#define SKC_NSLOT (SKY_LA + 1 + SKC_D)       // ring blocks: the SKY_LA + 1 a column pass reads + SKC_D in flight
+#define SKC_RING (SKC_NSLOT * SKY_H)
+struct SkyColsSmem {
+    float rf[(SKC_RING + SKY_LA * SKY_H) * SKY_W]; // ring of row-filtered rows + mirror of the first SKY_LA blocks
+    float gray[SKC_D + 1][SKY_H * SKY_W];          // cp.async targets
+    unsigned char mode[SKY_SEG_MAX / SKY_H];
+    double red[2][SKY_NT / 32];
+};
+constexpr int kSkyColsSmemBytes = (int)sizeof(SkyColsSmem);
+
+__global__ void __launch_bounds__(SKY_NT, 4)
+k_sky_cols(const float *__restrict__ gray, long long strideGray, const float *__restrict__ rf, long long strideRf,
+           float *__restrict__ stars, long long strideStars, float *__restrict__ segmax, long long strideSeg, int nseg,
+           double *__restrict__ partials, long long stridePart, Geom g, int seg_h)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SkyColsSmem &sm = *(SkyColsSmem *)smem_raw;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int x0 = blockIdx.x * SKY_W, ya = blockIdx.y * seg_h, yb = min(ya + seg_h, g.H), f = blockIdx.z;
+    const int nk = (yb - ya + SKY_H - 1) / SKY_H; // output blocks 0..nk-1; rf blocks 0..nk-1+SKY_LA, block j = rows ya - 16 + j*SKY_H ...
+    const float *G = gray + f * strideGray;
+    const float *R = rf + f * strideRf;
+    float *S = stars + f * strideStars;
+    float *SM = segmax + f * strideSeg;
+    const bool vec = (g.W & 3) == 0 && x0 + SKY_W <= g.W;
+    const int pr = tid >> 4, pq = tid & 15; // this thread's 16-byte chunk of rows pr and pr + 8 of a block
+    // Everything the step loop needs is kept as running values: shared-memory addresses of this thread's chunk, global
+    // pointers that advance by one block (16 rows) per step, ring slots that count modulo SKC_NSLOT.  (Recomputing them per
+    // step — reflections, 64-bit row products, j % 6 — cost more instructions than the arithmetic itself, and integer
+    // multiply-adds share the FMA pipe with it.)
+    const unsigned rf_s = (unsigned)__cvta_generic_to_shared(sm.rf + pr * SKY_W + 4 * pq);
+    const unsigned gray_s = (unsigned)__cvta_generic_to_shared(&sm.gray[0][0] + pr * SKY_W + 4 * pq);
+    const long long blk_f = (long long)SKY_H * g.W, half_b = (long long)(SKY_H / 2) * g.W * 4; // floats per block, bytes per 8 rows
+    const float *rf_g = R + (long long)(ya - 16 + pr) * g.W + x0 + 4 * pq;   // row pr of rf block 0 (only dereferenced when inside the frame)
+    const float *gray_g = G + (long long)(ya + pr) * g.W + x0 + 4 * pq;       // row pr of output block 0
+    int ld_y0 = ya - 16, ld_slot = 0;   // first row and ring slot of the next rf block to load
+    int gr_y0 = ya, gr_buf = 0;         // first row and buffer of the next gray tile to load
+
+    auto cp16 = [](unsigned dst, const void *src) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src)); };
+    // next rf block -> ring slot ld_slot (+ its mirror copy); rows beyond the frame's ends are BORDER_REFLECT_101 rows
+    auto load_next_block = [&]() {
+        const unsigned dst = rf_s + ld_slot * (SKY_H * SKY_W * 4);
+        if (vec && ld_y0 >= 0 && ld_y0 + SKY_H <= g.H) {          // the usual case: 16 rows inside the frame
+            cp16(dst, rf_g);
+            cp16(dst + (SKY_H / 2) * SKY_W * 4, (const char *)rf_g + half_b);
+            if (ld_slot < SKY_LA) {
+                cp16(dst + SKC_RING * SKY_W * 4, rf_g);
+                cp16(dst + (SKC_RING + SKY_H / 2) * SKY_W * 4, (const char *)rf_g + half_b);
+            }
+        } else if (vec) {
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int r = pr + 8 * h, y = reflect101(ld_y0 + r, g.H);
+                const float *src = R + (long long)y * g.W + x0 + 4 * pq;
+                cp16(dst + h * (SKY_H / 2) * SKY_W * 4, src);
+                if (ld_slot < SKY_LA) cp16(dst + (SKC_RING + h * (SKY_H / 2)) * SKY_W * 4, src);
+            }
+        } else {
+            for (int i = tid; i < SKY_H * SKY_W; i += SKY_NT) {
+                const int r = i >> 6, c = i & 63, y = reflect101(ld_y0 + r, g.H);
+                const float v = x0 + c < g.W ? __ldg(R + (long long)y * g.W + x0 + c) : 0.f;
+                sm.rf[(ld_slot * SKY_H + r) * SKY_W + c] = v;
+                if (ld_slot < SKY_LA) sm.rf[(SKC_RING + ld_slot * SKY_H + r) * SKY_W + c] = v;
+            }
+        }
+        rf_g += blk_f;
+        ld_y0 += SKY_H;
+        ld_slot = ld_slot == SKC_NSLOT - 1 ? 0 : ld_slot + 1;
+    };
+    auto load_next_gray = [&]() {
+        const unsigned dst = gray_s + gr_buf * (SKY_H * SKY_W * 4);
+        if (vec) {
+            if (gr_y0 + pr < g.H) cp16(dst, gray_g);
+            if (gr_y0 + pr + SKY_H / 2 < g.H) cp16(dst + (SKY_H / 2) * SKY_W * 4, (const char *)gray_g + half_b);
+        } else {
+            float *dstb = sm.gray[gr_buf];
+            for (int i = tid; i < SKY_H * SKY_W; i += SKY_NT) {
+                const int r = i >> 6, c = i & 63;
+                dstb[i] = (gr_y0 + r < g.H && x0 + c < g.W) ? __ldg(G + (long long)(gr_y0 + r) * g.W + x0 + c) : 0.f;
+            }
+        }
+        gray_g += blk_f;
+        gr_y0 += SKY_H;
+        gr_buf = gr_buf == SKC_D ? 0 : gr_buf + 1;
+    };
+    if (tid < nk) {
+        const int yblk = ya + SKY_H * tid;
+        const bool in_image = x0 + SKY_W <= g.W && yblk + SKY_H <= g.H && (g.W & 1) == 0;
+        const bool in_roi = x0 >= g.roi_x && x0 + SKY_W <= g.roi_x + g.roi_w && yblk >= g.roi_y && yblk + SKY_H <= g.roi_y + g.roi_h;
+        const bool off_roi = x0 >= g.roi_x + g.roi_w || x0 + SKY_W <= g.roi_x || yblk >= g.roi_y + g.roi_h || yblk + SKY_H <= g.roi_y;
+        sm.mode[tid] = (in_image && in_roi) ? 0 : (in_image && off_roi) ? 1 : 2;
+    }
+    // prologue: SKC_D groups in flight.  Group d holds what output block d still lacks: rf block d + SKY_LA (group 0 also the
+    // blocks below it) and its gray tile.  Blocks are loaded strictly in order, so the running state above stays in step.
+#pragma unroll
+    for (int d = 0; d < SKC_D; d++) {
+        if (d == 0) for (int j = 0; j < SKY_LA; j++) load_next_block();
+        load_next_block();      // (beyond the segment's last block: rows further down the frame, or reflections — loaded, never read)
+        load_next_gray();
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+
+    double sum = 0.0, sq = 0.0;
+    int slot = 0, gbuf = 0, yblk = ya;
+    // One barrier per step.  Step k: wait for group k (all but the SKC_D - 1 youngest) | barrier | queue group k + SKC_D into the
+    // slots output block k - 1 has just released | column pass of output block k (rf blocks k .. k + SKY_LA).
+    for (int k = 0; k < nk; k++) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(SKC_D - 1) : "memory");
+        __syncthreads();
+        if (k + SKC_D < nk) { load_next_block(); load_next_gray(); }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        const int mode = sm.mode[k];
+        const float *gt = sm.gray[gbuf];
+        if (mode == 0) sky_column_pass<0>(sm.rf, gt, slot * SKY_H, x0, yblk, tid, S, SM, nseg, g, sum, sq);
+        else if (mode == 1) sky_column_pass<1>(sm.rf, gt, slot * SKY_H, x0, yblk, tid, S, SM, nseg, g, sum, sq);
+        else sky_column_pass<2>(sm.rf, gt, slot * SKY_H, x0, yblk, tid, S, SM, nseg, g, sum, sq);
+        yblk += SKY_H;
+        slot = slot == SKC_NSLOT - 1 ? 0 : slot + 1;
+        gbuf = gbuf == SKC_D ? 0 : gbuf + 1;
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         sum += __shfl_xor_sync(0xffffffffu, sum, o);

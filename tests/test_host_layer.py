@@ -275,9 +275,10 @@ def test_cli_many_png_lights_pipelined_mono16_and_capacity_retry(host, tmp_path)
     --mono16 writes the GUI's 16-bit file.  Then the same stack starting from a detection work space that is too small
     (test hook OSS_STACKER_CAPACITY=64 at threshold 2): the facade must notice OSS_E_CAPACITY, enlarge and re-run — same file."""
     w, h = 640, 480
-    ds = synth.dataset(w, h, 40, 1, nstars=80, ndarks=7, seed=77)
+    ds = synth.dataset(w, h, 40, 1, nstars=80, ndarks=7, seed=5)
     lst = _write_stack(tmp_path, ds, ".png", lambda p, f: cv2.imwrite(p, f))
     want = oracle.stack(ds["ref"], ds["lights"], 20, dark_frames=ds["darks"])
+    assert 30 <= want["total_valid"] < 41      # a few lights fail in the reference's own clipping loop: skipped, in order
     out = str(tmp_path / "stack")
     r = subprocess.run([CLI, "-f", lst, "-o", out, "-t", "20", "-j", "6"], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
