@@ -7,6 +7,8 @@
 //   getCalibratedImage        util.cpp:266-274   ((x - bias) - dark) / flat
 //   cvtColor(BGR2GRAY)        stardetector.cpp:110-116
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace oss {
@@ -159,7 +161,7 @@ __device__ __forceinline__ void load_u16_stream(const uint16_t *src, float *v)
 }
 
 template <int C, bool HAS_B, bool HAS_D, bool HAS_F>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 k_calibrate_gray_batch(const __grid_constant__ FramePtrs raws, int nframes, const float *__restrict__ bias,
                        const float *__restrict__ dark, const float *__restrict__ flat, float *__restrict__ cal,
                        long long strideCal, float *__restrict__ gray, long long strideGray, long long P)
@@ -171,12 +173,24 @@ k_calibrate_gray_batch(const __grid_constant__ FramePtrs raws, int nframes, cons
     if (HAS_B) load_f32<N>(bias + p0 * C, mb);
     if (HAS_D) load_f32<N>(dark + p0 * C, md);
     if (HAS_F) load_f32<N>(flat + p0 * C, mf);
+    // cv::divide's "x / 0 = 0" (div_flat): whether any of this thread's flat values is zero is known once per launch, so the
+    // frame loop divides plainly and patches the (practically never taken) zero case behind one predicate per frame
+    bool flat_has_zero = false;
+    if (HAS_F) {
+#pragma unroll
+        for (int i = 0; i < N; i++) flat_has_zero |= mf[i] == 0.f;
+    }
     auto finish = [&](float *v, int f) {
 #pragma unroll
         for (int i = 0; i < N; i++) {
             if (HAS_B) v[i] = __fsub_rn(v[i], mb[i]);
             if (HAS_D) v[i] = __fsub_rn(v[i], md[i]);
-            if (HAS_F) v[i] = div_flat(v[i], mf[i]);
+            if (HAS_F) v[i] = __fdiv_rn(v[i], mf[i]);
+        }
+        if (HAS_F && flat_has_zero) {
+#pragma unroll
+            for (int i = 0; i < N; i++)
+                if (mf[i] == 0.f) v[i] = 0.f;
         }
         store_f32<N>(cal + (long long)f * strideCal + p0 * C, v);
         if (C == 3) {

@@ -303,7 +303,7 @@ k_root_flags(const int *__restrict__ parent, const int *__restrict__ comp_size, 
 // comp_root[c] = list position of component c's first pixel, comp_off[c] = scratch offset
 __global__ void __launch_bounds__(256)
 k_gather_roots(const int *__restrict__ flag, const int *__restrict__ flagscan, const int *__restrict__ sizescan,
-               int *__restrict__ comp_root, int *__restrict__ comp_off, const DetectState *__restrict__ ds, Geom g)
+               int *__restrict__ comp_root, int *__restrict__ comp_off, int *__restrict__ fill, const DetectState *__restrict__ ds, Geom g)
 {
     const int f = blockIdx.y;
     if (ds[f].overflow) return;
@@ -314,6 +314,7 @@ k_gather_roots(const int *__restrict__ flag, const int *__restrict__ flagscan, c
             long long c = (long long)f * g.cap + flagscan[q];
             comp_root[c] = i;
             comp_off[c] = sizescan[q];
+            fill[c] = 0; // member counter of k_comp_members (the array is comp_nstar: k_components overwrites it afterwards)
         }
     }
 }
@@ -387,14 +388,190 @@ __device__ oss_star create_star(const int *S, int ns, int *sorted, const int *__
     return st;
 }
 
-__global__ void __launch_bounds__(64)
+// One component, replayed literally by ONE thread over the global lists: the reference's DFS and peel orders (the fallback
+// of k_components for components larger than its shared-memory scratch, incl. the >= 10000-px deblender bypass).
+__device__ int component_serial(int c, long long fb, const int *__restrict__ cidx, const float *__restrict__ cval,
+                                const int4 *__restrict__ nb, int *__restrict__ own, const int *__restrict__ comp_size,
+                                const int *__restrict__ comp_root, const int *__restrict__ comp_off, int *__restrict__ scr,
+                                oss_star *__restrict__ star_tmp, float step, const Geom &g)
+{
+    int sp;
+    const int root = comp_root[fb + c];
+    const int n = comp_size[fb + root];
+    const int off = comp_off[fb + c];
+    int *list = scr + off;
+    int *S = scr + g.cap + off;
+    int *sorted = scr + 2 * (long long)g.cap + off;
+    int *acc_gx = scr + 3 * (long long)g.cap + off;
+    int *acc_gy = scr + 4 * (long long)g.cap + off;
+    int *stamp = scr + 5 * (long long)g.cap + off;
+    int *stack = scr + 6 * (long long)g.cap + 4 * (long long)off + c; // 4n+1 entries
+    oss_star *out = star_tmp + fb + off;
+
+    // detectAdjoiningPixel: explicit-stack DFS, push order up, left, right, down
+    int np = 0; sp = 0;
+    stack[sp++] = root;
+    while (sp > 0) {
+        int i = stack[--sp];
+        if (own[i] != -3) continue;
+        own[i] = -1; // REMAINING (for the deblender)
+        list[np++] = i;
+        int4 q = nb[i];
+        if (q.x >= 0 && own[q.x] == -3) stack[sp++] = q.x;
+        if (q.y >= 0 && own[q.y] == -3) stack[sp++] = q.y;
+        if (q.z >= 0 && own[q.z] == -3) stack[sp++] = q.z;
+        if (q.w >= 0 && own[q.w] == -3) stack[sp++] = q.w;
+    }
+
+    int nout = 0;
+    if (n >= OSS_DEBLEND_MAX) { // adjoiningpixel.cpp:45-48
+        out[nout++] = create_star(list, n, sorted, cidx, cval, g.W);
+        return nout;
+    }
+    int left = n, nacc = 0, iter = 0;
+    while (left > 0) {
+        iter++;
+        int pk = -1;
+        float mx = 0.f;
+        for (int q = 0; q < n; q++) { // getPeak: first maximum in list order
+            int i = list[q];
+            if (own[i] != -1) continue;
+            float v = cval[i];
+            if (pk < 0 || mx < v) { pk = i; mx = v; }
+        }
+        // adjoiningpixel.cpp:57
+        float T = (float)__dsub_rn((double)mx, __dmul_rn((double)step, sqrt(__dadd_rn((double)__fdiv_rn(mx, step), 1.0))));
+        // extract(): recursive pre-order up, left, right, down == stack with reversed pushes
+        int ns = 0;
+        sp = 0;
+        stack[sp++] = pk;
+        while (sp > 0) {
+            int i = stack[--sp];
+            if (own[i] != -1 || !(cval[i] > T)) continue;
+            own[i] = -2; // DROPPED unless accepted below
+            S[ns++] = i;
+            int4 q = nb[i];
+            if (q.w >= 0 && own[q.w] == -1) stack[sp++] = q.w;
+            if (q.z >= 0 && own[q.z] == -1) stack[sp++] = q.z;
+            if (q.y >= 0 && own[q.y] == -1) stack[sp++] = q.y;
+            if (q.x >= 0 && own[q.x] == -1) stack[sp++] = q.x;
+        }
+        if (ns == 0) break; // step <= 0 or NaN: the reference would never terminate
+        left -= ns;
+        // getGravityCenter (adjoiningpixel.cpp:104-118): fp32, list order, truncated
+        float gx = 0.f, gy = 0.f, gw = 0.f;
+        for (int q = 0; q < ns; q++) {
+            int i = S[q];
+            int lin = cidx[i];
+            int y = lin / g.W, x = lin - y * g.W;
+            float v = cval[i];
+            gx = __fadd_rn(gx, __fmul_rn(v, (float)x));
+            gy = __fadd_rn(gy, __fmul_rn(v, (float)y));
+            gw = __fadd_rn(gw, v);
+        }
+        int cx = (int)__fdiv_rn(gx, gw), cy = (int)__fdiv_rn(gy, gw);
+        // isAdjoining against every accepted region
+        for (int q = 0; q < ns; q++) {
+            int4 t = nb[S[q]];
+            if (t.x >= 0 && own[t.x] >= 0) stamp[own[t.x]] = iter;
+            if (t.y >= 0 && own[t.y] >= 0) stamp[own[t.y]] = iter;
+            if (t.z >= 0 && own[t.z] >= 0) stamp[own[t.z]] = iter;
+            if (t.w >= 0 && own[t.w] >= 0) stamp[own[t.w]] = iter;
+        }
+        int blending = 0;
+        for (int a = 0; a < nacc; a++)
+            if (stamp[a] == iter || (acc_gx[a] == cx && acc_gy[a] == cy)) blending++;
+        if (blending == 0) {
+            for (int q = 0; q < ns; q++) own[S[q]] = nacc;
+            acc_gx[nacc] = cx; acc_gy[nacc] = cy; stamp[nacc] = 0;
+            nacc++;
+            out[nout++] = create_star(S, ns, sorted, cidx, cval, g.W);
+        }
+    }
+    return nout;
+}
+
+// ---- K6  one WARP per component ----------------------------------------------------------
+// The component's pixels (k_comp_members: an unordered scatter by label) are staged in shared memory, sorted back into raster
+// order, and their neighbour links are translated to local indices; every traversal of the reference then runs on shared
+// memory instead of chasing pointers through L2:
+//   sequential by lane 0 (their ORDER is the result): the DFS of detectAdjoiningPixel, the deblender's extract();
+//   sequential chains spread over lanes 0..3 (one fp chain each, same operation order): gravity centre, createStar's sums;
+//   parallel over the warp: first-maximum search (getPeak), isAdjoining stamps, blending count, the (value, extraction
+//   order) ranking that replaces createStar's std::sort.
+// One thread per component over global memory (the first version) made the largest component of a batch its critical
+// path: ~2 us per pixel, 1.3 ms per 17-frame batch; here it is ~0.1 us per pixel.
+#define CW_CAP 512   // pixels per component handled in shared memory; larger ones (and the >= 10000-px bypass) go to component_serial
+#define CW_WARPS 4
+struct CompWarpSmem {
+    int gidx[CW_CAP];            // candidate-list positions, ascending = raster order
+    float val[CW_CAP];
+    int px[CW_CAP], py[CW_CAP];
+    short nb[CW_CAP][4];         // local neighbours: up, left, right, down (-1: none)
+    short own[CW_CAP];           // -3 unvisited, -1 remaining, -2 dropped, >= 0 accepted region
+    short list[CW_CAP];          // the reference's DFS order
+    short S[CW_CAP];             // region being peeled, extraction order
+    short sorted[CW_CAP];        // positions in S, ascending by (value, extraction order)
+    short stamp[CW_CAP];
+    int acc_gx[CW_CAP], acc_gy[CW_CAP];
+    short stack[4 * CW_CAP + 4];
+};
+constexpr int kCompSmemBytes = (int)sizeof(CompWarpSmem) * CW_WARPS;
+
+// createStar (adjoiningpixel.cpp:120-150) over region S[0..ns) by one warp.  Lanes 0..3 carry one chain each, all with the
+// formula acc = float(double(acc) + coord * double(v)): lanes 0 / 1 the flux-weighted x / y sums (coord = x + 0.5, y + 0.5, in
+// ascending-value order), lane 2 the weight and lane 3 `value` (coord = 1: double(acc) + double(v) rounded once to fp32 IS the
+// fp32 sum — 53 >= 2 * 24 + 2 bits, double rounding is innocuous), lane 3 in extraction order like the reference's first loop.
+__device__ oss_star create_star_warp(CompWarpSmem &sm, int ns, int lane)
+{
+    float *sv = (float *)sm.stack; // the region's values in extraction order (the DFS stack is idle here)
+    for (int q = lane; q < ns; q += 32) sv[q] = sm.val[sm.S[q]];
+    __syncwarp();
+    float peak = -INFINITY;
+    for (int q = lane; q < ns; q += 32) {
+        const float v = sv[q];
+        peak = fmaxf(peak, v);
+        // rank = number of elements ordered before this one: ascending value, ties by extraction order
+        int r = 0;
+        for (int p2 = 0; p2 < ns; p2++) {
+            const float u = sv[p2];
+            r += (u < v) || (u == v && p2 < q);
+        }
+        sm.sorted[r] = (short)q;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) peak = fmaxf(peak, __shfl_xor_sync(0xffffffffu, peak, o));
+    __syncwarp();
+    float acc = 0.f;
+    if (lane < 4) {
+        for (int q = 0; q < ns; q++) {
+            const int i = sm.S[lane == 3 ? q : sm.sorted[q]];
+            const double coord = lane == 0 ? (double)sm.px[i] + 0.5 : (lane == 1 ? (double)sm.py[i] + 0.5 : 1.0);
+            acc = (float)__dadd_rn((double)acc, __dmul_rn(coord, (double)sm.val[i]));
+        }
+    }
+    const float xa = __shfl_sync(0xffffffffu, acc, 0), ya = __shfl_sync(0xffffffffu, acc, 1);
+    const float wt = __shfl_sync(0xffffffffu, acc, 2), value = __shfl_sync(0xffffffffu, acc, 3);
+    oss_star st;
+    st.area = ns;
+    st.peak = peak;
+    st.value = value;
+    st.x = (int)__fdiv_rn(xa, wt);
+    st.y = (int)__fdiv_rn(ya, wt);
+    return st;
+}
+
+__global__ void __launch_bounds__(32 * CW_WARPS)
 k_components(const int *__restrict__ cand_idx, const float *__restrict__ cand_val, const int4 *__restrict__ nbr,
              int *__restrict__ owner, const int *__restrict__ comp_size, const int *__restrict__ comp_root,
              const int *__restrict__ comp_off, int *__restrict__ comp_nstar, int *__restrict__ scratch,
              oss_star *__restrict__ star_tmp, const DetectState *__restrict__ ds, Geom g)
 {
+    extern __shared__ __align__(16) unsigned char comp_smem_raw[];
     const int f = blockIdx.y;
     if (ds[f].overflow) return;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    CompWarpSmem &sm = ((CompWarpSmem *)comp_smem_raw)[wid];
     const int ncomp = ds[f].ncomp;
     const long long fb = (long long)f * g.cap;
     const int *cidx = cand_idx + fb;
@@ -404,101 +581,169 @@ k_components(const int *__restrict__ cand_idx, const float *__restrict__ cand_va
     int *scr = scratch + 12 * fb;
     const float step = ds[f].threshold;
 
-    for (int c = blockIdx.x * 64 + threadIdx.x; c < ncomp; c += gridDim.x * 64) {
+    for (int c = blockIdx.x * CW_WARPS + wid; c < ncomp; c += gridDim.x * CW_WARPS) {
         const int root = comp_root[fb + c];
         const int n = comp_size[fb + root];
         const int off = comp_off[fb + c];
-        int *list = scr + off;
-        int *S = scr + g.cap + off;
-        int *sorted = scr + 2 * (long long)g.cap + off;
-        int *acc_gx = scr + 3 * (long long)g.cap + off;
-        int *acc_gy = scr + 4 * (long long)g.cap + off;
-        int *stamp = scr + 5 * (long long)g.cap + off;
-        int *stack = scr + 6 * (long long)g.cap + 4 * (long long)off + c; // 4n+1 entries
         oss_star *out = star_tmp + fb + off;
-
-        // detectAdjoiningPixel: explicit-stack DFS, push order up, left, right, down
-        int np = 0, sp = 0;
-        stack[sp++] = root;
-        while (sp > 0) {
-            int i = stack[--sp];
-            if (own[i] != -3) continue;
-            own[i] = -1; // REMAINING (for the deblender)
-            list[np++] = i;
-            int4 q = nb[i];
-            if (q.x >= 0 && own[q.x] == -3) stack[sp++] = q.x;
-            if (q.y >= 0 && own[q.y] == -3) stack[sp++] = q.y;
-            if (q.z >= 0 && own[q.z] == -3) stack[sp++] = q.z;
-            if (q.w >= 0 && own[q.w] == -3) stack[sp++] = q.w;
-        }
-
-        int nout = 0;
-        if (n >= OSS_DEBLEND_MAX) { // adjoiningpixel.cpp:45-48
-            out[nout++] = create_star(list, n, sorted, cidx, cval, g.W);
-            comp_nstar[fb + c] = nout;
+        if (n > CW_CAP) { // rare: one lane replays it over global memory
+            int nout = 0;
+            if (lane == 0) nout = component_serial(c, fb, cidx, cval, nb, own, comp_size, comp_root, comp_off, scr, star_tmp, step, g);
+            if (lane == 0) comp_nstar[fb + c] = nout;
+            __syncwarp();
             continue;
         }
-        int left = n, nacc = 0, iter = 0;
-        while (left > 0) {
-            iter++;
-            int pk = -1;
-            float mx = 0.f;
-            for (int q = 0; q < n; q++) { // getPeak: first maximum in list order
-                int i = list[q];
-                if (own[i] != -1) continue;
-                float v = cval[i];
-                if (pk < 0 || mx < v) { pk = i; mx = v; }
-            }
-            // adjoiningpixel.cpp:57
-            float T = (float)__dsub_rn((double)mx, __dmul_rn((double)step, sqrt(__dadd_rn((double)__fdiv_rn(mx, step), 1.0))));
-            // extract(): recursive pre-order up, left, right, down == stack with reversed pushes
-            int ns = 0;
-            sp = 0;
-            stack[sp++] = pk;
-            while (sp > 0) {
-                int i = stack[--sp];
-                if (own[i] != -1 || !(cval[i] > T)) continue;
-                own[i] = -2; // DROPPED unless accepted below
-                S[ns++] = i;
-                int4 q = nb[i];
-                if (q.w >= 0 && own[q.w] == -1) stack[sp++] = q.w;
-                if (q.z >= 0 && own[q.z] == -1) stack[sp++] = q.z;
-                if (q.y >= 0 && own[q.y] == -1) stack[sp++] = q.y;
-                if (q.x >= 0 && own[q.x] == -1) stack[sp++] = q.x;
-            }
-            if (ns == 0) break; // step <= 0 or NaN: the reference would never terminate
-            left -= ns;
-            // getGravityCenter (adjoiningpixel.cpp:104-118): fp32, list order, truncated
-            float gx = 0.f, gy = 0.f, gw = 0.f;
-            for (int q = 0; q < ns; q++) {
-                int i = S[q];
-                int lin = cidx[i];
-                int y = lin / g.W, x = lin - y * g.W;
-                float v = cval[i];
-                gx = __fadd_rn(gx, __fmul_rn(v, (float)x));
-                gy = __fadd_rn(gy, __fmul_rn(v, (float)y));
-                gw = __fadd_rn(gw, v);
-            }
-            int cx = (int)__fdiv_rn(gx, gw), cy = (int)__fdiv_rn(gy, gw);
-            // isAdjoining against every accepted region
-            for (int q = 0; q < ns; q++) {
-                int4 t = nb[S[q]];
-                if (t.x >= 0 && own[t.x] >= 0) stamp[own[t.x]] = iter;
-                if (t.y >= 0 && own[t.y] >= 0) stamp[own[t.y]] = iter;
-                if (t.z >= 0 && own[t.z] >= 0) stamp[own[t.z]] = iter;
-                if (t.w >= 0 && own[t.w] >= 0) stamp[own[t.w]] = iter;
-            }
-            int blending = 0;
-            for (int a = 0; a < nacc; a++)
-                if (stamp[a] == iter || (acc_gx[a] == cx && acc_gy[a] == cy)) blending++;
-            if (blending == 0) {
-                for (int q = 0; q < ns; q++) own[S[q]] = nacc;
-                acc_gx[nacc] = cx; acc_gy[nacc] = cy; stamp[nacc] = 0;
-                nacc++;
-                out[nout++] = create_star(S, ns, sorted, cidx, cval, g.W);
+        // ---- stage: members (any order) -> ascending candidate positions (rank sort; positions are distinct)
+        const int *member = scr + off;
+        for (int k = lane; k < n; k += 32) sm.px[k] = member[k];
+        __syncwarp();
+        for (int k = lane; k < n; k += 32) {
+            const int v = sm.px[k];
+            int r = 0;
+            for (int j = 0; j < n; j++) r += sm.px[j] < v;
+            sm.gidx[r] = v;
+        }
+        __syncwarp();
+        for (int k = lane; k < n; k += 32) {
+            const int i = sm.gidx[k];
+            sm.val[k] = cval[i];
+            const int lin = cidx[i];
+            const int y = lin / g.W;
+            sm.py[k] = y;
+            sm.px[k] = lin - y * g.W;
+            sm.own[k] = -3;
+            const int4 q = nb[i];
+            const int gl[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int d = 0; d < 4; d++) {
+                int loc = -1;
+                if (gl[d] >= 0) { // neighbours above the threshold belong to the same component: binary search
+                    int lo = 0, hi = n - 1;
+                    while (lo < hi) { const int mid = (lo + hi) >> 1; if (sm.gidx[mid] < gl[d]) lo = mid + 1; else hi = mid; }
+                    loc = lo;
+                }
+                sm.nb[k][d] = (short)loc;
             }
         }
-        comp_nstar[fb + c] = nout;
+        __syncwarp();
+        // ---- detectAdjoiningPixel: explicit-stack DFS from the raster-first pixel, push order up, left, right, down
+        if (lane == 0) {
+            int np = 0, sp = 0;
+            sm.stack[sp++] = 0;
+            while (sp > 0) {
+                const int i = sm.stack[--sp];
+                if (sm.own[i] != -3) continue;
+                sm.own[i] = -1; // REMAINING (for the deblender)
+                sm.list[np++] = (short)i;
+#pragma unroll
+                for (int d = 0; d < 4; d++) {
+                    const int t = sm.nb[i][d];
+                    if (t >= 0 && sm.own[t] == -3) sm.stack[sp++] = (short)t;
+                }
+            }
+        }
+        __syncwarp();
+        // ---- AdjoiningPixel::deblend (adjoiningpixel.cpp:41-102); n < OSS_DEBLEND_MAX here
+        int left = n, nacc = 0, iter = 0, nout = 0;
+        while (left > 0) {
+            iter++;
+            // getPeak: first maximum in list order among the remaining pixels
+            float mx = 0.f;
+            int pos = 0x7fffffff;
+            for (int q = lane; q < n; q += 32) {
+                const int i = sm.list[q];
+                if (sm.own[i] != -1) continue;
+                const float v = sm.val[i];
+                if (pos == 0x7fffffff || mx < v) { mx = v; pos = q; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float v2 = __shfl_xor_sync(0xffffffffu, mx, o);
+                const int p2 = __shfl_xor_sync(0xffffffffu, pos, o);
+                // the sequential scan keeps the earlier element unless a later one is strictly larger
+                const bool take = p2 != 0x7fffffff && (pos == 0x7fffffff || (p2 < pos ? !(v2 < mx) : mx < v2));
+                if (take) { mx = v2; pos = p2; }
+            }
+            if (pos == 0x7fffffff) break;
+            const int pk = sm.list[pos];
+            const float T = (float)__dsub_rn((double)mx, __dmul_rn((double)step, sqrt(__dadd_rn((double)__fdiv_rn(mx, step), 1.0)))); // adjoiningpixel.cpp:57
+            // extract(): recursive pre-order up, left, right, down == stack with reversed pushes
+            int ns = 0;
+            if (lane == 0) {
+                int sp = 0;
+                sm.stack[sp++] = (short)pk;
+                while (sp > 0) {
+                    const int i = sm.stack[--sp];
+                    if (sm.own[i] != -1 || !(sm.val[i] > T)) continue;
+                    sm.own[i] = -2; // DROPPED unless accepted below
+                    sm.S[ns++] = (short)i;
+#pragma unroll
+                    for (int d = 3; d >= 0; d--) {
+                        const int t = sm.nb[i][d];
+                        if (t >= 0 && sm.own[t] == -1) sm.stack[sp++] = (short)t;
+                    }
+                }
+            }
+            ns = __shfl_sync(0xffffffffu, ns, 0);
+            if (ns == 0) break; // step <= 0 or NaN: the reference would never terminate
+            left -= ns;
+            // getGravityCenter (adjoiningpixel.cpp:104-118): fp32, list order; lanes 0..2 carry gx, gy, gw (v * 1.f == v)
+            float gacc = 0.f;
+            if (lane < 3) {
+                for (int q = 0; q < ns; q++) {
+                    const int i = sm.S[q];
+                    const float coord = lane == 0 ? (float)sm.px[i] : (lane == 1 ? (float)sm.py[i] : 1.f);
+                    gacc = __fadd_rn(gacc, __fmul_rn(sm.val[i], coord));
+                }
+            }
+            const float gx = __shfl_sync(0xffffffffu, gacc, 0), gy = __shfl_sync(0xffffffffu, gacc, 1), gw = __shfl_sync(0xffffffffu, gacc, 2);
+            const int cx = (int)__fdiv_rn(gx, gw), cy = (int)__fdiv_rn(gy, gw);
+            // isAdjoining against every accepted region
+            for (int q = lane; q < ns; q += 32) {
+                const int i = sm.S[q];
+#pragma unroll
+                for (int d = 0; d < 4; d++) {
+                    const int t = sm.nb[i][d];
+                    if (t >= 0) { const int o2 = sm.own[t]; if (o2 >= 0) sm.stamp[o2] = (short)iter; }
+                }
+            }
+            __syncwarp();
+            int blending = 0;
+            for (int a = lane; a < nacc; a += 32) blending += (sm.stamp[a] == iter) || (sm.acc_gx[a] == cx && sm.acc_gy[a] == cy);
+            blending = __any_sync(0xffffffffu, blending != 0);
+            if (!blending) {
+                for (int q = lane; q < ns; q += 32) sm.own[sm.S[q]] = (short)nacc;
+                if (lane == 0) { sm.acc_gx[nacc] = cx; sm.acc_gy[nacc] = cy; sm.stamp[nacc] = 0; }
+                nacc++;
+                __syncwarp();
+                const oss_star st = create_star_warp(sm, ns, lane);
+                if (lane == 0) out[nout] = st;
+                nout++;
+            }
+            __syncwarp();
+        }
+        if (lane == 0) comp_nstar[fb + c] = nout;
+        __syncwarp();
+    }
+}
+
+// members of every kept component, gathered by label into the component's scratch slice (any order; k_components sorts)
+__global__ void __launch_bounds__(256)
+k_comp_members(const int *__restrict__ parent, const int *__restrict__ flag, const int *__restrict__ flagscan,
+               const int *__restrict__ comp_off, int *__restrict__ fill, int *__restrict__ scratch,
+               const DetectState *__restrict__ ds, Geom g)
+{
+    const int f = blockIdx.y;
+    if (ds[f].overflow) return;
+    const int n = ds[f].ncand;
+    const long long fb = (long long)f * g.cap;
+    int *member = scratch + 12 * fb;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+        const int r = parent[fb + i];
+        if (!flag[fb + r]) continue;
+        const int c = flagscan[fb + r];
+        const int pos = atomicAdd(&fill[fb + c], 1);
+        member[comp_off[fb + c] + pos] = i;
     }
 }
 

@@ -481,6 +481,7 @@ int oss_create(oss_ctx **out, int device)
         cudaFuncSetAttribute(k_sky_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, kSkyRowsSmemBytes) != cudaSuccess ||
         cudaFuncSetAttribute(k_sky_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, kSkyColsSmemBytes) != cudaSuccess ||
         cudaFuncSetAttribute(k_focas, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FocasSmem)) != cudaSuccess ||
+        cudaFuncSetAttribute(k_components, cudaFuncAttributeMaxDynamicSharedMemorySize, kCompSmemBytes) != cudaSuccess ||
         cudaFuncSetAttribute(k_warp_accumulate_tiled<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, warp_tiled_smem<3>()) != cudaSuccess ||
         cudaFuncSetAttribute(k_warp_accumulate_tiled<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, warp_tiled_smem<1>()) != cudaSuccess ||
         cudaFuncSetAttribute(k_warp_accumulate_tma<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WarpTmaSmem<3>) + 128) != cudaSuccess ||
@@ -899,9 +900,10 @@ static int run_detect_tail(oss_ctx *c, int n, int threshold)
     if (r) return r;
     r = run_scan(c, w.comp_staroff, g.cap, w.comp_staroff, g.cap, ncand, DS, g.cap, n, nullptr, 0);
     if (r) return r;
-    LAUNCH("gather_roots", k_gather_roots, dim3(gs, n), 256, 0, w.flag, w.flagscan, w.comp_staroff, w.comp_root, w.comp_off, w.ds, g);
-    LAUNCH("components", k_components, dim3(4 * kSparseGrid, n), 64, 0, w.cand_idx, w.cand_val, w.nbr, w.owner, w.comp_size, w.comp_root,
-           w.comp_off, w.comp_nstar, w.scratch, w.star_tmp, w.ds, g);
+    LAUNCH("gather_roots", k_gather_roots, dim3(gs, n), 256, 0, w.flag, w.flagscan, w.comp_staroff, w.comp_root, w.comp_off, w.comp_nstar, w.ds, g);
+    LAUNCH("comp_members", k_comp_members, dim3(gs, n), 256, 0, w.parent, w.flag, w.flagscan, w.comp_off, w.comp_nstar, w.scratch, w.ds, g);
+    LAUNCH("components", k_components, dim3(kSparseGrid, n), 32 * CW_WARPS, kCompSmemBytes, w.cand_idx, w.cand_val, w.nbr, w.owner, w.comp_size,
+           w.comp_root, w.comp_off, w.comp_nstar, w.scratch, w.star_tmp, w.ds, g);
     r = run_scan(c, w.comp_nstar, g.cap, w.comp_staroff, g.cap, ncomp, DS, g.cap, n, nstars, DS);
     if (r) return r;
     LAUNCH("gather_stars", k_gather_stars, dim3(gs, n), 256, 0, w.star_tmp, w.comp_off, w.comp_nstar, w.comp_staroff, w.star_out,
