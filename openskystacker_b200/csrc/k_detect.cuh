@@ -501,7 +501,7 @@ __device__ int component_serial(int c, long long fb, const int *__restrict__ cid
 //   order) ranking that replaces createStar's std::sort.
 // One thread per component over global memory (the first version) made the largest component of a batch its critical
 // path: ~2 us per pixel, 1.3 ms per 17-frame batch; here it is ~0.1 us per pixel.
-#define CW_CAP 512   // pixels per component handled in shared memory; larger ones (and the >= 10000-px bypass) go to component_serial
+#define CW_CAP 256   // pixels per component handled in shared memory (12.5 KB per warp: 4 CTAs per SM); larger ones (and the >= 10000-px bypass) go to component_serial
 #define CW_WARPS 4
 struct CompWarpSmem {
     int gidx[CW_CAP];            // candidate-list positions, ascending = raster order

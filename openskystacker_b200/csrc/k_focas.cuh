@@ -458,6 +458,8 @@ k_focas(const RefTriangles *__restrict__ ref, const int *__restrict__ xy_tgt, co
         sm.xy1[tid] = ref->xy[tid];
         sm.xy2[tid] = tid < 2 * n2 ? xy_tgt[f * 2 * OSS_NOBJS + tid] : 0;
     }
+    // (votes as fire-and-forget global RED.ADD into a per-frame table were measured slower than these shared-memory atomics:
+    // 625 k vs 495 k cycles for the vote phase at 8000 triangles)
     for (int i = tid; i < OSS_NOBJS * OSS_NOBJS; i += FOCAS_NT) sm.table[i] = 0;
     for (int i = tid; i < 3 * (OSS_MAX_MATCH + 1); i += FOCAS_NT) (&sm.matches[0][0])[i] = 0;
     __syncthreads();
@@ -494,7 +496,11 @@ k_focas(const RefTriangles *__restrict__ ref, const int *__restrict__ xy_tgt, co
     // missed) and is replayed literally; the [first,last] window it then widens by linear scans
     // is the in-tolerance run around `mid` plus one element each side (or slot 0 / n-1 when the
     // scan runs off the end), which two more bisections over the sorted part give directly.
-    const double tol = 0.002, tol2 = 0.002 * 0.002;
+    const double tol = 0.002;
+    // the reference compares float differences with the doubles 0.002 and 0.002 * 0.002 (checkTolerance, focas.cpp:251-279);
+    // for a float d, (double)d < t is d < (the smallest float >= t): the window loop then needs no fp64 conversion per entry
+    // (it is issue-bound: one CTA, ~80 B triangles per A triangle).  tests/test_kernel_tables.py checks both constants.
+    const float kTolUp = __uint_as_float(0x3b03126fu), kTol2Up = __uint_as_float(0x368637beu);
     const int nA = ref->n;
     auto in_tol = [&](int i, float ax) { return !(fabs((double)__fsub_rn(sm.kx[F(i)], ax)) > tol); };
     for (int t = tid; t < nA; t += FOCAS_NT) {
@@ -522,9 +528,11 @@ k_focas(const RefTriangles *__restrict__ ref, const int *__restrict__ xy_tgt, co
         sm.alast[t] = (unsigned short)last;
     }
     __syncthreads();
-    // phase 2: a warp takes 32 consecutive A triangles at a time — ONE coalesced load of their (x, y, vertices, window) instead
-    // of a dependent global load per triangle (that latency, ~250 triangles per warp, was half of this kernel's time) — and
-    // walks each one's window with its lanes; votes are integer atomics, so their order does not matter
+    const long long c3b = clock64();
+    // phase 2: a warp takes 32 consecutive A triangles at a time (one coalesced load of their x, y, vertices and window) and walks
+    // each one's window with its lanes; votes are integer atomics, so their order does not matter.  Measured at ~8000 triangles
+    // per list (clock64, tools/focas_clk.py): 380 k cycles, of which ~100 k the shared-memory atomics (~200 k votes), ~105 k the
+    // two tolerance tests and ~175 k the bare window walk (~80 B triangles per A triangle); global RED votes were slower.
     for (int t0 = (tid >> 5) * 32; t0 < nA; t0 += FOCAS_NW * 32) {
         const int lane = tid & 31, tl = t0 + lane;
         float axl = 0.f, ayl = 0.f;
@@ -539,12 +547,12 @@ k_focas(const RefTriangles *__restrict__ ref, const int *__restrict__ xy_tgt, co
             const uint32_t as = __shfl_sync(0xffffffffu, asl, j);
             for (int i = first + lane; i <= last; i += 32) {
                 const int fi = F(i);
-                int id = sm.kid[fi];
+                const int id = sm.kid[fi];
                 float dy = __fsub_rn(ay, sm.by[id]);
-                if ((double)dy < tol) { // signed test, focas.cpp:261
+                if (dy < kTolUp) { // signed test, focas.cpp:261: (double)dy < 0.002  <=>  dy < the smallest float above 0.002
                     float dx = __fsub_rn(ax, sm.kx[fi]);
                     float d2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
-                    if ((double)d2 < tol2) {
+                    if (d2 < kTol2Up) { // (double)d2 < 4e-6
                         uint32_t bs = sm.bs[id];
                         atomicAdd(&sm.table[(as & 255) * OSS_NOBJS + (bs & 255)], 1);
                         atomicAdd(&sm.table[((as >> 8) & 255) * OSS_NOBJS + ((bs >> 8) & 255)], 1);
@@ -640,7 +648,7 @@ k_focas(const RefTriangles *__restrict__ ref, const int *__restrict__ xy_tgt, co
         if (dbg_clk) {
             long long c6 = clock64();
             dbg_clk[0] = c1 - c0; dbg_clk[1] = c2 - c1; dbg_clk[2] = c3 - c2; dbg_clk[3] = c4 - c3; dbg_clk[4] = c5 - c4;
-            dbg_clk[5] = c6 - c5; dbg_clk[6] = nB; dbg_clk[7] = e_pos;
+            dbg_clk[5] = c6 - c5; dbg_clk[6] = nB; dbg_clk[7] = c3b - c3; // [7]: the bisection phase of the vote
         }
     }
     if (dbg_table)

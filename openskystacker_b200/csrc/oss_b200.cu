@@ -1512,7 +1512,7 @@ int oss_align_lists(oss_ctx *c, const int32_t *xy1, int n1, const int32_t *xy2, 
     if (getenv("OSS_B200_FOCAS_CLK")) {
         long long clk[8];
         cudaMemcpy(clk, c->d_dbg_clk, sizeof clk, cudaMemcpyDeviceToHost);
-        fprintf(stderr, "focas clocks: tri %lld chain %lld rebuild+sort %lld vote %lld select %lld fit %lld (nB %lld e_pos %lld)\n",
+        fprintf(stderr, "focas clocks: tri %lld chain %lld rebuild+sort %lld vote %lld select %lld fit %lld (nB %lld, vote bisections %lld)\n",
                 clk[0], clk[1], clk[2], clk[3], clk[4], clk[5], clk[6], clk[7]);
     }
     if (k) *k = o.k;

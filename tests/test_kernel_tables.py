@@ -33,3 +33,18 @@ def test_median_network():
         wires[a], wires[b] = wires[a] & wires[b], wires[a] | wires[b]
     got = ((wires[12][:, None] >> bits[None, :]) & np.uint64(1)).astype(bool)
     assert np.array_equal(got, ones >= 13)
+
+
+def test_focas_vote_thresholds_are_the_floats_just_above_the_double_constants():
+    """k_focas compares float differences with float constants instead of converting every window entry to double:
+    for a float d, (double)d < t  <=>  d < f where f is the smallest float32 >= t (t itself is not a float32)."""
+    import re
+    src = open(os.path.join(os.path.dirname(__file__), "..", "openskystacker_b200", "csrc", "k_focas.cuh")).read()
+    bits = [int(x, 16) for x in re.search(r"kTolUp = __uint_as_float\((0x[0-9a-f]+)u\), kTol2Up = __uint_as_float\((0x[0-9a-f]+)u\)", src).groups()]
+    for b, t in zip(bits, (0.002, 0.002 * 0.002)):
+        f = np.array([b], np.uint32).view(np.float32)[0]
+        below = np.nextafter(f, np.float32(-np.inf))
+        assert float(below) < t <= float(f)
+        # exhaustive around the boundary: the float test and the double test agree
+        for d in (below, f, np.nextafter(below, np.float32(-np.inf)), np.nextafter(f, np.float32(np.inf)), np.float32(-t), np.float32(0)):
+            assert (float(d) < t) == bool(d < f)

@@ -35,7 +35,7 @@ def main():
         return float(r[col[name]].replace(",", "")) * UNIT.get(units[col[name]], 1.0)
     kernels = {}
     for r in rows[2:]:
-        fn = r[col["Kernel Name"]].split("(")[0].split("<")[0].split("::")[-1]
+        fn = r[col["Kernel Name"]].split("(")[0].split("<")[0].split("::")[-1].replace("void ", "").strip()
         name = NAMES.get(fn)
         if not name:
             continue
