@@ -347,6 +347,20 @@ __device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *m
                  "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)) : "memory");
 }
 
+__device__ __forceinline__ unsigned long long pack_f32x2(float lo, float hi)
+{
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack_f32x2(unsigned long long v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ unsigned long long mul_f32x2(unsigned long long a, unsigned long long b)
+{
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+
 struct WarpFootT { int sx0, sy0; bool empty, fits; };
 
 template <int C>
@@ -451,7 +465,9 @@ k_warp_accumulate_tma(const __grid_constant__ CUtensorMap tmap, const float *__r
 #pragma unroll
                     for (int ch = 0; ch < C; ch++) acc[k][ch] = __fadd_rn(acc[k][ch], 0.f);
             } else if (t.fits) {
-                // every tap is inside the staged box; taps outside the frame were filled with zeros by the TMA unit
+                // every tap is inside the staged box; taps outside the frame were filled with zeros by the TMA unit.
+                // The four products of a channel are two packed multiplies (mul.rn.f32x2: each half an IEEE fp32 product, no
+                // contraction with the scalar adds that follow): the kernel is issue-bound, this takes 6 instructions per pixel out
                 const float *tb = sm.tiles[s] - t.sx0 * C - t.sy0 * ROWF;
 #pragma unroll
                 for (int k = 0; k < 8; k++) {
@@ -461,13 +477,15 @@ k_warp_accumulate_tma(const __grid_constant__ CUtensorMap tmap, const float *__r
                     const int X = (b.x + abx.x) >> 5, Y = (b.y + abx.y) >> 5;
                     const float fx = (float)(X & 31) * (1.f / 32), fy = (float)(Y & 31) * (1.f / 32);
                     const float ix = 1.f - fx, iy = 1.f - fy;
-                    const float w00 = iy * ix, w01 = iy * fx, w10 = fy * ix, w11 = fy * fx; // exact: multiples of 1/1024
+                    const unsigned long long wtop = pack_f32x2(iy * ix, iy * fx), wbot = pack_f32x2(fy * ix, fy * fx); // exact: multiples of 1/1024
                     const float *p0 = tb + (Y >> 5) * ROWF + (X >> 5) * C;
                     const float *p1 = p0 + ROWF;
 #pragma unroll
                     for (int ch = 0; ch < C; ch++) {
-                        float val = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(p0[ch], w00), __fmul_rn(p0[C + ch], w01)), __fmul_rn(p1[ch], w10)),
-                                              __fmul_rn(p1[C + ch], w11));
+                        float m00, m01, m10, m11;
+                        unpack_f32x2(mul_f32x2(pack_f32x2(p0[ch], p0[C + ch]), wtop), m00, m01);
+                        unpack_f32x2(mul_f32x2(pack_f32x2(p1[ch], p1[C + ch]), wbot), m10, m11);
+                        const float val = __fadd_rn(__fadd_rn(__fadd_rn(m00, m01), m10), m11);
                         acc[k][ch] = __fadd_rn(acc[k][ch], val);
                     }
                 }
