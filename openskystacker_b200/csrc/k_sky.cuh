@@ -157,17 +157,24 @@ __device__ __forceinline__ void cp_async16_sky(void *smem, const void *gmem)
 #endif
 #define SKY_NT (SKY_H * 8)          // threads per CTA: 8 pixels per thread and step
 #define SKY_LA (1 + 30 / SKY_H)     // row-filtered blocks the column pass of a block waits for (its 15-row lower apron)
-#define SKY_NSLOT (SKY_LA + 2)      // ring blocks: those a column pass reads + the one being written
+#ifndef SKY_NSLOT
+#define SKY_NSLOT (SKY_LA + 1)      // ring blocks: the LA + 1 a column pass reads; the row pass of the next step overwrites the oldest
+#endif                              // one, whose column pass ended before barrier B
 #define SKY_R 15                    // Gaussian radius
 #define SKY_UW (SKY_W + 2 * SKY_R)  // 94 upsampled columns per strip
-#define SKY_ULD 102                 // float2 per row pair of up2: 36-wide windows starting at 4*gx stay inside; an ODD number
-                                    // of 16-byte chunks (51), so neighbouring row pairs start 4 banks apart (see the row filter)
-#define SKY_HRS 16                  // hrow ring slots
+#ifndef SKY_ULD
+#define SKY_ULD 98                  // float2 per row pair of up2: 34-wide windows starting at 4*gx stay inside; an ODD number
+#endif                              // of 16-byte chunks (49), so neighbouring row pairs start 4 banks apart (see the row filter)
+#ifndef SKY_HRS
+#define SKY_HRS 8                   // hrow ring slots: the low-res rows of ONE block (SKY_H / 8 + 3 <= 7) — hrow(b+1) runs after up(b)
+#endif
 #define SKY_HLD 96                  // floats per hrow row
 #define SKY_RING (SKY_NSLOT * SKY_H) // row-filtered ring rows; the first SKY_LA blocks are mirrored behind the ring
 #define SKY_LRC 16                  // low-res patch columns (94/8 + 2 = 14 needed)
-#define SKY_LRR 144                 // low-res patch rows: covers segments of up to 1024 rows
+#ifndef SKY_SEG_MAX
 #define SKY_SEG_MAX 1024            // rows per segment (multiple of SKY_H)
+#endif
+#define SKY_LRR (SKY_SEG_MAX / 8 + 16) // low-res patch rows of a segment with its aprons
 // a row tap with the hrow-ring offsets of its two low-res rows already resolved
 struct SkyRowTap { int o0, o1; float w0, w1; };
 struct SkySmem {
@@ -204,24 +211,33 @@ __device__ __forceinline__ void sky_column_pass(const float *__restrict__ ring, 
     const int gy = tid >> 5, cp = tid & 31, lane = cp;
     const int x = x0 + 2 * cp, y = yblk + 4 * gy;
     const f32x2_t *q = (const f32x2_t *)(ring + (ring_row0 + 4 * gy + 1) * SKY_W + 2 * cp);
+    // sliding window: tap pair j needs rows 15 - j .. 18 - j and 15 + j .. 18 + j, so the loads are interleaved with the
+    // arithmetic (j outer, the four output rows inner) and only ~10 window values are live at a time
     f32x2_t w[34];
 #pragma unroll
-    for (int j = 0; j < 34; j++) w[j] = q[j * (SKY_W / 2)];
+    for (int j = 15; j < 19; j++) w[j] = q[j * (SKY_W / 2)];
+    float ca[4], cb[4];
+#pragma unroll
+    for (int e = 0; e < 4; e++) unpack2(mul2_bcast(c_gauss[15], w[e + 15]), ca[e], cb[e]);
+#pragma unroll
+    for (int j = 1; j <= 15; j++) {
+        w[18 + j] = q[(18 + j) * (SKY_W / 2)];
+        w[15 - j] = q[(15 - j) * (SKY_W / 2)];
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            float u, v;
+            unpack2(mul2_bcast(c_gauss[15 + j], add2(w[e + 15 + j], w[e + 15 - j])), u, v);
+            ca[e] = __fadd_rn(ca[e], u);
+            cb[e] = __fadd_rn(cb[e], v);
+        }
+    }
     const float2 *gq = (const float2 *)(gtile + (4 * gy) * SKY_W + 2 * cp);
     float *sp = S + (long long)y * g.W + x;
     float *mp = SM + (long long)y * nseg + (x0 >> 5); // warp-uniform: the two segments of this warp's row
     const bool seg2 = (x0 >> 5) + 1 < nseg;
 #pragma unroll
     for (int e = 0; e < 4; e++) {
-        float a, b;
-        unpack2(mul2_bcast(c_gauss[15], w[e + 15]), a, b);
-#pragma unroll
-        for (int j = 1; j <= 15; j++) {
-            float u, v;
-            unpack2(mul2_bcast(c_gauss[15 + j], add2(w[e + 15 + j], w[e + 15 - j])), u, v);
-            a = __fadd_rn(a, u);
-            b = __fadd_rn(b, v);
-        }
+        const float a = ca[e], b = cb[e];
         const float2 gv = gq[e * (SKY_W / 2)];
         float va = __fsub_rn(gv.x, a), vb = __fsub_rn(gv.y, b);
         if (MODE < 2) {
@@ -398,22 +414,21 @@ k_sky_sub_stats(const float *__restrict__ gray, long long strideGray, const floa
             // mapping is a 2-way conflict on every window load)
             const int rp = 2 * wid + ((lane >> 2) & 1), gx = (lane & 3) | ((lane >> 3) << 2);
             const ulonglong2 *src = (const ulonglong2 *)(sm.up2 + rp * SKY_ULD + 4 * gx);
+            // sliding window: tap j needs columns j .. j + 3, so the window loads are interleaved with the arithmetic
+            // (taps outer, the four output columns inner: eight independent accumulation chains, few live window values)
             f32x2_t w[36];
-#pragma unroll
-            for (int q = 0; q < 18; q++) { ulonglong2 v = src[q]; w[2 * q] = v.x; w[2 * q + 1] = v.y; }
+            { ulonglong2 v = src[0]; w[0] = v.x; w[1] = v.y; v = src[1]; w[2] = v.x; w[3] = v.y; }
             float o0[4], o1[4];
 #pragma unroll
-            for (int e = 0; e < 4; e++) {
-                float a0, a1;
-                unpack2(mul2_bcast(c_gauss[0], w[e]), a0, a1);
+            for (int j = 0; j < 31; j++) {
+                if (j & 1) { ulonglong2 v = src[(j + 3) / 2]; w[j + 3] = v.x; w[j + 4] = v.y; }
 #pragma unroll
-                for (int j = 1; j < 31; j++) {
+                for (int e = 0; e < 4; e++) {
                     float u, v;
                     unpack2(mul2_bcast(c_gauss[j], w[e + j]), u, v);
-                    a0 = __fadd_rn(a0, u);
-                    a1 = __fadd_rn(a1, v);
+                    if (j == 0) { o0[e] = u; o1[e] = v; }
+                    else { o0[e] = __fadd_rn(o0[e], u); o1[e] = __fadd_rn(o1[e], v); }
                 }
-                o0[e] = a0; o1[e] = a1;
             }
             float *d0 = sm.rf + (slot * SKY_H + 2 * rp) * SKY_W + 4 * gx;
             ((float4 *)d0)[0] = make_float4(o0[0], o0[1], o0[2], o0[3]);
@@ -458,6 +473,7 @@ k_sky_sub_stats(const float *__restrict__ gray, long long strideGray, const floa
     }
 }
 
+#define SKR_HRS 16                  // hrow ring slots of k_sky_rows (the rows of two consecutive blocks coexist)
 // =======================================================================================
 // K3 split in two (alternative to k_sky_sub_stats, OSS_B200_SKY_SPLIT=1): the same arithmetic, cut where the data flow is narrowest.
 //   k_sky_rows   upsample + 31-tap ROW filter of every image row -> `rf` plane in HBM (4 B/px written).  No vertical
@@ -473,7 +489,7 @@ k_sky_sub_stats(const float *__restrict__ gray, long long strideGray, const floa
 // neither kernel's bound notices.
 struct SkyRowsSmem {
     float2 up2[2][(SKY_H / 2) * SKY_ULD];    // double-buffered upsampled block (row pairs interleaved)
-    float hr[SKY_HRS * SKY_HLD];
+    float hr[SKR_HRS * SKY_HLD];
     float lr[SKY_LRR * SKY_LRC];
     ResizeTap tcol[SKY_UW];
     SkyRowTap trow[4][SKY_H];
@@ -496,7 +512,7 @@ k_sky_rows(const float *__restrict__ med, long long strideLo, int lw, const Resi
     auto fetch_row_tap = [&](int bb) { return uy[min(ya + SKY_H * bb + (lane & (SKY_H - 1)), g.H - 1)]; };
     auto publish_row_taps = [&](int bb, const ResizeTap &t) {
         SkyRowTap r;
-        r.o0 = (t.i0 & (SKY_HRS - 1)) * SKY_HLD; r.o1 = (t.i1 & (SKY_HRS - 1)) * SKY_HLD; r.w0 = t.w0; r.w1 = t.w1;
+        r.o0 = (t.i0 & (SKR_HRS - 1)) * SKY_HLD; r.o1 = (t.i1 & (SKR_HRS - 1)) * SKY_HLD; r.w0 = t.w0; r.w1 = t.w1;
         if (lane < SKY_H) sm.trow[bb & 3][lane] = r;
         const int lo = __reduce_min_sync(0xffffffffu, t.i0), hi = __reduce_max_sync(0xffffffffu, t.i1);
         if (lane == 0) { sm.blk_lo[bb & 3] = lo; sm.blk_hi[bb & 3] = hi; }
@@ -528,17 +544,17 @@ k_sky_rows(const float *__restrict__ med, long long strideLo, int lw, const Resi
         int first;
         if (lo >= hr_lo && lo <= hr_hi + 1) { first = max(hr_hi + 1, lo); hr_hi = max(hr_hi, hi); }
         else { first = lo; hr_lo = lo; hr_hi = hi; }
-        hr_lo = max(hr_lo, hr_hi - (SKY_HRS - 1));
+        hr_lo = max(hr_lo, hr_hi - (SKR_HRS - 1));
         if (tid < SKY_UW && first <= hi) {
             const ResizeTap a = sm.tcol[tid];
             if (patch_ok) {
                 const float *p0 = sm.lr + (first - pr0) * SKY_LRC - pc0;
                 for (int r = first; r <= hi; r++, p0 += SKY_LRC)
-                    sm.hr[(r & (SKY_HRS - 1)) * SKY_HLD + tid] = lerp2(p0[a.i0], a.w0, p0[a.i1], a.w1);
+                    sm.hr[(r & (SKR_HRS - 1)) * SKY_HLD + tid] = lerp2(p0[a.i0], a.w0, p0[a.i1], a.w1);
             } else {
                 for (int r = first; r <= hi; r++) {
                     const float *row = L + (long long)r * lw;
-                    sm.hr[(r & (SKY_HRS - 1)) * SKY_HLD + tid] = lerp2(__ldg(row + a.i0), a.w0, __ldg(row + a.i1), a.w1);
+                    sm.hr[(r & (SKR_HRS - 1)) * SKY_HLD + tid] = lerp2(__ldg(row + a.i0), a.w0, __ldg(row + a.i1), a.w1);
                 }
             }
         }
@@ -573,7 +589,7 @@ k_sky_rows(const float *__restrict__ med, long long strideLo, int lw, const Resi
         }
     };
     hrow_pass(0);
-    if (nb > 1) hrow_pass(1); // rows of two consecutive blocks coexist in the ring: <= 2 * (16 / 8) + 3 <= SKY_HRS
+    if (nb > 1) hrow_pass(1); // rows of two consecutive blocks coexist in the ring: <= 2 * (16 / 8) + 3 <= SKR_HRS
     __syncthreads();
     up_pass(0);
 
