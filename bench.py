@@ -559,11 +559,9 @@ def main():
     per_frame = {  # algorithmic bytes per light frame, SURVEY.md section 8(d)
         "calibrate_gray": P * (2 * C + 4 * C * M + 4 * C + (4 if C > 1 else 0)),
         "warp_accumulate": P * (12 * C),
-        "sky_sub_stats": P * (4 + 4),       # fused form (OSS_B200_SKY_FUSED=1)
-        "sky_rows": P * 4,                  # split form: the row-filtered plane written ...
-        "sky_cols": P * (4 + 4 + 4),        # ... and read back, gray read, stars written
+        "sky_sub_stats": P * (4 + 4),       # gray read, stars written
     }
-    frames_of = {"calibrate_gray": nl + 1, "warp_accumulate": nl, "sky_sub_stats": nl + 1, "sky_rows": nl + 1, "sky_cols": nl + 1}
+    frames_of = {"calibrate_gray": nl + 1, "warp_accumulate": nl, "sky_sub_stats": nl + 1}
     total_ms = sum(ms for ms, _ in prof.values())
     shares = {k: round(ms / total_ms, 4) for k, (ms, n) in sorted(prof.items(), key=lambda kv: -kv[1][0])}
     traffic_file = ncu_traffic()
@@ -582,12 +580,12 @@ def main():
                 per = t["dram_bytes_per_launch"] / t["frames_per_launch"]
                 k.update(traffic_bytes_per_frame=per, physical_gbs=per / (us * 1e-6) / 1e9, physical_frac=per / (us * 1e-6) / 1e9 / peak)
             kernels[name] = k
-    for kname, ops_px in (("sky_sub_stats", SKY_OPS_PER_PIXEL), ("sky_rows", SKY_ROWS_OPS_PER_PIXEL), ("sky_cols", SKY_COLS_OPS_PER_PIXEL)):
-        if kname in kernels:
-            k = kernels[kname]
-            k.update(fp32_ops_per_pixel=ops_px, achieved_tflops=ops_px * P / (k["us_per_frame"] * 1e-6) / 1e12, peak_tflops=fp32_peak)
-            k["fp32_frac"] = k["achieved_tflops"] / fp32_peak
-            k["bound"] = "hbm" if kname == "sky_cols" else "fp32 pipe (no FMA)"
+    if "sky_sub_stats" in kernels:
+        k = kernels["sky_sub_stats"]
+        k.update(fp32_ops_per_pixel=SKY_OPS_PER_PIXEL, achieved_tflops=SKY_OPS_PER_PIXEL * P / (k["us_per_frame"] * 1e-6) / 1e12,
+                 peak_tflops=fp32_peak)
+        k["fp32_frac"] = k["achieved_tflops"] / fp32_peak
+        k["bound"] = "fp32 pipe (no FMA)"
     roof = None
     if kernels:
         name = max(kernels, key=lambda k: prof[k][0])   # the dominant kernel BY TIME
@@ -604,7 +602,7 @@ def main():
                          "reference's operation order without FMA (fp32_frac is its fraction of the non-fused fp32 peak); its HBM "
                          "fraction is low by construction.  For the HBM-bound kernels lead with physical_frac (ncu dram bytes / time): "
                          "hbm_frac counts SURVEY 8(d)'s algorithmic bytes, which re-read the masters per frame and so can exceed 1.")
-                if name in ("sky_sub_stats", "sky_rows") else
+                if name == "sky_sub_stats" else
                 "achieved counts SURVEY section 8(d)'s algorithmic bytes; physical_frac = ncu dram bytes per launch / launch time / peak",
                 "measured": "CUDA events around every launch on the launching stream, one extra serial step (1 pipeline) of the "
                             "same job inside this run; in the timed region detection tails overlap bulk kernels",
@@ -662,8 +660,6 @@ def main():
 
 # non-fusable fp32 operations per pixel of k_sky_sub_stats (kept next to the kernel's description in DESIGN.md section 4)
 SKY_OPS_PER_PIXEL = 113.0
-SKY_ROWS_OPS_PER_PIXEL = 65.4    # k_sky_rows: 31 mul + 30 add per row-filtered value + the bilinear upsample (3 ops x 94/64 apron columns)
-SKY_COLS_OPS_PER_PIXEL = 47.0    # k_sky_cols: 16 mul + 15 pair adds + 15 adds + the subtraction
 
 
 def run_checks(eng, B, job, res_n, reports_n, tv_n, world):

@@ -15,6 +15,7 @@
 #define OSS_MAX_MATCH 120 // focas.h:52
 #define OSS_MAX_TRI 9880  // C(40,3)
 #define OSS_SEG 32        // pixels per detection segment (one warp-wide row piece)
+#define OSS_SEGROWS 8    // rows per segment-maximum cell (k_sky_sub_stats writes one maximum per OSS_SEG px x OSS_SEGROWS rows)
 #define OSS_DEBLEND_MAX 10000 // adjoiningpixel.cpp:45
 
 namespace oss {
@@ -55,10 +56,9 @@ struct Workspace {
     float *cal;     // [slots][P*C]  calibrated frame
     float *gray;    // [slots][P]    luminance (aliases cal when C == 1)
     float *stars;   // [slots][P]    gray - sky
-    float *rf;      // [slots][P]    row-filtered upsampled sky (between k_sky_rows and k_sky_cols)
     float *lo;      // [slots][lw*lh]
     float *med;     // [slots][lw*lh]
-    float *segmax;  // [slots][H*nseg]
+    float *segmax;  // [slots][H*nseg]  maxima of 32 px x 8 rows cells, cell (y / 8, x / 32) at (y / 8) * nseg + x / 32
     uint32_t *segmask; // [slots][H*nseg]
     int *segoff;    // [slots][H*nseg + 1]
     double *partials; // [slots][2*stat_blocks]

@@ -133,8 +133,8 @@ k_scan_phase3(int *__restrict__ out, long long strideOut, const int *__restrict_
 }
 
 // ---- K4a  per-segment candidate masks ---------------------------------------------------
-// A segment is 32 consecutive pixels of one row.  Segments whose maximum (from K3) does not
-// exceed the threshold are skipped without touching the image: at t=20 that is > 99.9 %.
+// A segment is 32 consecutive pixels of one row.  Segments inside a 32 px x 8 rows cell whose maximum (from K3) does not
+// exceed the threshold are skipped without touching the image: at t=20 that is > 99 %.
 __global__ void __launch_bounds__(256)
 k_segment_masks(const float *__restrict__ stars, long long strideStars, const float *__restrict__ segmax,
                 long long strideSeg, uint32_t *__restrict__ segmask, int *__restrict__ segcount,
@@ -145,9 +145,9 @@ k_segment_masks(const float *__restrict__ stars, long long strideStars, const fl
     const long long s = (long long)blockIdx.x * 256 + threadIdx.x;
     if (s >= nsegs) return;
     const float th = ds[f].threshold;
+    const int y = (int)(s / g.nseg), sx = (int)(s - (long long)y * g.nseg);
     uint32_t m = 0;
-    if (segmax[f * strideSeg + s] > th) {
-        const int y = (int)(s / g.nseg), sx = (int)(s - (long long)y * g.nseg);
+    if (segmax[f * strideSeg + (long long)(y / OSS_SEGROWS) * g.nseg + sx] > th) {
         const float *row = stars + f * strideStars + (long long)y * g.W + sx * OSS_SEG;
         const int n = min(OSS_SEG, g.W - sx * OSS_SEG);
         for (int b = 0; b < n; b++)

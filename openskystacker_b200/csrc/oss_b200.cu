@@ -104,8 +104,7 @@ struct oss_ctx {
     long long ticket_count = 0;
     struct MasterBuild { int kind = -1, n_total = 0, added = 0, row0 = 0, rows = 0; bool sliced = false; } mb;
     int slice_row0[4] = {0, 0, 0, 0}, slice_rows[4] = {0, 0, 0, 0}; // rows of each master this rank built last (0 rows: whole)
-    int cap_one_in = 16;
-    bool sky_fused = true;               // the single marching kernel k_sky_sub_stats; false (OSS_B200_SKY_SPLIT=1): k_sky_rows + k_sky_cols                 // detection work space: P / cap_one_in candidate pixels per frame
+    int cap_one_in = 16;                 // detection work space: P / cap_one_in candidate pixels per frame
     cudaStream_t bulk = nullptr;         // the one low-priority stream of all bulk kernels
     // SM partition (green contexts): the FP32-bound sky kernel runs on `fp_stream`, which lives in a green context of
     // split_fp SMs, while the HBM-bound bulk kernels (masters, calibration, warp) run on `bulk`, re-created in the green
@@ -464,7 +463,6 @@ int oss_create(oss_ctx **out, int device)
     }
     if (const char *e = getenv("OSS_B200_PIPES")) c->want_pipes = atoi(e);
     if (const char *e = getenv("OSS_B200_SPLIT")) c->split_fp = atoi(e);
-    if (const char *e = getenv("OSS_B200_SKY_SPLIT")) c->sky_fused = atoi(e) == 0;
     if (const char *e = getenv("OSS_B200_CAP_DIV")) { int v = atoi(e); if (v >= 1 && v <= 64) c->cap_one_in = v; } // default only
     c->stream = c->bulk;
     c->copy_stream = c->pipes[0].copy_stream;
@@ -478,8 +476,6 @@ int oss_create(oss_ctx **out, int device)
     if (cudaMemcpyToSymbol(c_gauss, taps, sizeof taps) != cudaSuccess ||
         cudaMemcpyToSymbol(d_tri_ijk, ijk.data(), ijk.size() * 4) != cudaSuccess ||
         cudaFuncSetAttribute(k_sky_sub_stats, cudaFuncAttributeMaxDynamicSharedMemorySize, kSkySmemBytes) != cudaSuccess ||
-        cudaFuncSetAttribute(k_sky_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, kSkyRowsSmemBytes) != cudaSuccess ||
-        cudaFuncSetAttribute(k_sky_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, kSkyColsSmemBytes) != cudaSuccess ||
         cudaFuncSetAttribute(k_focas, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FocasSmem)) != cudaSuccess ||
         cudaFuncSetAttribute(k_components, cudaFuncAttributeMaxDynamicSharedMemorySize, kCompSmemBytes) != cudaSuccess ||
         cudaFuncSetAttribute(k_warp_accumulate_tiled<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, warp_tiled_smem<3>()) != cudaSuccess ||
@@ -634,7 +630,6 @@ int oss_set_geometry(oss_ctx *c, int W, int H, int C, int sample, int slots)
         DA(w.cal, slots * w.stridePC + 1024); // + slack: staged warp rows may run past the last frame's end
         if (C == 3) { DA(w.gray, slots * w.strideP); } else w.gray = w.cal;
         DA(w.stars, slots * w.strideP);
-        if (!c->sky_fused) DA(w.rf, slots * w.strideP);
         DA(w.lo, slots * lo); DA(w.med, slots * lo);
         DA(w.segmax, slots * nsegs); DA(w.segmask, slots * nsegs); DA(w.segoff, slots * (nsegs + 1));
         DA(w.partials, slots * w.stridePart);
@@ -848,14 +843,8 @@ static int detect_sky(oss_ctx *c, int n)
     const int seg_h = sky_segment_rows(g.W, g.H, n);
     const dim3 grid((g.W + SKY_W - 1) / SKY_W, (g.H + seg_h - 1) / seg_h, n);
     c->sky_blocks = grid.x * grid.y;
-    if (c->sky_fused) {
-        LAUNCH("sky_sub_stats", k_sky_sub_stats, grid, SKY_NT, kSkySmemBytes, w.gray, strideGray, w.med, w.strideLo, g.lw, c->ux, c->uy,
-               w.stars, w.strideP, w.segmax, w.strideSeg, g.nseg, w.partials, w.stridePart, g, seg_h);
-    } else {
-        LAUNCH("sky_rows", k_sky_rows, grid, SKY_NT, kSkyRowsSmemBytes, w.med, w.strideLo, g.lw, c->ux, c->uy, w.rf, w.strideP, g, seg_h);
-        LAUNCH("sky_cols", k_sky_cols, grid, SKY_NT, kSkyColsSmemBytes, w.gray, strideGray, w.rf, w.strideP, w.stars, w.strideP, w.segmax,
-               w.strideSeg, g.nseg, w.partials, w.stridePart, g, seg_h);
-    }
+    LAUNCH("sky_sub_stats", k_sky_sub_stats, grid, SKY_NT, kSkySmemBytes, w.gray, strideGray, w.med, w.strideLo, g.lw, c->ux, c->uy,
+           w.stars, w.strideP, w.segmax, w.strideSeg, g.nseg, w.partials, w.stridePart, g, seg_h);
     // the rest of the batch's detection (and whatever the caller queues next) goes to the pipeline's high-priority stream
     CK(cudaEventRecord(c->pipes[c->cur].sky_done, c->stream));
     c->stream = c->pipes[c->cur].chain_stream;

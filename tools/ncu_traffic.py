@@ -11,7 +11,7 @@ import os
 import subprocess
 
 NAMES = {"k_calibrate_gray_batch": "calibrate_gray", "k_warp_accumulate_tma": "warp_accumulate", "k_warp_accumulate_tiled": "warp_accumulate",
-         "k_sky_sub_stats": "sky_sub_stats", "k_sky_rows": "sky_rows", "k_sky_cols": "sky_cols", "k_master_accumulate": "master_accumulate"}
+         "k_sky_sub_stats": "sky_sub_stats", "k_master_accumulate": "master_accumulate"}
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12, "ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3, "usecond": 1e-3,
         "msecond": 1.0, "nsecond": 1e-6, "second": 1e3}
 
