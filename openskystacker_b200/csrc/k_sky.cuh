@@ -183,6 +183,8 @@ struct SkySmem {
     ResizeTap tcol[SKY_UW];
     SkyRowTap trow[2][SKY_H];
     int blk_lo[2], blk_hi[2];
+    int patch[4];                            // low-res patch: usable, first row, first column (read by hrow once per step: kept out of
+                                             // registers, where they would spill to local memory — an L2 round trip per step)
     unsigned char mode[SKY_SEG_MAX / SKY_H]; // column-pass variant of every output block of the segment
     double red[2][SKY_NT / 32];
 };
@@ -313,7 +315,7 @@ k_sky_sub_stats(const float *__restrict__ gray, long long strideGray, const floa
     float *S = stars + f * strideStars;
     float *SM = segmax + f * strideSeg;
 
-    // row taps of block bb (rows ya - 16 + 32 bb ...), by warp 0: the table lookup is issued a phase early
+    // row taps of block bb (rows ya - 16 + 32 bb ...), by warp 3 (warps 0..2 do the hrow pass): the table lookup is issued a phase early
     auto fetch_row_tap = [&](int bb) { return uy[reflect101(ya - 16 + SKY_H * bb + lane, g.H)]; };
     auto publish_row_taps = [&](int bb, const ResizeTap &t) {
         SkyRowTap r;
@@ -325,18 +327,21 @@ k_sky_sub_stats(const float *__restrict__ gray, long long strideGray, const floa
 
     // ---- prologue: column taps, first block's row taps, the segment's low-res patch
     for (int i = tid; i < SKY_UW; i += SKY_NT) sm.tcol[i] = ux[reflect101(x0 - SKY_R + i, g.W)];
-    if (wid == 0) publish_row_taps(0, fetch_row_tap(0));
+    if (wid == 3) publish_row_taps(0, fetch_row_tap(0));
     int xlo, xhi, ylo, yhi;
     reflect_range(x0 - SKY_R, x0 + SKY_W + SKY_R - 1, g.W, xlo, xhi);
     reflect_range(ya - 16, ya - 16 + SKY_H * (bmax + 1) - 1, g.H, ylo, yhi);
     const int pc0 = ux[xlo].i0, pc1 = ux[xhi].i1, pr0 = uy[ylo].i0, pr1 = uy[yhi].i1; // taps are monotone
-    const bool patch_ok = pc1 - pc0 < SKY_LRC && pr1 - pr0 < SKY_LRR;
-    if (patch_ok) {
-        const int nrow = pr1 - pr0 + 1, ncol = pc1 - pc0 + 1;
-        for (int i = tid; i < nrow * SKY_LRC; i += SKY_NT) {
-            const int r = i >> 4, cc = i & 15;
-            if (cc < ncol) sm.lr[i] = __ldg(L + (long long)(pr0 + r) * lw + pc0 + cc);
+    {
+        const bool patch_ok = pc1 - pc0 < SKY_LRC && pr1 - pr0 < SKY_LRR;
+        if (patch_ok) {
+            const int nrow = pr1 - pr0 + 1, ncol = pc1 - pc0 + 1;
+            for (int i = tid; i < nrow * SKY_LRC; i += SKY_NT) {
+                const int r = i >> 4, cc = i & 15;
+                if (cc < ncol) sm.lr[i] = __ldg(L + (long long)(pr0 + r) * lw + pc0 + cc);
+            }
         }
+        if (tid == 0) { sm.patch[0] = patch_ok; sm.patch[1] = pr0; sm.patch[2] = pc0; }
     }
     __syncthreads();
 
@@ -353,13 +358,13 @@ k_sky_sub_stats(const float *__restrict__ gray, long long strideGray, const floa
             for (int r = first; r <= hi; r++) sm.hr[(r & (SKY_HRS - 1)) * SKY_HLD + tid] = 0.f;
         } else if (first <= hi) {
             const ResizeTap a = sm.tcol[tid];
-            if (patch_ok) {
-                const float *p0 = sm.lr + (first - pr0) * SKY_LRC - pc0;
+            if (sm.patch[0]) {
+                const float *p0 = sm.lr + (first - sm.patch[1]) * SKY_LRC - sm.patch[2];
                 for (int r = first; r <= hi; r++, p0 += SKY_LRC)
                     sm.hr[(r & (SKY_HRS - 1)) * SKY_HLD + tid] = lerp2(p0[a.i0], a.w0, p0[a.i1], a.w1);
             } else {
                 for (int r = first; r <= hi; r++) {
-                    const float *row = L + (long long)r * lw;
+                    const float *row = med + blockIdx.z * strideLo + (long long)r * lw;
                     sm.hr[(r & (SKY_HRS - 1)) * SKY_HLD + tid] = lerp2(__ldg(row + a.i0), a.w0, __ldg(row + a.i1), a.w1);
                 }
             }
@@ -401,7 +406,7 @@ k_sky_sub_stats(const float *__restrict__ gray, long long strideGray, const floa
     hrow_pass(0);
     __syncthreads();
     up_pass(0);
-    if (wid == 0 && bmax >= 1) publish_row_taps(1, fetch_row_tap(1));
+    if (wid == 3 && bmax >= 1) publish_row_taps(1, fetch_row_tap(1));
 
     // row pass: this thread's row pair and column group.  A quarter-warp (8 lanes, one LDS.128 / STS.128 wavefront) = 2 neighbouring
     // column groups x 4 neighbouring row pairs; warp w makes rows 8 w .. 8 w + 7 of the block
@@ -418,7 +423,7 @@ k_sky_sub_stats(const float *__restrict__ gray, long long strideGray, const floa
     for (int b = 0; b <= bmax; b++) {
         __syncthreads(); // B: up2(b), row taps of b+1 visible; everyone left the previous column pass
         ResizeTap tnext;
-        const bool taps_due = wid == 0 && b + 2 <= bmax;
+        const bool taps_due = wid == 3 && b + 2 <= bmax; // warp 3 has no hrow work
         if (taps_due) tnext = fetch_row_tap(b + 2); // lands behind the row filter
         {   // rows (2rp, 2rp+1), columns 8gx .. 8gx+7 of this step's row-filtered block; sliding window: tap j needs columns
             // j .. j + 7, so the window loads are interleaved with the taps (taps outer, the eight columns inner)
