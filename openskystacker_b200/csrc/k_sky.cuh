@@ -172,6 +172,9 @@ __device__ __forceinline__ float2 ld_stream2(const float *p)
 #define SKY_LRC 16                  // low-res patch columns (94/8 + 2 = 14 needed)
 #define SKY_SEG_MAX 1024            // rows per segment (multiple of SKY_H)
 #define SKY_LRR (SKY_SEG_MAX / 8 + 16) // low-res patch rows of a segment with its aprons
+#ifndef SKY_ROW_ROLLED
+#define SKY_ROW_ROLLED 1
+#endif
 static_assert(SKY_H == 32 && SKY_NT == 128 && SKY_W == 64, "thread mappings of the row and column passes");
 // a row tap with the hrow-ring offsets of its two low-res rows already resolved
 struct SkyRowTap { int o0, o1; float w0, w1; };
@@ -427,6 +430,50 @@ k_sky_sub_stats(const float *__restrict__ gray, long long strideGray, const floa
         if (taps_due) tnext = fetch_row_tap(b + 2); // lands behind the row filter
         {   // rows (2rp, 2rp+1), columns 8gx .. 8gx+7 of this step's row-filtered block; sliding window: tap j needs columns
             // j .. j + 7, so the window loads are interleaved with the taps (taps outer, the eight columns inner)
+#if SKY_ROW_ROLLED
+            // taps 0..2 peeled, then two passes of a 14-tap body (code size: the fully unrolled 31 x 8 form is 800 instructions,
+            // and the whole step no longer fits the instruction caches).  Window entry i = column 8 gx + i.  The body sees
+            // entries base .. base + 21 (base = 2 + 14 t): W[0..7] carried from the previous pass, W[8..21] loaded.
+            f32x2_t cw[8];
+            float o0[8], o1[8];
+            {
+                f32x2_t w[10];
+#pragma unroll
+                for (int q = 0; q < 5; q++) { ulonglong2 v = row_src[q]; w[2 * q] = v.x; w[2 * q + 1] = v.y; }
+#pragma unroll
+                for (int j = 0; j < 3; j++)
+#pragma unroll
+                    for (int e = 0; e < 8; e++) {
+                        float u, v;
+                        unpack2(mul2_bcast(c_gauss[j], w[e + j]), u, v);
+                        if (j == 0) { o0[e] = u; o1[e] = v; }
+                        else { o0[e] = __fadd_rn(o0[e], u); o1[e] = __fadd_rn(o1[e], v); }
+                    }
+#pragma unroll
+                for (int i = 0; i < 8; i++) cw[i] = w[2 + i];
+            }
+#pragma unroll 1
+            for (int t = 0; t < 2; t++) {
+                const ulonglong2 *src = row_src + 5 + 7 * t;
+                const float *kt = c_gauss + 3 + 14 * t;
+                f32x2_t w[22];
+#pragma unroll
+                for (int i = 0; i < 8; i++) w[i] = cw[i];
+#pragma unroll
+                for (int jj = 0; jj < 14; jj++) {
+                    if (!(jj & 1)) { ulonglong2 v = src[jj / 2]; w[8 + jj] = v.x; w[9 + jj] = v.y; }
+                    const float k = kt[jj];
+#pragma unroll
+                    for (int e = 0; e < 8; e++) {
+                        float u, v;
+                        unpack2(mul2_bcast(k, w[1 + jj + e]), u, v);
+                        o0[e] = __fadd_rn(o0[e], u); o1[e] = __fadd_rn(o1[e], v);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 8; i++) cw[i] = w[14 + i];
+            }
+#else
             f32x2_t w[38];
 #pragma unroll
             for (int q = 0; q < 4; q++) { ulonglong2 v = row_src[q]; w[2 * q] = v.x; w[2 * q + 1] = v.y; }
@@ -442,6 +489,7 @@ k_sky_sub_stats(const float *__restrict__ gray, long long strideGray, const floa
                     else { o0[e] = __fadd_rn(o0[e], u); o1[e] = __fadd_rn(o1[e], v); }
                 }
             }
+#endif
             float *d0 = sm.rf + (slot * SKY_H + 2 * rp) * SKY_W;
             *(float4 *)(d0 + st0) = make_float4(o0[0], o0[1], o0[2], o0[3]);
             *(float4 *)(d0 + st1) = make_float4(o0[4], o0[5], o0[6], o0[7]);
