@@ -218,6 +218,79 @@ k_calibrate_gray_batch(const __grid_constant__ FramePtrs raws, int nframes, cons
 }
 
 // ---------------------------------------------------------------------------------------
+// K1c  the batch calibration with its frames in flight as BULK COPIES: the same arithmetic as k_calibrate_gray_batch.  A CTA
+// of 64 threads owns one chunk of 64 * PX consecutive pixels of EVERY frame of the launch: thread 0 fetches the chunk of all
+// frames with one `cp.async.bulk` each (-> shared memory, one mbarrier per frame): nframes * 1.5 KB in flight per CTA without
+// a register, 8 CTAs per SM (the register version K1b needs ~20 resident warps per SM for less).  The masters go to registers
+// once per CTA (as in K1b); the threads convert / subtract / divide frame by frame as the copies land.
+// 24 MP RGB, 3 masters, 17 frames per launch: 91.4 us per frame = 6.30 TB/s of physical traffic (K1b: 97.0 us).
+#define CALR_NT 64
+template <int C, bool HAS_B, bool HAS_D, bool HAS_F>
+__global__ void __launch_bounds__(CALR_NT, 8)
+k_calibrate_gray_ring(const __grid_constant__ FramePtrs raws, int nframes, const float *__restrict__ bias,
+                      const float *__restrict__ dark, const float *__restrict__ flat, float *__restrict__ cal,
+                      long long strideCal, float *__restrict__ gray, long long strideGray)
+{
+    constexpr int PX = C == 3 ? 4 : 8, N = PX * C;
+    constexpr unsigned CHUNK_BYTES = CALR_NT * N * 2; // u16 samples of one frame's chunk
+    extern __shared__ __align__(128) unsigned char calr_smem[];
+    unsigned long long *bar = (unsigned long long *)calr_smem;            // [OSS_MAX_BATCH]
+    unsigned char *ring = calr_smem + OSS_MAX_BATCH * 8;                  // [nframes][CHUNK_BYTES]
+    const int tid = threadIdx.x;
+    const long long p0 = ((long long)blockIdx.x * CALR_NT + tid) * PX;    // whole chunks only: the host sends the rest to K1
+    if (tid == 0) {
+        for (int f = 0; f < nframes; f++) mbar_init(&bar[f], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const size_t off = (size_t)blockIdx.x * CHUNK_BYTES;
+        for (int f = 0; f < nframes; f++) {
+            mbar_arrive_expect_tx(&bar[f], CHUNK_BYTES);
+            bulk_load(ring + (size_t)f * CHUNK_BYTES, (const unsigned char *)raws.p[f] + off, CHUNK_BYTES, &bar[f]);
+        }
+    }
+    float mb[N], md[N], mf[N];
+    if (HAS_B) load_f32<N>(bias + p0 * C, mb);
+    if (HAS_D) load_f32<N>(dark + p0 * C, md);
+    if (HAS_F) load_f32<N>(flat + p0 * C, mf);
+    bool flat_has_zero = false; // cv::divide's "x / 0 = 0", patched behind one predicate per frame (see K1b)
+    if (HAS_F) {
+#pragma unroll
+        for (int i = 0; i < N; i++) flat_has_zero |= mf[i] == 0.f;
+    }
+    __syncthreads(); // the barriers are initialised before anyone waits on them
+    const unsigned char *mine = ring + tid * (N * 2);
+    for (int f = 0; f < nframes; f++) {
+        mbar_wait(&bar[f], 0);
+        union { uint2 q[N / 4]; uint16_t s[N]; } u;
+#pragma unroll
+        for (int i = 0; i < N / 4; i++) u.q[i] = *(const uint2 *)(mine + (size_t)f * CHUNK_BYTES + 8 * i);
+        float v[N];
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+            v[i] = Sample<uint16_t>::conv(u.s[i]);
+            if (HAS_B) v[i] = __fsub_rn(v[i], mb[i]);
+            if (HAS_D) v[i] = __fsub_rn(v[i], md[i]);
+            if (HAS_F) v[i] = __fdiv_rn(v[i], mf[i]);
+        }
+        if (HAS_F && flat_has_zero) {
+#pragma unroll
+            for (int i = 0; i < N; i++)
+                if (mf[i] == 0.f) v[i] = 0.f;
+        }
+        store_f32<N>(cal + (long long)f * strideCal + p0 * C, v);
+        if (C == 3) {
+            float g[PX];
+#pragma unroll
+            for (int i = 0; i < PX; i++)
+                g[i] = __fadd_rn(__fadd_rn(__fmul_rn(v[3 * i], 0.114f), __fmul_rn(v[3 * i + 1], 0.587f)),
+                                 __fmul_rn(v[3 * i + 2], 0.299f));
+            store_f32<PX>(gray + (long long)f * strideGray + p0, g);
+        }
+    }
+}
+template <int C>
+static inline int calr_smem_bytes(int nframes) { return OSS_MAX_BATCH * 8 + nframes * CALR_NT * (C == 3 ? 12 : 8) * 2; }
+
+// ---------------------------------------------------------------------------------------
 // K0  master accumulation: acc = sum_f ((conv(raw_f) - sub1) - sub2), frames added in
 // order, then (last pass) acc *= r with r = float(1.0 / n_total)   [util.cpp:584-722].
 // Up to OSS_MAX_BATCH frames per launch so each master pixel is read/written once per

@@ -105,6 +105,8 @@ struct oss_ctx {
     struct MasterBuild { int kind = -1, n_total = 0, added = 0, row0 = 0, rows = 0; bool sliced = false; } mb;
     int slice_row0[4] = {0, 0, 0, 0}, slice_rows[4] = {0, 0, 0, 0}; // rows of each master this rank built last (0 rows: whole)
     int cap_one_in = 16;                 // detection work space: P / cap_one_in candidate pixels per frame
+    bool cal_ring = true;                // batch calibration by k_calibrate_gray_ring (bulk copies); OSS_B200_CAL_RING=0: k_calibrate_gray_batch
+    unsigned calr_attr = 0;              // k_calibrate_gray_ring instantiations whose attributes are set on this device
     cudaStream_t bulk = nullptr;         // the one low-priority stream of all bulk kernels
     // SM partition (green contexts): the FP32-bound sky kernel runs on `fp_stream`, which lives in a green context of
     // split_fp SMs, while the HBM-bound bulk kernels (masters, calibration, warp) run on `bulk`, re-created in the green
@@ -463,6 +465,7 @@ int oss_create(oss_ctx **out, int device)
     }
     if (const char *e = getenv("OSS_B200_PIPES")) c->want_pipes = atoi(e);
     if (const char *e = getenv("OSS_B200_SPLIT")) c->split_fp = atoi(e);
+    if (const char *e = getenv("OSS_B200_CAL_RING")) c->cal_ring = atoi(e) != 0;
     if (const char *e = getenv("OSS_B200_CAP_DIV")) { int v = atoi(e); if (v >= 1 && v <= 64) c->cap_one_in = v; } // default only
     c->stream = c->bulk;
     c->copy_stream = c->pipes[0].copy_stream;
@@ -719,7 +722,14 @@ static int launch_calibrate(oss_ctx *c, const FramePtrs &fp, int n, const float 
     if (batched) {
         constexpr int PXB = C == 3 ? 4 : 8;
         unsigned gridb = (unsigned)((g.P / PXB + 255) / 256);
-#define CALB(HB, HD, HF) { auto kf = k_calibrate_gray_batch<C, HB, HD, HF>; LAUNCH("calibrate_gray", kf, gridb, 256, 0, fp, n, b, d, f, w.cal, w.stridePC, w.gray, w.strideP, g.P); }
+        const bool ring = c->cal_ring && g.P >= CALR_NT * PXB;
+        const unsigned gridr = (unsigned)(g.P / (CALR_NT * PXB)); // whole chunks; the rest goes to the generic kernel below
+        const int smemr = calr_smem_bytes<C>(n);
+#define CALB(HB, HD, HF) { if (ring) { auto kr = k_calibrate_gray_ring<C, HB, HD, HF>; \
+            const unsigned abit = 1u << (key + (C == 3 ? 8 : 0)); /* function attributes are per device: remembered per context */ \
+            if (!(c->calr_attr & abit)) { CK(cudaFuncSetAttribute(kr, cudaFuncAttributeMaxDynamicSharedMemorySize, calr_smem_bytes<C>(OSS_MAX_BATCH))); c->calr_attr |= abit; } \
+            LAUNCH("calibrate_gray", kr, gridr, CALR_NT, smemr, fp, n, b, d, f, w.cal, w.stridePC, w.gray, w.strideP); } \
+          else { auto kf = k_calibrate_gray_batch<C, HB, HD, HF>; LAUNCH("calibrate_gray", kf, gridb, 256, 0, fp, n, b, d, f, w.cal, w.stridePC, w.gray, w.strideP, g.P); } }
         switch (key) {
         case 1: CALB(false, false, true); break;
         case 2: CALB(false, true, false); break;
@@ -730,7 +740,7 @@ static int launch_calibrate(oss_ctx *c, const FramePtrs &fp, int n, const float 
         case 7: CALB(true, true, true); break;
         }
 #undef CALB
-        P_tail_from = g.P / PXB * PXB;
+        P_tail_from = ring ? (long long)gridr * CALR_NT * PXB : g.P / PXB * PXB;
         if (P_tail_from == g.P) return OSS_OK;
     }
     // generic kernel: whole frames, or only the ragged tail the batched kernel left
