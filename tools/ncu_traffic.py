@@ -2,7 +2,7 @@
 """Dev aid: turn an `ncu --set full` report of the bulk kernels into profiles/ncu_traffic.json, the per-build record bench.py
 reads for `roofline.traffic` (dram__bytes_read.sum + dram__bytes_write.sum per launch) instead of a literal.
 
-    python tools/ncu_traffic.py gpurun_out/r02_prof_bulk.ncu-rep --frames 17 --width 6000 --height 4000 --channels 3 --masters 3
+    python tools/ncu_traffic.py gpurun_out/r02_prof_bulk2.ncu-rep --frames 17 --width 6000 --height 4000 --channels 3 --masters 3
 """
 import argparse
 import csv
@@ -10,7 +10,7 @@ import json
 import os
 import subprocess
 
-NAMES = {"k_calibrate_gray_batch": "calibrate_gray", "k_warp_accumulate_tma": "warp_accumulate", "k_warp_accumulate_tiled": "warp_accumulate",
+NAMES = {"k_calibrate_gray_batch": "calibrate_gray", "k_calibrate_gray_ring": "calibrate_gray", "k_warp_accumulate_tma": "warp_accumulate", "k_warp_accumulate_tiled": "warp_accumulate",
          "k_sky_sub_stats": "sky_sub_stats", "k_master_accumulate": "master_accumulate"}
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12, "ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3, "usecond": 1e-3,
         "msecond": 1.0, "nsecond": 1e-6, "second": 1e3}
