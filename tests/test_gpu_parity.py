@@ -85,6 +85,59 @@ def test_masters_and_calibration(eng, w, h, c, dt):
     assert np.array_equal(bits(eng.debug_plane(0)), bits(conv(light)))
 
 
+@pytest.mark.parametrize("ring", ["1", "0"])
+def test_batch_calibration_kernels_bit_exact(ring):
+    """The batch calibration of a launch of several u16 frames that share masters — k_calibrate_gray_ring (bulk copies on
+    mbarriers, the default) and k_calibrate_gray_batch (OSS_B200_CAL_RING=0) — against the oracle, slot by slot: RGB and mono,
+    frame sizes that leave a ragged tail behind the last whole chunk, every combination of masters, a zero flat pixel."""
+    import os
+    os.environ["OSS_B200_CAL_RING"] = ring
+    try:
+        e2 = ob.Engine(0)
+    finally:
+        del os.environ["OSS_B200_CAL_RING"]
+    try:
+        e2.set_pipelines(1)
+        for (w, h, c), masters in [((203, 165, 3), "bdf"), ((333, 211, 1), "bdf"), ((256, 64, 3), "b"), ((97, 131, 3), "df"),
+                                   ((640, 360, 1), "f"), ((64, 40, 3), "bd")]:
+            rng = np.random.default_rng(w * h + c)
+            shape = (h, w) if c == 1 else (h, w, c)
+            e2.set_geometry(w, h, c, np.uint16, 5)
+            mk = lambda lo, hi: rng.integers(lo, hi, shape).astype(np.uint16)
+            o_bias = o_dark = o_flat = None
+            if "b" in masters:
+                bias = [mk(300, 900) for _ in range(3)]
+                e2.build_master(B.BIAS, bias)
+                o_bias = oracle.stack_mean([oracle.u16_to_f32(f) for f in bias])
+            if "d" in masters:
+                dark = [mk(900, 3000) for _ in range(3)]
+                e2.build_master(B.DARK, dark)
+                o_dark = oracle.stack_mean([oracle.u16_to_f32(f) for f in dark], o_bias)
+            if "f" in masters:
+                flat = [mk(20000, 40000) for _ in range(3)]
+                if "b" in masters:  # one pixel whose flats equal the bias: master flat exactly 0 there (cv::divide gives 0)
+                    for f in flat:
+                        f.reshape(-1)[7] = 0
+                    for f in bias:
+                        f.reshape(-1)[7] = 0
+                e2.build_master(B.FLAT, flat)
+                o_flat = oracle.flat_normalize(oracle.stack_mean([oracle.u16_to_f32(f) for f in flat], o_bias))
+            lights = [mk(3000, 60000) for _ in range(5)]
+            e2.set_reference(lights[0], 20)
+            try:
+                e2.add_lights(lights)
+            except ob.OssError:
+                pass  # random frames: nothing aligns, which is not what this test is about
+            for i, f in enumerate(lights):
+                o_cal = oracle.calibrate(oracle.u16_to_f32(f), o_bias, o_dark, o_flat)
+                assert np.array_equal(bits(e2.debug_plane(0, i)), bits(o_cal)), (w, h, c, masters, i)
+                if c == 3:
+                    assert np.array_equal(bits(e2.debug_plane(1, i)), bits(oracle.gray(o_cal))), (w, h, c, masters, i)
+            e2.clear_masters()
+    finally:
+        e2.close()
+
+
 def test_masters_in_pieces_and_row_slices(eng):
     """oss_master_begin / add / end: (1) the whole master from chunks of frames equals oss_build_master's (the accumulation
     order is the frame order either way); (2) built as row slices [0, a) and [a, H) one after the other — what the ranks of
