@@ -157,16 +157,23 @@ class Inputs:
         return self.bias + self.darks + self.flats + [self.ref] + self.lights
 
 
+MASTERS = "auto"   # --masters: how N > 1 ranks get their masters (run_job)
+
+
 def run_job(eng, B, cal, ref, light_arr, nlights, mem, result_host, comm=None, rank=0, threshold=20):
     """One step.  cal = [(kind, ctypes pointer array, count)] in build order (bias, dark, flat).  With N > 1 every rank holds
     the calibration frames and accumulates ITS 1/N row slice of every master; the slices are exchanged over NVLink
     (bit-identical masters, 1/N of the calibration bytes read per rank).  Returns totalValidImages on rank 0
     (imagestacker.cpp:304,350), 0 elsewhere."""
     L, h = eng._L, eng._h
-    if comm:
+    # N > 1: calibration frames that come from the host are uploaded and accumulated as 1/N row slices per rank and the slices
+    # exchanged over NVLink (1/N of the PCIe bytes per rank); frames that are ALREADY resident in every rank's HBM are cheaper
+    # to accumulate whole on every rank (1.0 ms at 24 MP, what one GPU does anyway) than to all-gather (3 x 288 MB per rank).
+    sliced = bool(comm) and (MASTERS == "slices" or (MASTERS == "auto" and mem != B.DEVICE))
+    if sliced:
         row0, rows = eng.comm_master_slice()
     for kind, arr, n in cal:
-        if comm:
+        if sliced:
             eng._ck(L.oss_master_begin(h, kind, n, row0, rows))
             eng._ck(L.oss_master_add(h, arr, n, mem))
             eng._ck(L.oss_master_end(h))
@@ -409,8 +416,13 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-also", action="store_true", help="skip the short runs of the other configurations")
+    ap.add_argument("--masters", choices=["auto", "slices", "full"], default="auto",
+                    help="N > 1: masters as row slices + NVLink all-gather, accumulated whole on every rank, or auto "
+                         "(whole when the calibration frames are device-resident, slices when they come from the host)")
     ap.add_argument("--no-checks", action="store_true")
     a = ap.parse_args()
+    global MASTERS
+    MASTERS = a.masters
     a.warmup = max(a.warmup, 3) if a.impl != "reference" else a.warmup
 
     rank = int(os.environ.get("RANK", "0"))
@@ -434,8 +446,10 @@ def main():
               "frames_in_flight": cf["slots"], "pipelines": cf["pipes"],
               "e2e_frames_in_flight": a.e2e_slots, "e2e_pipelines": a.e2e_pipes,
               "l2": "inputs (%.1f GB per step) are far larger than L2" % ((lights_per_gpu + 1 + ncal_total) * W * H * C * 2 / 1e9),
-              "parallelism": (f"lights sharded over {world} GPUs, masters built in {world} row slices + NVLink all-gather, one ncclReduce of the "
-                              "f32 sum") if world > 1 else "1 GPU"}
+              "parallelism": (f"lights sharded over {world} GPUs; masters: " +
+                              ("every rank accumulates its resident calibration frames whole (device-resident run), " if a.masters != "slices" else "") +
+                              (f"{world} row slices + NVLink all-gather" + (" (host-fed run)" if a.masters == "auto" else "") + "; "
+                               if a.masters != "full" else "; ") + "one ncclReduce of the f32 sum") if world > 1 else "1 GPU"}
 
     # ------------------------------------------------------------------ reference arm (CPU only, nothing of ours loaded)
     if a.impl == "reference":
