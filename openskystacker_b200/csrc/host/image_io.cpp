@@ -243,7 +243,7 @@ bool open(const std::string &path, size_t limit, Reader *r, Ifd *d, ImageInfo *i
     if (r->buf.size() < 8) return fail(err, path + ": not a TIFF file");
     if (r->buf[0] == 'I' && r->buf[1] == 'I') r->big = false;
     else if (r->buf[0] == 'M' && r->buf[1] == 'M') r->big = true;
-    else return fail(err, path + ": not a TIFF, PNG or FITS file (JPEG and camera RAW decoding are not part of this build)");
+    else return fail(err, path + ": not a TIFF, PNG, JPEG or FITS file (camera RAW decoding is not part of this build)");
     if (!parseIfd(*r, d, err)) {
         if (limit) { // directory at the end of the file: read it all
             if (!loadFile(path, &r->buf, 0, err)) return false;
@@ -302,6 +302,7 @@ bool probeImage(const std::string &path, ImageInfo *info, std::string *err)
 {
     if (isFitsFile(path)) return probeFits(path, info, err);
     if (isPngFile(path)) return probePng(path, info, err);
+    if (isJpegFile(path)) return probeJpeg(path, info, err);
     Reader r;
     Ifd d;
     return open(path, 1 << 16, &r, &d, info, err);
@@ -311,6 +312,7 @@ bool readImageInto(const std::string &path, const ImageInfo &expect, void *dst, 
 {
     if (isFitsFile(path)) return readFitsInto(path, &expect, nullptr, dst, nullptr, err);
     if (isPngFile(path)) return readPngInto(path, &expect, nullptr, dst, nullptr, err);
+    if (isJpegFile(path)) return readJpegInto(path, &expect, nullptr, dst, nullptr, err);
     Reader r;
     Ifd d;
     ImageInfo info;
@@ -324,6 +326,7 @@ bool readImage(const std::string &path, ImageInfo *info, std::vector<uint8_t> *p
 {
     if (isFitsFile(path)) return readFitsInto(path, nullptr, info, nullptr, pixels, err);
     if (isPngFile(path)) return readPngInto(path, nullptr, info, nullptr, pixels, err);
+    if (isJpegFile(path)) return readJpegInto(path, nullptr, info, nullptr, pixels, err);
     Reader r;
     Ifd d;
     if (!open(path, 0, &r, &d, info, err)) return false;

@@ -1,7 +1,7 @@
 // Host-side image decode / encode for the ImageStacker facade (file codecs stay on the host,
 // as in the reference: readImage -> cv::imread, libstacker/src/util.cpp:277-298; cl/cl.cpp:205
 // cv::imwrite).  TIFF: baseline strips, 8/16-bit unsigned or 32-bit float samples, 1 or 3
-// channels, uncompressed, LZW or Deflate (+ horizontal predictor), either byte order.  PNG: png_io.cpp.  Frames come back
+// channels, uncompressed, LZW or Deflate (+ horizontal predictor), either byte order.  PNG: png_io.cpp, JPEG: jpeg_io.cpp.  Frames come back
 // interleaved HWC in cv::imread's channel order (B, G, R).  FITS (fits_io.cpp): the primary HDU's first plane, BITPIX 8 / 16 /
 // -32 / -64, like fitsToMat (util.cpp:300-346); recognised by content ("SIMPLE  ="), so all three entry points take either.
 #pragma once
@@ -36,6 +36,11 @@ bool isPngFile(const std::string &path);
 bool probePng(const std::string &path, ImageInfo *info, std::string *err);
 bool readPngInto(const std::string &path, const ImageInfo *expect, ImageInfo *info_out, void *dst, std::vector<uint8_t> *alloc,
                  std::string *err);
+// JPEG (jpeg_io.cpp): 8-bit baseline / progressive Huffman files, grey or YCbCr / RGB, EXIF orientation applied like cv::imread
+bool isJpegFile(const std::string &path);
+bool probeJpeg(const std::string &path, ImageInfo *info, std::string *err);
+bool readJpegInto(const std::string &path, const ImageInfo *expect, ImageInfo *info_out, void *dst, std::vector<uint8_t> *alloc,
+                  std::string *err);
 bool writeTiffU16(const std::string &path, const uint16_t *hwc_bgr, int width, int height, int channels, std::string *err);
 
 }  // namespace openskystacker

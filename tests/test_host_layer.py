@@ -127,6 +127,81 @@ def test_png_reader_matches_imread(host, tmp_path):
     assert np.array_equal(read_tiff(host, path), a)
 
 
+def _jpeg_test_image(rng, h, w, ch):
+    yy, xx = np.mgrid[0:h, 0:w]
+    base = 90 + 70 * np.sin(xx / 7.0) * np.cos(yy / 5.0)
+    if ch == 3:
+        base = np.stack([base, base[::-1] * 0.8 + 20, 255 - base], 2)
+    a = base + rng.normal(0, 12, base.shape)
+    for _ in range(6):   # hard edges: large coefficients, values the range limiter has to clip
+        y, x = rng.integers(0, h), rng.integers(0, w)
+        a[max(y - 1, 0):y + 2, max(x - 1, 0):x + 2] = rng.integers(0, 256)
+    return np.clip(a, 0, 255).astype(np.uint8)
+
+
+def test_jpeg_reader_matches_imread(host, tmp_path):
+    """The reference's own test stacks a directory of JPEGs through cv::imread (test/testoss.cpp:48, util.cpp:291-294).  The
+    facade's decoder (jpeg_io.cpp: Huffman baseline / progressive, islow inverse DCT, fancy upsampling, fixed-point YCbCr) must
+    return cv2.imread's pixels exactly: every chroma subsampling cv2 writes, grey, qualities 5..100, progressive, optimised
+    Huffman tables, restart intervals, frame sizes that are not MCU multiples (down to 1 x 1 and 2-sample chroma rows)."""
+    rng = np.random.default_rng(1)
+    sf = {"411": cv2.IMWRITE_JPEG_SAMPLING_FACTOR_411, "420": cv2.IMWRITE_JPEG_SAMPLING_FACTOR_420,
+          "422": cv2.IMWRITE_JPEG_SAMPLING_FACTOR_422, "440": cv2.IMWRITE_JPEG_SAMPLING_FACTOR_440,
+          "444": cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444}
+    n = 0
+    for (h, w) in [(41, 67), (1, 1), (7, 9), (16, 16), (3, 40), (17, 2), (33, 5), (131, 70)]:
+        for ch in (1, 3):
+            for q, (prog, opt, rst) in [(5, (0, 0, 0)), (50, (1, 0, 0)), (92, (0, 1, 3)), (100, (1, 1, 2))]:
+                for name in (["444"] if ch == 1 else list(sf)):
+                    a = _jpeg_test_image(rng, h, w, ch)
+                    path = str(tmp_path / f"t{n}.jpg")
+                    params = [cv2.IMWRITE_JPEG_QUALITY, q, cv2.IMWRITE_JPEG_PROGRESSIVE, prog, cv2.IMWRITE_JPEG_OPTIMIZE, opt,
+                              cv2.IMWRITE_JPEG_RST_INTERVAL, rst] + ([cv2.IMWRITE_JPEG_SAMPLING_FACTOR, sf[name]] if ch == 3 else [])
+                    assert cv2.imwrite(path, a, params)
+                    want = cv2.imread(path, cv2.IMREAD_ANYDEPTH | cv2.IMREAD_ANYCOLOR)   # util.cpp:292
+                    got = read_tiff(host, path)
+                    assert got.dtype == want.dtype and got.shape == want.shape and np.array_equal(got, want), (h, w, ch, q, name, prog, opt, rst)
+                    n += 1
+    assert n == 8 * (4 + 4 * 5)
+
+
+def test_jpeg_exif_orientation_and_refusals(host, tmp_path):
+    """cv::imread applies the EXIF orientation (the reference's flags do not include IMREAD_IGNORE_ORIENTATION): all eight
+    values, both TIFF byte orders, width / height swapped in the probe for the transposing ones.  CMYK files and files that
+    only look like JPEG are refused with a message instead of decoded wrongly."""
+    import struct
+    rng = np.random.default_rng(2)
+    for ch in (1, 3):
+        a = _jpeg_test_image(rng, 37, 58, ch)
+        path = str(tmp_path / f"e{ch}.jpg")
+        assert cv2.imwrite(path, a, [cv2.IMWRITE_JPEG_QUALITY, 90])
+        plain = open(path, "rb").read()
+        for o in range(1, 9):
+            for big in (False, True):
+                e = ">" if big else "<"
+                tiff = (b"MM\0*" if big else b"II*\0") + struct.pack(e + "I", 8) + struct.pack(e + "H", 1) + \
+                    struct.pack(e + "HHIHH", 0x0112, 3, 1, o, 0) + struct.pack(e + "I", 0)
+                seg = b"Exif\0\0" + tiff
+                p2 = str(tmp_path / f"e{ch}_{o}{int(big)}.jpg")
+                open(p2, "wb").write(plain[:2] + b"\xff\xe1" + struct.pack(">H", len(seg) + 2) + seg + plain[2:])
+                want = cv2.imread(p2, cv2.IMREAD_ANYDEPTH | cv2.IMREAD_ANYCOLOR)
+                got = read_tiff(host, p2)
+                assert got.shape == want.shape and np.array_equal(got, want), (ch, o, big)
+                assert (got.shape[0] == 58) == (o >= 5)
+    whcs = (C.c_int * 4)()
+    err = C.create_string_buffer(256)
+    try:
+        from PIL import Image
+        Image.fromarray(_jpeg_test_image(rng, 40, 40, 3)).convert("CMYK").save(str(tmp_path / "cmyk.jpg"))
+        assert host.oss_host_probe_image(str(tmp_path / "cmyk.jpg").encode(), whcs, err, 256) != 0 and b"CMYK" in err.value
+    except ImportError:
+        pass
+    open(str(tmp_path / "trunc.jpg"), "wb").write(plain[:len(plain) // 2])   # half a file: decodes (zeros after the cut), like libjpeg
+    assert host.oss_host_probe_image(str(tmp_path / "trunc.jpg").encode(), whcs, err, 256) == 0
+    open(str(tmp_path / "junk.jpg"), "wb").write(b"\xff\xd8\xff\xe0" + b"\0" * 40)
+    assert host.oss_host_probe_image(str(tmp_path / "junk.jpg").encode(), whcs, err, 256) != 0
+
+
 def test_gui_output_path_writes_mono_as_16_bit(host, tmp_path):
     """MainWindow::finishedStacking (openskystacker/ui/mainwindow.cpp:91-101): a single-channel stack goes through
     convertTo(CV_16U, 65535) before imwrite, a colour one is written as float32."""
@@ -341,6 +416,37 @@ def write_fits(path, data, bitpix, bzero=None, extra_axis=None):
     body += b"\0" * (-len(body) % 2880)
     with open(path, "wb") as f:
         f.write(head + body)
+
+
+@pytest.mark.gpu
+def test_cli_stacks_jpeg_lights_like_the_same_pixels_from_tiff(host, tmp_path):
+    """A stack whose frames are 8-bit JPEG files (the reference's test data, test/testoss.cpp:48) against the stack of the very
+    same pixels — cv2.imread of those files — stored as lossless 8-bit TIFF: identical output file, bit for bit."""
+    w, h = 800, 600
+    ds = synth.dataset(w, h, 4, 3, nstars=100, ndarks=2, seed=9)
+    to8 = lambda f: (f >> 8).astype(np.uint8)
+    dj, dt = tmp_path / "jpg", tmp_path / "tif"
+    dj.mkdir(); dt.mkdir()
+    lists = []
+    for d, ext in ((dj, ".jpg"), (dt, ".tif")):
+        entries = []
+        for name, frame, kind in [("ref", ds["ref"], "ref")] + [(f"light{i}", f, "light") for i, f in enumerate(ds["lights"])] + \
+                [(f"dark{i}", f, "dark") for i, f in enumerate(ds["darks"])]:
+            if ext == ".jpg":
+                assert cv2.imwrite(str(d / (name + ext)), to8(frame), [cv2.IMWRITE_JPEG_QUALITY, 97])
+            else:
+                px = cv2.imread(str(dj / (name + ".jpg")), cv2.IMREAD_ANYDEPTH | cv2.IMREAD_ANYCOLOR)
+                assert px.dtype == np.uint8 and cv2.imwrite(str(d / (name + ext)), px)
+            entries.append({"filename": name + ext, "type": kind, "checked": True})
+        lists.append(write_list(d, entries))
+    outs = []
+    for lst, d in zip(lists, (dj, dt)):
+        out = str(d / "stack")
+        r = subprocess.run([CLI, "-f", lst, "-o", out, "-t", "20", "-j", "3"], capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout + r.stderr
+        outs.append(cv2.imread(out + ".tif", cv2.IMREAD_ANYDEPTH | cv2.IMREAD_ANYCOLOR))
+    assert outs[0].dtype == np.float32 and outs[0].shape == (h, w, 3)
+    assert np.array_equal(outs[0].view(np.uint32), outs[1].view(np.uint32))
 
 
 def test_fits_reader_follows_fitsToMat(host, tmp_path):
