@@ -268,6 +268,27 @@ def reference_arm(a, cf, cores, config):
                       "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
+def balance_host_fed(rates, extras, total):
+    """Lights per rank for the host-fed run: rank r copies (n_r + extras[r]) frames at rates[r] (measured with every rank copying
+    at once); equal finishing times T mean n_r + extras[r] = T * rates[r] with sum(n_r) = total.  Largest-remainder rounding,
+    every rank keeps at least one light.  (The reference's static stride, util.cpp:738, assumes equal workers; the host links of
+    an 8-GPU box are not equal: GPUs on the far socket get ~2/3 of the near ones' host bandwidth when all copy at once.)"""
+    T = (total + sum(extras)) / sum(rates)
+    want = [max(1.0, T * r - e) for r, e in zip(rates, extras)]
+    scale = total / sum(want)
+    want = [w * scale for w in want]
+    n = [max(1, int(w)) for w in want]
+    order = sorted(range(len(n)), key=lambda i: want[i] - int(want[i]), reverse=True)
+    i = 0
+    while sum(n) < total:
+        n[order[i % len(n)]] += 1
+        i += 1
+    while sum(n) > total:
+        j = max(range(len(n)), key=lambda k: n[k])
+        n[j] -= 1
+    return n
+
+
 class Job:
     """One configuration on this rank: engine geometry, device-resident inputs, the step function."""
 
@@ -294,10 +315,11 @@ class Job:
         self.lights = arr(self.inp.lights)
         self.tv = []
 
-    def step(self, mem=None, cal=None, ref=None, lights=None, result_host=None, comm="same"):
+    def step(self, mem=None, cal=None, ref=None, lights=None, result_host=None, comm="same", nlights=None):
         B = self.B
         tv = run_job(self.eng, B, cal if cal is not None else self.cal, ref if ref is not None else Ct.c_void_p(self.inp.ref),
-                     lights if lights is not None else self.lights, self.nl, B.DEVICE if mem is None else mem, result_host,
+                     lights if lights is not None else self.lights, self.nl if nlights is None else nlights,
+                     B.DEVICE if mem is None else mem, result_host,
                      self.comm if comm == "same" else comm, self.rank, self.cf["threshold"])
         self.tv.append(tv)
         return tv
@@ -412,6 +434,8 @@ def main():
     ap.add_argument("--pipes", type=int, default=0, help="pipelines, device-resident run")
     ap.add_argument("--e2e-slots", type=int, default=5, help="frames in flight for the host-fed run (shorter drain after the last H2D copy)")
     ap.add_argument("--e2e-pipes", type=int, default=3)
+    ap.add_argument("--e2e-balance", choices=["auto", "off"], default="auto",
+                    help="N > 1, host-fed run: lights per rank in proportion to the rank's measured host link rate (off: equal shares)")
     ap.add_argument("--cpu-lights", type=int, default=0, help="lights in the CPU sample (0 = host cores)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -523,22 +547,76 @@ def main():
             host[p] = hp
         hp_arr = lambda ps: (Ct.c_void_p * len(ps))(*[host[p] for p in ps])
         cal_h = [(k, hp_arr(ps), len(ps)) for k, ps in ((B.BIAS, inp.bias), (B.DARK, inp.darks), (B.FLAT, inp.flats)) if ps]
-        lights_h = hp_arr(inp.lights)
         res_host = L.oss_host_alloc(W * H * C * 4) if rank == 0 else None
+        # N > 1: lights per rank in proportion to what each rank's host link delivers while EVERY rank is copying (balance_host_fed)
+        nl_e2e, light_ptrs, balance = nl, [host[p] for p in inp.lights], None
+        if world > 1 and a.e2e_balance == "auto":
+            import torch
+            probe = [host[p] for p in inp.lights[:8]]
+            job.barrier()
+            t0, moved = time.perf_counter(), 0
+            while time.perf_counter() - t0 < 0.4:      # pinned host -> the device buffer the frame came from (same bytes back)
+                src = inp.lights[(moved // nb) % len(probe)]
+                eng._ck(L.oss_memcpy_h2d(eng._h, src, host[src], nb))
+                moved += nb
+            rate = moved / (time.perf_counter() - t0) / 1e9
+            t = torch.zeros(world, dtype=torch.float64, device="cuda")
+            t[rank] = rate
+            dist.all_reduce(t)
+            rates = t.cpu().tolist()
+            if os.environ.get("OSS_BENCH_RATES"):      # dev aid: exercise an unequal split on a box with equal links
+                rates = [float(x) for x in os.environ["OSS_BENCH_RATES"].split(",")][:world]
+            extras = [ncal_total / world + (1 if r == 0 else 0) for r in range(world)]
+            counts = balance_host_fed(rates, extras, job.total_lights)
+            all_idx = list(range(1, 1 + job.total_lights))
+            off = sum(counts[:rank])
+            mine = all_idx[off:off + counts[rank]]
+            have = dict(zip(job.my, inp.lights))
+            scratch, light_ptrs = None, []
+            for idx in mine:
+                if idx in have:
+                    light_ptrs.append(host[have[idx]])
+                    continue
+                if scratch is None:
+                    scratch = eng.device_alloc(nb)
+                eng.synth_light(scratch, star_motion(inp.field, idx, W, H), pedestal_adu=inp.pedestal, vignette=inp.vignette, seed=1000 + idx)
+                hp = L.oss_host_alloc(nb)
+                if not hp:
+                    raise SystemExit("pinned allocation failed")
+                eng._ck(L.oss_memcpy_d2h(eng._h, hp, scratch, nb))
+                host[("extra", idx)] = hp
+                light_ptrs.append(hp)
+            if scratch is not None:
+                eng.device_free(scratch)
+            nl_e2e = len(mine)
+            balance = {"lights_per_rank": counts, "h2d_gbs_per_rank_all_copying": [round(r, 1) for r in rates],
+                       "note": "host-fed run only: lights per rank in proportion to the rank's measured host -> device rate while every "
+                               "rank copies (0.4 s probe outside the timed region); the device-resident run keeps lights_per_gpu on every rank"}
+        lights_h = (Ct.c_void_p * len(light_ptrs))(*light_ptrs)
         if (a.e2e_slots, a.e2e_pipes) != (job.slots, job.pipes):
             eng.set_pipelines(a.e2e_pipes)
             eng.set_geometry(W, H, C, np.uint16, a.e2e_slots)
-        step_host = lambda: job.step(B.HOST, cal_h, Ct.c_void_p(host[inp.ref]), lights_h, Ct.c_void_p(res_host) if rank == 0 else None)
+        step_host = lambda: job.step(B.HOST, cal_h, Ct.c_void_p(host[inp.ref]), lights_h, Ct.c_void_p(res_host) if rank == 0 else None,
+                                     nlights=nl_e2e)
         job.timed(step_host, 1)
         t_host = job.timed(step_host, max(1, min(a.steps, 3)))
         _, tv_e2e = job.expect_valid("e2e")
         if rank == 0 and tv_e2e != tv_timed:
             raise SystemExit(f"bench invalid: host-fed run stacked {tv_e2e} frames, device-resident run {tv_timed}")
         wall_s = float(np.mean([t[1] for t in t_host]))
-        h2d = (nl + (1 if rank == 0 else 0) + ncal_total / world) * nb   # every rank uploads its 1/N row slice of each calibration frame
+        h2d = (nl_e2e + (1 if rank == 0 else 0) + ncal_total / world) * nb   # every rank uploads its 1/N row slice of each calibration frame
         e2e = {"value": frames_total / wall_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(W * H * C * 4), "ms_per_step": 1e3 * wall_s,
                "timing": "wall clock between stream syncs (covers H2D, kernels, D2H of the float32 stack)"}
+        if world > 1:
+            e2e["h2d_bytes_per_step_all_ranks"] = int((job.total_lights + 1 + ncal_total) * nb)
+            e2e["h2d_bytes_per_step_note"] = "h2d_bytes_per_step is rank 0's share"
+        if balance:
+            e2e["balance"] = balance
+        if rank == 0 and res_n is not None:
+            # the host-fed stack against the device-resident one of the same lights (another split over the ranks: fp32 sum order)
+            got = np.ctypeslib.as_array(Ct.cast(res_host, Ct.POINTER(Ct.c_float)), shape=(H * W * C,)).reshape(res_n.shape)
+            e2e["result_vs_device_resident_maxabs"] = float(np.max(np.abs(got - res_n)))
         for hp in host.values():
             L.oss_host_free(hp)
         if res_host:
