@@ -1,7 +1,7 @@
 // openskystacker-cl without Qt: same flags, same stdout as cl/cl.cpp:63-225.
 //   -f <list.json>  -s  -o <output>  -t <threshold 1-100, default 20>  -j <threads, default 1>  -v
 // Extra (not in the reference): --device N, --devices a,b,c | all (the lights are sharded over these GPUs, light k -> GPU k % N like
-// the reference's -j workers, util.cpp:738; masters in row slices, one NCCL reduce), --mono16 (write a single-channel
+// the reference's -j workers, util.cpp:738; masters in row slices, one NCCL reduce), --balance (lights from one shared queue), --mono16 (write a single-channel
 // result as 16-bit like the GUI does, openskystacker/ui/mainwindow.cpp:91-101).
 #include <cstdio>
 #include <cstdlib>
@@ -28,6 +28,8 @@ static void usage(int code)
            "  --device <n>    CUDA device to run on. Default: 0\n"
            "  --devices <l>   Comma-separated CUDA devices (or 'all') to shard the\n"
            "                  light frames over.\n"
+           "  --balance       With several devices: lights from one shared queue\n"
+           "                  instead of light k -> device k mod N (unequal host links).\n"
            "  --mono16        Write a single-channel result as a 16-bit TIFF, like\n"
            "                  the GUI does.\n");
     exit(code);
@@ -36,7 +38,7 @@ static void usage(int code)
 int main(int argc, char **argv)
 {
     std::string listFile, output, thresholdArg = "20", threadsArg = "1";
-    bool detect = false, verbose = false, haveList = false, haveOutput = false, mono16 = false;
+    bool detect = false, verbose = false, haveList = false, haveOutput = false, mono16 = false, balance = false;
     int device = 0;
     std::string devicesArg;
     for (int i = 1; i < argc; i++) {
@@ -52,6 +54,7 @@ int main(int argc, char **argv)
         else if (a == "--device") device = atoi(value().c_str());
         else if (a == "--devices") devicesArg = value();
         else if (a == "--mono16") mono16 = true;
+        else if (a == "--balance") balance = true;
         else { printf("Unknown option '%s'.\n", a.c_str()); usage(1); }
     }
     if (!haveList) { printf("Error: Must specify an image list\n\n"); usage(1); }
@@ -84,6 +87,7 @@ int main(int argc, char **argv)
     }
     ImageStacker stacker(devices.empty() ? device : devices[0]);
     if (!devices.empty()) stacker.setDevices(devices);
+    stacker.setDynamicSharding(balance);
     std::string ref;
     std::vector<std::string> lights, darks, darkFlats, flats, bias;
     bool referenceSet = false;

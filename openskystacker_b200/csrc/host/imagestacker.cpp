@@ -25,6 +25,7 @@ public:
     std::vector<oss_ctx *> ctxs;         // one per entry of `devices`
     int ctx_device[64] = {};
     bool comm_ready = false;             // the contexts share an NCCL communicator
+    bool dynamic_sharding = false;       // lights from one shared queue instead of light k -> GPU k % N
     std::atomic<int> lightsDone{0};
     std::string lastCapacityError;
     mutable std::mutex mutex; // the reference guards every accessor with a QMutex (imagestacker.cpp:591-786)
@@ -115,6 +116,8 @@ void ImageStacker::setDevices(const std::vector<int> &devices)
     d_ptr->devices = devices;
     if (d_ptr->devices.size() > 64) d_ptr->devices.resize(64);
 }
+void ImageStacker::setDynamicSharding(bool on) { std::lock_guard<std::mutex> lk(d_ptr->mutex); d_ptr->dynamic_sharding = on; }
+bool ImageStacker::getDynamicSharding() const { std::lock_guard<std::mutex> lk(d_ptr->mutex); return d_ptr->dynamic_sharding; }
 std::vector<int> ImageStacker::getDevices() const
 {
     std::lock_guard<std::mutex> lk(d_ptr->mutex);
@@ -261,7 +264,11 @@ void ImageStacker::process(int tolerance, int threads)
     const std::vector<std::string> &lights = d->targetImageFileNames;
 
     // ---- one attempt at the whole stack with a given detection work space; OSS_E_CAPACITY asks for a larger one
+    const bool dynamic = d->dynamic_sharding && N > 1;
+    std::vector<std::vector<size_t>> takenIdx(N); // list positions of the lights each GPU processed, in its own order
     auto attempt = [&](int capacity_one_in, Image *out, int *valid_out, std::vector<std::vector<LightReport>> *reps) -> int {
+        std::vector<std::vector<size_t>> *taken = &takenIdx;
+        std::atomic<size_t> next_light{0};
         std::atomic<int> status(0);
         std::string first_error;
         std::mutex emu;
@@ -374,12 +381,21 @@ void ImageStacker::process(int tolerance, int threads)
             bar.wait();
             if (status) return;
             if (N > 1) ok = ck(oss_comm_broadcast_reference(ctx, 0, tolerance));
-            // ---- lights r, r + N, r + 2N, ... (util.cpp:738), two pinned sets: decode(b + 1) overlaps copy + compute of b
+            // ---- lights r, r + N, r + 2N, ... (util.cpp:738) or, with dynamic sharding, the next `slots` lights of the shared
+            // queue whenever this GPU is ready for more; two pinned sets: decode(b + 1) overlaps copy + compute of b
             std::vector<std::string> mine;
-            for (size_t k = (size_t)r; k < lights.size(); k += (size_t)N) mine.push_back(lights[k]);
+            std::vector<size_t> &mineIdx = (*taken)[r];
+            mineIdx.clear();
+            if (!dynamic)
+                for (size_t k = (size_t)r; k < lights.size(); k += (size_t)N) { mine.push_back(lights[k]); mineIdx.push_back(k); }
             size_t done = 0;
             int set = 0;
-            while (ok && done < mine.size() && !status) {
+            while (ok && !status) {
+                if (dynamic) {
+                    const size_t first = next_light.fetch_add((size_t)slots);
+                    for (size_t k = first; k < std::min(lights.size(), first + (size_t)slots); k++) { mine.push_back(lights[k]); mineIdx.push_back(k); }
+                }
+                if (done >= mine.size()) break;
                 const size_t nb = std::min<size_t>((size_t)slots, mine.size() - done);
                 std::string e;
                 if (!decodeMany(mine, done, nb, ref, stage[r][set].data(), workers_per_dev, &e)) { fail(OSS_E_ARG, e); ok = false; break; }
@@ -454,7 +470,7 @@ void ImageStacker::process(int tolerance, int threads)
         d->reports.assign(lights.size(), LightReport{0, 0, -1, {}, 0});
         for (int r = 0; r < N; r++)
             for (size_t i = 0; i < reps[r].size(); i++)
-                if ((size_t)r + i * (size_t)N < lights.size()) d->reports[(size_t)r + i * (size_t)N] = reps[r][i]; // back to list order
+                if (i < takenIdx[r].size() && takenIdx[r][i] < lights.size()) d->reports[takenIdx[r][i]] = reps[r][i]; // back to list order
     }
     d->releasePinned();
     if (st) return; // OSS_E_NO_ALIGNED carries the reference's text (imagestacker.cpp:355-359)

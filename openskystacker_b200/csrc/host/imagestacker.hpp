@@ -53,6 +53,13 @@ public:
     // split over its -j worker threads, util.cpp:738); default: the constructor's device alone
     void setDevices(const std::vector<int> &devices);
     std::vector<int> getDevices() const;
+    // not in the reference: with several GPUs, hand the lights out from ONE shared queue (each GPU thread takes the next
+    // batch when its pinned set is free) instead of the static stride: the host links of a multi-GPU box are not equal (GPUs
+    // on the far socket copy at ~2/3 of the rate of the near ones when all copy at once) and a static split waits for the
+    // slowest.  The per-GPU order of additions then depends on timing: the stack is reproducible to float reassociation
+    // (1e-6 of full scale) instead of bit for bit; reports stay in list order.  Default: off (the reference's split).
+    void setDynamicSharding(bool on);
+    bool getDynamicSharding() const;
 
     // get/set — imagestacker.h:38-78
     std::string getRefImageFileName() const;

@@ -390,6 +390,7 @@ def test_cli_shards_the_lights_over_two_gpus(host, tmp_path):
     out = str(tmp_path / "stack2")
     r = subprocess.run([CLI, "-f", lst, "-o", out, "-t", "20", "-j", "8", "--devices", "0,1", "-v"], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
+    r0_stdout = r.stdout
     got = cv2.imread(out + ".tif", cv2.IMREAD_ANYDEPTH | cv2.IMREAD_ANYCOLOR)
     assert got.shape == want["image"].shape and float(np.max(np.abs(got - want["image"]))) <= 1e-6
     one = str(tmp_path / "stack1")
@@ -397,6 +398,14 @@ def test_cli_shards_the_lights_over_two_gpus(host, tmp_path):
     assert r.returncode == 0, r.stdout + r.stderr
     got_all = cv2.imread(one + ".tif", cv2.IMREAD_ANYDEPTH | cv2.IMREAD_ANYCOLOR)
     assert float(np.max(np.abs(got_all - want["image"]))) <= 1e-6
+    # --balance: the lights come from one shared queue (which GPU takes which batch depends on timing): same stack up to
+    # the order of the float additions
+    bal = str(tmp_path / "stack_bal")
+    rb = subprocess.run([CLI, "-f", lst, "-o", bal, "-t", "20", "-j", "8", "--devices", "0,1", "--balance", "-v"], capture_output=True, text=True)
+    assert rb.returncode == 0, rb.stdout + rb.stderr
+    got_bal = cv2.imread(bal + ".tif", cv2.IMREAD_ANYDEPTH | cv2.IMREAD_ANYCOLOR)
+    assert float(np.max(np.abs(got_bal - want["image"]))) <= 1e-6
+    assert rb.stdout.splitlines()[-1] == r0_stdout.splitlines()[-1].replace("stack2", "stack_bal")  # "File saved to ..."
 
 
 # ---- FITS (fitsToMat, libstacker/src/util.cpp:300-346) -----------------------------------------------------------------
