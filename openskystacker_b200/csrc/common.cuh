@@ -41,7 +41,7 @@ struct DetectState {
     int ncomp;   // components with peak > minPeak
     int nstars;
     int overflow;
-    int pad;
+    int nbig;    // components handed to k_components_big (more than CW_CAP pixels, below the deblender bypass)
 };
 
 // Result of the alignment kernel for one light.

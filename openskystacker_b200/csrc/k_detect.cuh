@@ -565,7 +565,7 @@ __global__ void __launch_bounds__(32 * CW_WARPS)
 k_components(const int *__restrict__ cand_idx, const float *__restrict__ cand_val, const int4 *__restrict__ nbr,
              int *__restrict__ owner, const int *__restrict__ comp_size, const int *__restrict__ comp_root,
              const int *__restrict__ comp_off, int *__restrict__ comp_nstar, int *__restrict__ scratch,
-             oss_star *__restrict__ star_tmp, const DetectState *__restrict__ ds, Geom g)
+             oss_star *__restrict__ star_tmp, DetectState *__restrict__ ds, Geom g)
 {
     extern __shared__ __align__(16) unsigned char comp_smem_raw[];
     const int f = blockIdx.y;
@@ -586,7 +586,11 @@ k_components(const int *__restrict__ cand_idx, const float *__restrict__ cand_va
         const int n = comp_size[fb + root];
         const int off = comp_off[fb + c];
         oss_star *out = star_tmp + fb + off;
-        if (n > CW_CAP) { // rare: one lane replays it over global memory
+        if (n > CW_CAP && n < OSS_DEBLEND_MAX) { // k_components_big: one CTA per component (queued after this kernel)
+            if (lane == 0) scr[11ll * g.cap + atomicAdd(&ds[f].nbig, 1)] = c; // [11 cap, 12 cap) of the scratch is nobody's
+            continue;
+        }
+        if (n > CW_CAP) { // the deblender bypass (>= 10000 px, adjoiningpixel.cpp:45-48): one lane replays the DFS over global memory
             int nout = 0;
             if (lane == 0) nout = component_serial(c, fb, cidx, cval, nb, own, comp_size, comp_root, comp_off, scr, star_tmp, step, g);
             if (lane == 0) comp_nstar[fb + c] = nout;
@@ -724,6 +728,280 @@ k_components(const int *__restrict__ cand_idx, const float *__restrict__ cand_va
         }
         if (lane == 0) comp_nstar[fb + c] = nout;
         __syncwarp();
+    }
+}
+
+// ---- K6b  one CTA per LARGE component (CW_CAP < n < OSS_DEBLEND_MAX) ----------------------------------------------------------
+// Same algorithm and orders as k_components, for the components its per-warp scratch cannot hold (a saturated star with its
+// halo, a galaxy core: hundreds to thousands of pixels).  One thread replaying such a component over global memory costs
+// ~1 us per pixel and peel iteration (37 ms for one 1400-px blob, tools/big_blob_probe.py); here
+//   in shared memory, sequential on thread 0 (their ORDER is the result): the DFS of detectAdjoiningPixel and the
+//     deblender's extract() — value, neighbour links (up / down as local indices, left / right are k -+ 1 in raster order),
+//     a state byte and the DFS stack (4 n + 4 entries: the reference's recursion pushes duplicates);
+//   parallel over the CTA: staging (bitonic sort of the member list back to raster order, links by binary search), getPeak
+//     (maximum, ties to the earlier DFS position), isAdjoining stamps, the blending test, createStar's (value, extraction
+//     order) ranking;
+//   fp chains on lanes 0..3 of warp 0 in the reference's operation order, their operands gathered 32 at a time by the whole
+//     warp (coordinates live in global scratch) and handed over by shuffles, the next 32 in flight meanwhile.
+// CB = capacity in pixels: two instances, 2048 (43 KB of shared memory: several CTAs per SM) and OSS_DEBLEND_MAX - 1
+// (210 KB: one CTA per SM, like k_focas); a CTA skips the list entries of the other instance.
+#define CBIG_NT 256
+constexpr int kCompBigSmall = 2048;
+template <int CB> struct CompBigSmem {
+    float val[CB];
+    short up[CB], dn[CB];
+    short lpos[CB];              // position in the reference's DFS list (getPeak's tie-break)
+    short S[CB];                 // region being peeled, extraction order
+    short stack[4 * CB + 8];     // DFS stack; staging: the member list (int, padded to a power of two); createStar: values + ranks
+    unsigned char st[CB];        // bits 0-1: 0 unvisited, 1 remaining, 2 dropped, 3 accepted; bit 2: left neighbour, bit 3: right
+    float red_v[CBIG_NT / 32];
+    int red_p[CBIG_NT / 32];
+    int bc[4];
+};
+
+template <int CB>
+__global__ void __launch_bounds__(CBIG_NT)
+k_components_big(const int *__restrict__ cand_idx, const float *__restrict__ cand_val, const int4 *__restrict__ nbr,
+                 const int *__restrict__ comp_size, const int *__restrict__ comp_root, const int *__restrict__ comp_off,
+                 int *__restrict__ comp_nstar, int *__restrict__ scratch, oss_star *__restrict__ star_tmp,
+                 const DetectState *__restrict__ ds, int nframes, int lo_excl, Geom g)
+{
+    extern __shared__ __align__(16) unsigned char comp_smem_raw[];
+    CompBigSmem<CB> &sm = *reinterpret_cast<CompBigSmem<CB> *>(comp_smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    int item = 0; // running index over (frame, list entry) pairs of THIS instance's size class
+    for (int f = 0; f < nframes; f++) {
+        if (ds[f].overflow) continue;
+        const int nbig = ds[f].nbig;
+        const long long fb = (long long)f * g.cap;
+        int *scr = scratch + 12 * fb;
+        const int *big_list = scr + 11ll * g.cap;
+        const float step = ds[f].threshold;
+        for (int e = 0; e < nbig; e++) {
+            const int c = big_list[e];
+            const int n = comp_size[fb + comp_root[fb + c]];
+            if (n <= lo_excl || n > CB) continue;
+            if ((item++) % (int)gridDim.x != (int)blockIdx.x) continue;
+            const int off = comp_off[fb + c];
+            const int *member = scr + off;                        // unordered (k_comp_members)
+            int *reg = scr + g.cap + off;                         // accepted region of a pixel
+            int *px = scr + 2ll * g.cap + off, *py = scr + 6ll * g.cap + 4ll * off + c;
+            int *acc_gx = scr + 3ll * g.cap + off, *acc_gy = scr + 4ll * g.cap + off, *stamp = scr + 5ll * g.cap + off;
+            oss_star *out = star_tmp + fb + off;
+            __syncthreads(); // the previous component's shared memory is dead
+            // ---- stage: member list -> ascending (raster order), bitonic sort of ints padded with INT_MAX
+            int *A = reinterpret_cast<int *>(sm.stack);
+            int N = 2;
+            while (N < n) N <<= 1;
+            for (int k = tid; k < N; k += CBIG_NT) A[k] = k < n ? member[k] : 0x7fffffff;
+            __syncthreads();
+            for (int k2 = 2; k2 <= N; k2 <<= 1)
+                for (int j = k2 >> 1; j > 0; j >>= 1) {
+                    for (int t = tid; t < (N >> 1); t += CBIG_NT) {
+                        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), l = i | j;
+                        const int a = A[i], b = A[l];
+                        if ((a > b) == ((i & k2) == 0)) { A[i] = b; A[l] = a; }
+                    }
+                    __syncthreads();
+                }
+            for (int k = tid; k < n; k += CBIG_NT) {
+                const int i = A[k];
+                sm.val[k] = cand_val[fb + i];
+                const int lin = cand_idx[fb + i];
+                const int y = lin / g.W;
+                py[k] = y;
+                px[k] = lin - y * g.W;
+                const int4 q = nbr[fb + i];
+                auto local = [&](int gl) {
+                    if (gl < 0) return -1;
+                    int lo = 0, hi = n - 1;
+                    while (lo < hi) { const int mid = (lo + hi) >> 1; if (A[mid] < gl) lo = mid + 1; else hi = mid; }
+                    return lo;
+                };
+                sm.up[k] = (short)local(q.x);
+                sm.dn[k] = (short)local(q.w);
+                // a left / right neighbour above the threshold is the previous / next entry of the raster-ordered candidate
+                // list and of this component's member list
+                sm.st[k] = (unsigned char)((q.y >= 0 ? 4 : 0) | (q.z >= 0 ? 8 : 0));
+            }
+            __syncthreads(); // A (aliases the stack) is dead from here on
+            // ---- detectAdjoiningPixel: explicit-stack DFS from the raster-first pixel, push order up, left, right, down
+            if (tid == 0) {
+                int np = 0, sp = 0;
+                sm.stack[sp++] = 0;
+                while (sp > 0) {
+                    const int i = sm.stack[--sp];
+                    const unsigned char s0 = sm.st[i];
+                    if (s0 & 3) continue;
+                    sm.st[i] = s0 | 1; // REMAINING
+                    sm.lpos[i] = (short)np++;
+                    const int u = sm.up[i], d = sm.dn[i];
+                    if (u >= 0 && !(sm.st[u] & 3)) sm.stack[sp++] = (short)u;
+                    if ((s0 & 4) && !(sm.st[i - 1] & 3)) sm.stack[sp++] = (short)(i - 1);
+                    if ((s0 & 8) && !(sm.st[i + 1] & 3)) sm.stack[sp++] = (short)(i + 1);
+                    if (d >= 0 && !(sm.st[d] & 3)) sm.stack[sp++] = (short)d;
+                }
+            }
+            __syncthreads();
+            // ---- AdjoiningPixel::deblend (adjoiningpixel.cpp:41-102)
+            int left = n, nacc = 0, iter = 0, nout = 0;
+            while (left > 0) {
+                iter++;
+                // getPeak: the maximum among the remaining pixels, ties to the earlier DFS position
+                float mx = 0.f;
+                int pos = 0x7fffffff, pk = -1;
+                for (int k = tid; k < n; k += CBIG_NT) {
+                    if ((sm.st[k] & 3) != 1) continue;
+                    const float v = sm.val[k];
+                    const int lp = sm.lpos[k];
+                    if (pos == 0x7fffffff || mx < v || (v == mx && lp < pos)) { mx = v; pos = lp; pk = k; }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const float v2 = __shfl_xor_sync(0xffffffffu, mx, o);
+                    const int p2 = __shfl_xor_sync(0xffffffffu, pos, o), k2 = __shfl_xor_sync(0xffffffffu, pk, o);
+                    if (p2 != 0x7fffffff && (pos == 0x7fffffff || mx < v2 || (v2 == mx && p2 < pos))) { mx = v2; pos = p2; pk = k2; }
+                }
+                if (lane == 0) { sm.red_v[wid] = mx; sm.red_p[wid] = pos == 0x7fffffff ? -1 : (pos | (pk << 16)); }
+                __syncthreads();
+                mx = 0.f; pos = 0x7fffffff; pk = -1;
+#pragma unroll
+                for (int w2 = 0; w2 < CBIG_NT / 32; w2++) {
+                    const int pp = sm.red_p[w2];
+                    if (pp < 0) continue;
+                    const float v2 = sm.red_v[w2];
+                    const int p2 = pp & 0xffff;
+                    if (pos == 0x7fffffff || mx < v2 || (v2 == mx && p2 < pos)) { mx = v2; pos = p2; pk = pp >> 16; }
+                }
+                if (pk < 0) break;
+                const float T = (float)__dsub_rn((double)mx, __dmul_rn((double)step, sqrt(__dadd_rn((double)__fdiv_rn(mx, step), 1.0)))); // adjoiningpixel.cpp:57
+                // extract(): recursive pre-order up, left, right, down == stack with reversed pushes
+                if (tid == 0) {
+                    int ns0 = 0, sp = 0;
+                    sm.stack[sp++] = (short)pk;
+                    while (sp > 0) {
+                        const int i = sm.stack[--sp];
+                        const unsigned char s0 = sm.st[i];
+                        if ((s0 & 3) != 1 || !(sm.val[i] > T)) continue;
+                        sm.st[i] = (s0 & ~3) | 2; // DROPPED unless accepted below
+                        sm.S[ns0++] = (short)i;
+                        const int u = sm.up[i], d = sm.dn[i];
+                        if (d >= 0 && (sm.st[d] & 3) == 1) sm.stack[sp++] = (short)d;
+                        if ((s0 & 8) && (sm.st[i + 1] & 3) == 1) sm.stack[sp++] = (short)(i + 1);
+                        if ((s0 & 4) && (sm.st[i - 1] & 3) == 1) sm.stack[sp++] = (short)(i - 1);
+                        if (u >= 0 && (sm.st[u] & 3) == 1) sm.stack[sp++] = (short)u;
+                    }
+                    sm.bc[0] = ns0;
+                }
+                __syncthreads();
+                const int ns = sm.bc[0];
+                if (ns == 0) break; // step <= 0 or NaN: the reference would never terminate
+                left -= ns;
+                // getGravityCenter (adjoiningpixel.cpp:104-118): fp32, extraction order; lanes 0..2 of warp 0 carry gx, gy, gw
+                if (wid == 0) {
+                    float gacc = 0.f;
+                    int i0 = lane < ns ? sm.S[lane] : 0;
+                    float v0 = sm.val[i0];
+                    int x0 = px[i0], y0 = py[i0];
+                    for (int q0 = 0; q0 < ns; q0 += 32) {
+                        const float vc = v0;
+                        const int xc = x0, yc = y0;
+                        if (q0 + 32 < ns) { // the next 32 operands are in flight while this chunk's chain runs
+                            i0 = q0 + 32 + lane < ns ? sm.S[q0 + 32 + lane] : 0;
+                            v0 = sm.val[i0]; x0 = px[i0]; y0 = py[i0];
+                        }
+                        const int cnt = min(32, ns - q0);
+                        for (int j = 0; j < cnt; j++) {
+                            const float v = __shfl_sync(0xffffffffu, vc, j);
+                            const int x = __shfl_sync(0xffffffffu, xc, j), y = __shfl_sync(0xffffffffu, yc, j);
+                            const float coord = lane == 0 ? (float)x : (lane == 1 ? (float)y : 1.f);
+                            gacc = __fadd_rn(gacc, __fmul_rn(v, coord));
+                        }
+                    }
+                    const float gx = __shfl_sync(0xffffffffu, gacc, 0), gy = __shfl_sync(0xffffffffu, gacc, 1), gw = __shfl_sync(0xffffffffu, gacc, 2);
+                    if (lane == 0) { sm.bc[1] = (int)__fdiv_rn(gx, gw); sm.bc[2] = (int)__fdiv_rn(gy, gw); }
+                }
+                // isAdjoining against every accepted region
+                for (int q = tid; q < ns; q += CBIG_NT) {
+                    const int i = sm.S[q];
+                    const unsigned char s0 = sm.st[i];
+                    const int u = sm.up[i], d = sm.dn[i];
+                    if (u >= 0 && (sm.st[u] & 3) == 3) stamp[reg[u]] = iter;
+                    if ((s0 & 4) && (sm.st[i - 1] & 3) == 3) stamp[reg[i - 1]] = iter;
+                    if ((s0 & 8) && (sm.st[i + 1] & 3) == 3) stamp[reg[i + 1]] = iter;
+                    if (d >= 0 && (sm.st[d] & 3) == 3) stamp[reg[d]] = iter;
+                }
+                __syncthreads();
+                const int cx = sm.bc[1], cy = sm.bc[2];
+                int blending = 0;
+                for (int a = tid; a < nacc; a += CBIG_NT) blending |= (stamp[a] == iter) || (acc_gx[a] == cx && acc_gy[a] == cy);
+                blending = __syncthreads_or(blending);
+                if (!blending) {
+                    for (int q = tid; q < ns; q += CBIG_NT) { const int i = sm.S[q]; sm.st[i] |= 3; reg[i] = nacc; }
+                    if (tid == 0) { acc_gx[nacc] = cx; acc_gy[nacc] = cy; stamp[nacc] = 0; }
+                    nacc++;
+                    // createStar (adjoiningpixel.cpp:120-150): values in extraction order + ranks, in the idle stack
+                    float *sv = reinterpret_cast<float *>(sm.stack);
+                    short *sorted = reinterpret_cast<short *>(sv + ns);
+                    for (int q = tid; q < ns; q += CBIG_NT) sv[q] = sm.val[sm.S[q]];
+                    __syncthreads();
+                    float peak = -INFINITY;
+                    for (int q = tid; q < ns; q += CBIG_NT) {
+                        const float v = sv[q];
+                        peak = fmaxf(peak, v);
+                        int r = 0; // elements ordered before this one: ascending value, ties by extraction order
+                        for (int p2 = 0; p2 < ns; p2++) {
+                            const float u2 = sv[p2];
+                            r += (u2 < v) || (u2 == v && p2 < q);
+                        }
+                        sorted[r] = (short)q;
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) peak = fmaxf(peak, __shfl_xor_sync(0xffffffffu, peak, o));
+                    if (lane == 0) sm.red_v[wid] = peak;
+                    __syncthreads();
+                    if (wid == 0) {
+                        peak = sm.red_v[0];
+#pragma unroll
+                        for (int w2 = 1; w2 < CBIG_NT / 32; w2++) peak = fmaxf(peak, sm.red_v[w2]);
+                        // lanes 0 / 1: flux-weighted x / y sums in ascending-value order, lane 2 the weight, lane 3 `value` in
+                        // extraction order; every step acc = float(double(acc) + coord * double(v)) (see create_star_warp)
+                        float acc = 0.f;
+                        int is = lane < ns ? sm.S[sorted[lane]] : 0;
+                        float vs0 = sm.val[is], ve0 = lane < ns ? sv[lane] : 0.f;
+                        int x0 = px[is], y0 = py[is];
+                        for (int q0 = 0; q0 < ns; q0 += 32) {
+                            const float vsc = vs0, vec = ve0;
+                            const int xc = x0, yc = y0;
+                            if (q0 + 32 < ns) {
+                                const int q = q0 + 32 + lane;
+                                is = q < ns ? sm.S[sorted[q]] : 0;
+                                vs0 = sm.val[is]; ve0 = q < ns ? sv[q] : 0.f; x0 = px[is]; y0 = py[is];
+                            }
+                            const int cnt = min(32, ns - q0);
+                            for (int j = 0; j < cnt; j++) {
+                                const float v_s = __shfl_sync(0xffffffffu, vsc, j), v_e = __shfl_sync(0xffffffffu, vec, j);
+                                const int x = __shfl_sync(0xffffffffu, xc, j), y = __shfl_sync(0xffffffffu, yc, j);
+                                const double coord = lane == 0 ? (double)x + 0.5 : (lane == 1 ? (double)y + 0.5 : 1.0);
+                                acc = (float)__dadd_rn((double)acc, __dmul_rn(coord, (double)(lane == 3 ? v_e : v_s)));
+                            }
+                        }
+                        const float xa = __shfl_sync(0xffffffffu, acc, 0), ya = __shfl_sync(0xffffffffu, acc, 1);
+                        const float wt = __shfl_sync(0xffffffffu, acc, 2), value = __shfl_sync(0xffffffffu, acc, 3);
+                        if (lane == 0) {
+                            oss_star st;
+                            st.area = ns; st.peak = peak; st.value = value;
+                            st.x = (int)__fdiv_rn(xa, wt);
+                            st.y = (int)__fdiv_rn(ya, wt);
+                            out[nout] = st;
+                        }
+                    }
+                    nout++;
+                }
+                __syncthreads();
+            }
+            if (tid == 0) comp_nstar[fb + c] = nout;
+        }
     }
 }
 

@@ -481,6 +481,8 @@ int oss_create(oss_ctx **out, int device)
         cudaFuncSetAttribute(k_sky_sub_stats, cudaFuncAttributeMaxDynamicSharedMemorySize, kSkySmemBytes) != cudaSuccess ||
         cudaFuncSetAttribute(k_focas, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FocasSmem)) != cudaSuccess ||
         cudaFuncSetAttribute(k_components, cudaFuncAttributeMaxDynamicSharedMemorySize, kCompSmemBytes) != cudaSuccess ||
+        cudaFuncSetAttribute(k_components_big<kCompBigSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CompBigSmem<kCompBigSmall>)) != cudaSuccess ||
+        cudaFuncSetAttribute(k_components_big<OSS_DEBLEND_MAX - 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CompBigSmem<OSS_DEBLEND_MAX - 1>)) != cudaSuccess ||
         cudaFuncSetAttribute(k_warp_accumulate_tiled<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, warp_tiled_smem<3>()) != cudaSuccess ||
         cudaFuncSetAttribute(k_warp_accumulate_tiled<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, warp_tiled_smem<1>()) != cudaSuccess ||
         cudaFuncSetAttribute(k_warp_accumulate_tma<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WarpTmaSmem<3>) + 128) != cudaSuccess ||
@@ -903,6 +905,11 @@ static int run_detect_tail(oss_ctx *c, int n, int threshold)
     LAUNCH("comp_members", k_comp_members, dim3(gs, n), 256, 0, w.parent, w.flag, w.flagscan, w.comp_off, w.comp_nstar, w.scratch, w.ds, g);
     LAUNCH("components", k_components, dim3(kSparseGrid, n), 32 * CW_WARPS, kCompSmemBytes, w.cand_idx, w.cand_val, w.nbr, w.owner, w.comp_size,
            w.comp_root, w.comp_off, w.comp_nstar, w.scratch, w.star_tmp, w.ds, g);
+    // components of more than CW_CAP pixels (listed by k_components): one CTA each, two shared-memory size classes
+    LAUNCH("components_big", k_components_big<kCompBigSmall>, 32, CBIG_NT, sizeof(CompBigSmem<kCompBigSmall>), w.cand_idx, w.cand_val, w.nbr,
+           w.comp_size, w.comp_root, w.comp_off, w.comp_nstar, w.scratch, w.star_tmp, w.ds, n, CW_CAP, g);
+    LAUNCH("components_big", k_components_big<OSS_DEBLEND_MAX - 1>, 8, CBIG_NT, sizeof(CompBigSmem<OSS_DEBLEND_MAX - 1>), w.cand_idx, w.cand_val,
+           w.nbr, w.comp_size, w.comp_root, w.comp_off, w.comp_nstar, w.scratch, w.star_tmp, w.ds, n, kCompBigSmall, g);
     r = run_scan(c, w.comp_nstar, g.cap, w.comp_staroff, g.cap, ncomp, DS, g.cap, n, nstars, DS);
     if (r) return r;
     LAUNCH("gather_stars", k_gather_stars, dim3(gs, n), 256, 0, w.star_tmp, w.comp_off, w.comp_nstar, w.comp_staroff, w.star_out,

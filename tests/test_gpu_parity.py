@@ -199,6 +199,47 @@ def test_star_lists_identical(eng, seed, t):
     assert info.nstars == len(want)
 
 
+def large_component_image(w, h, seed):
+    """Components of a few hundred to ~9000 pixels: noisy 1-px lattices on an 8-px pitch (the low-res sky grid never sees
+    them) in patches of 70 ... 190 px, and flat-topped disks with several sub-peaks (deblended into several stars)."""
+    r = np.random.default_rng(seed)
+    img = r.normal(0.05, 0.002, (h, w))
+    yy, xx = np.mgrid[0:h, 0:w]
+    for x0, y0, L in ((40, 40, 70), (160, 40, 100), (304, 40, 150), (504, 40, 190), (744, 40, 120)):
+        patch = np.zeros((h, w), bool)
+        patch[y0:y0 + L:8, x0:x0 + L] = True
+        patch[y0:y0 + L, x0:x0 + L:8] = True
+        # noisy ridges on a brightness ramp: many local maxima, tens of peel iterations, regions that blend and are dropped
+        img += patch * (0.35 + 1.3 * np.clip((xx - x0) / L, 0, 1) * np.clip((yy - y0 + 20) / L, 0, 1) + r.normal(0, 0.04, (h, w)))
+    for cx, cy, rad in ((120, 420, 9), (300, 430, 14), (520, 440, 18), (760, 450, 24)):
+        r2 = (xx + 0.5 - cx) ** 2 + (yy + 0.5 - cy) ** 2
+        img += 0.3 * np.exp(-r2 / (2 * (rad / 2.0) ** 2)) + 0.4 * (r2 < rad ** 2)
+        for _ in range(4):
+            dx, dy = r.uniform(-rad, rad, 2) * 0.6
+            img += r.uniform(0.2, 0.6) * np.exp(-0.5 * ((xx + 0.5 - cx - dx) ** 2 + (yy + 0.5 - cy - dy) ** 2) / r.uniform(1.5, 3.0) ** 2)
+    return img.astype(np.float32)
+
+
+@pytest.mark.parametrize("seed,t", [(21, 1), (22, 2), (23, 3)])
+def test_large_components_match_oracle(eng, seed, t):
+    """Components above k_components' per-warp capacity (256 px) go to k_components_big, one CTA each, in two shared-memory
+    size classes (<= 2048 px, < 10000 px): DFS order, peel order, blending tests, createStar sums — star for star."""
+    from scipy import ndimage
+    w, h = 1600, 1000
+    eng.set_geometry(w, h, 1, np.float32, 3)
+    g = large_component_image(w, h, seed)
+    want, oinfo = oracle.get_stars(g, t)
+    lab, ncomp = ndimage.label((g - oracle.sky_background(g)) > np.float32(oinfo.threshold))
+    sizes = np.bincount(lab.ravel())[1:]
+    assert ((sizes > 256) & (sizes <= 2048)).sum() >= 2 and ((sizes > 2048) & (sizes < 10000)).sum() >= 2, sorted(sizes)[-8:]
+    got, info = eng.detect_stars(g, t)
+    assert info.ncomponents == oinfo.ncomponents
+    same_stars(got, want)
+    # the same frame twice in one batch next to an ordinary one: per-frame lists, work split over the CTAs
+    counts = eng.detect_stars_batch([g, blob_image(w, h, 40, seed), g], t)
+    assert counts[0] == counts[2] == len(want)
+
+
 def test_star_lists_edge_cases(eng):
     w, h = 160, 120
     eng.set_geometry(w, h, 1, np.float32, 2)

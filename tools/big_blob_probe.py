@@ -1,5 +1,7 @@
 """Dev aid (GPU box): detection time and parity on frames with ONE very large component (a saturated star / galaxy core):
-components of 300 ... 9 900 pixels go through k_components' large-component path (deblending replayed by one thread)."""
+components above 256 pixels go through k_components_big (one CTA per component; before it: one thread, 6 - 37 ms for these
+frames).  Second part: the large-component test image (ramped noisy lattices of 260 ... 8 500 px, ~100 stars out of ~10
+components) in a batch of 8 frames."""
 import sys
 import time
 
@@ -28,4 +30,18 @@ for radius in (9, 18, 30, 45, 55, 60):
     big = max((int(s["area"]) for s in stars), default=0)
     print(f"radius {radius}: candidates {info.ncandidates}, stars {len(stars)} (largest area {big}), GPU {1e3 * (t1 - t0):.1f} ms, "
           f"oracle {1e3 * (t2 - t1):.1f} ms, identical {same}")
+sys.path.insert(0, "tests")
+from test_gpu_parity import large_component_image   # noqa: E402
+w, h = 1600, 1000
+eng.set_geometry(w, h, 1, np.float32, 8)
+for seed, t in ((21, 1), (22, 2), (23, 3)):
+    g = large_component_image(w, h, seed)
+    eng.detect_stars_batch([g] * 8, t)
+    t0 = time.perf_counter()
+    counts = eng.detect_stars_batch([g] * 8, t)
+    t1 = time.perf_counter()
+    o_stars, _ = oracle.get_stars(g, t)
+    t2 = time.perf_counter()
+    print(f"lattices seed {seed} t {t}: stars {counts[0]} (oracle {len(o_stars)}), GPU {1e3 * (t1 - t0) / 8:.2f} ms per frame (batch of 8, "
+          f"incl. H2D), oracle {1e3 * (t2 - t1):.1f} ms")
 eng.close()
