@@ -12,8 +12,10 @@
 //     bit masks + an exclusive scan, so "position in the list" == raster rank;
 //   - a union-find over the sparse list labels components by their raster-first pixel,
 //     which reproduces the reference's component order;
-//   - one thread per component replays the reference's DFS and peel loops over
-//     precomputed neighbour links (no image access, no coordinate searches).
+//   - one WARP per component (k_components, <= 256 px) or one CTA per component (k_components_big, incl. the
+//     >= 10000-px deblender bypass) replays the reference's DFS and peel loops on shared memory over precomputed
+//     neighbour links (no image access, no coordinate searches): traversals whose ORDER is the result run on one
+//     thread, everything else (peak search, adjacency stamps, rankings) in parallel.
 #pragma once
 #include "common.cuh"
 
@@ -328,169 +330,6 @@ struct CompScratch {
     int *acc_gx, *acc_gy, *stamp; // [n] per accepted region
 };
 
-// createStar (adjoiningpixel.cpp:120-150) over region S[0..ns) (positions into the lists)
-__device__ oss_star create_star(const int *S, int ns, int *sorted, const int *__restrict__ cand_idx,
-                                const float *__restrict__ cand_val, int W)
-{
-    oss_star st;
-    st.area = ns;
-    float peak = 0.f, value = 0.f;
-    for (int q = 0; q < ns; q++) {
-        float v = cand_val[S[q]];
-        if (q == 0 || peak < v) peak = v;
-        value = __fadd_rn(value, v);
-        sorted[q] = q;
-    }
-    st.peak = peak;
-    st.value = value;
-    // ascending by (value, extraction order): heap sort on indices into S
-    auto less = [&](int a, int b) {
-        float va = cand_val[S[a]], vb = cand_val[S[b]];
-        return va < vb || (va == vb && a < b);
-    };
-    auto sift = [&](int start, int end) {
-        int root = start;
-        for (;;) {
-            int child = 2 * root + 1;
-            if (child > end) break;
-            if (child + 1 <= end && less(sorted[child], sorted[child + 1])) child++;
-            if (less(sorted[root], sorted[child])) {
-                int t = sorted[root]; sorted[root] = sorted[child]; sorted[child] = t;
-                root = child;
-            } else break;
-        }
-    };
-    if (ns <= 24) { // insertion sort
-        for (int i = 1; i < ns; i++) {
-            int key = sorted[i], j = i - 1;
-            while (j >= 0 && less(key, sorted[j])) { sorted[j + 1] = sorted[j]; j--; }
-            sorted[j + 1] = key;
-        }
-    } else {
-        for (int start = (ns - 2) / 2; start >= 0; start--) sift(start, ns - 1);
-        for (int end = ns - 1; end > 0; end--) {
-            int t = sorted[0]; sorted[0] = sorted[end]; sorted[end] = t;
-            sift(0, end - 1);
-        }
-    }
-    float xa = 0.f, ya = 0.f, wt = 0.f;
-    for (int q = 0; q < ns; q++) {
-        int i = S[sorted[q]];
-        int lin = cand_idx[i];
-        int y = lin / W, x = lin - y * W;
-        double v = (double)cand_val[i];
-        xa = (float)__dadd_rn((double)xa, __dmul_rn((double)x + 0.5, v));
-        ya = (float)__dadd_rn((double)ya, __dmul_rn((double)y + 0.5, v));
-        wt = __fadd_rn(wt, cand_val[i]);
-    }
-    st.x = (int)__fdiv_rn(xa, wt);
-    st.y = (int)__fdiv_rn(ya, wt);
-    return st;
-}
-
-// One component, replayed literally by ONE thread over the global lists: the reference's DFS and peel orders (the fallback
-// of k_components for components larger than its shared-memory scratch, incl. the >= 10000-px deblender bypass).
-__device__ int component_serial(int c, long long fb, const int *__restrict__ cidx, const float *__restrict__ cval,
-                                const int4 *__restrict__ nb, int *__restrict__ own, const int *__restrict__ comp_size,
-                                const int *__restrict__ comp_root, const int *__restrict__ comp_off, int *__restrict__ scr,
-                                oss_star *__restrict__ star_tmp, float step, const Geom &g)
-{
-    int sp;
-    const int root = comp_root[fb + c];
-    const int n = comp_size[fb + root];
-    const int off = comp_off[fb + c];
-    int *list = scr + off;
-    int *S = scr + g.cap + off;
-    int *sorted = scr + 2 * (long long)g.cap + off;
-    int *acc_gx = scr + 3 * (long long)g.cap + off;
-    int *acc_gy = scr + 4 * (long long)g.cap + off;
-    int *stamp = scr + 5 * (long long)g.cap + off;
-    int *stack = scr + 6 * (long long)g.cap + 4 * (long long)off + c; // 4n+1 entries
-    oss_star *out = star_tmp + fb + off;
-
-    // detectAdjoiningPixel: explicit-stack DFS, push order up, left, right, down
-    int np = 0; sp = 0;
-    stack[sp++] = root;
-    while (sp > 0) {
-        int i = stack[--sp];
-        if (own[i] != -3) continue;
-        own[i] = -1; // REMAINING (for the deblender)
-        list[np++] = i;
-        int4 q = nb[i];
-        if (q.x >= 0 && own[q.x] == -3) stack[sp++] = q.x;
-        if (q.y >= 0 && own[q.y] == -3) stack[sp++] = q.y;
-        if (q.z >= 0 && own[q.z] == -3) stack[sp++] = q.z;
-        if (q.w >= 0 && own[q.w] == -3) stack[sp++] = q.w;
-    }
-
-    int nout = 0;
-    if (n >= OSS_DEBLEND_MAX) { // adjoiningpixel.cpp:45-48
-        out[nout++] = create_star(list, n, sorted, cidx, cval, g.W);
-        return nout;
-    }
-    int left = n, nacc = 0, iter = 0;
-    while (left > 0) {
-        iter++;
-        int pk = -1;
-        float mx = 0.f;
-        for (int q = 0; q < n; q++) { // getPeak: first maximum in list order
-            int i = list[q];
-            if (own[i] != -1) continue;
-            float v = cval[i];
-            if (pk < 0 || mx < v) { pk = i; mx = v; }
-        }
-        // adjoiningpixel.cpp:57
-        float T = (float)__dsub_rn((double)mx, __dmul_rn((double)step, sqrt(__dadd_rn((double)__fdiv_rn(mx, step), 1.0))));
-        // extract(): recursive pre-order up, left, right, down == stack with reversed pushes
-        int ns = 0;
-        sp = 0;
-        stack[sp++] = pk;
-        while (sp > 0) {
-            int i = stack[--sp];
-            if (own[i] != -1 || !(cval[i] > T)) continue;
-            own[i] = -2; // DROPPED unless accepted below
-            S[ns++] = i;
-            int4 q = nb[i];
-            if (q.w >= 0 && own[q.w] == -1) stack[sp++] = q.w;
-            if (q.z >= 0 && own[q.z] == -1) stack[sp++] = q.z;
-            if (q.y >= 0 && own[q.y] == -1) stack[sp++] = q.y;
-            if (q.x >= 0 && own[q.x] == -1) stack[sp++] = q.x;
-        }
-        if (ns == 0) break; // step <= 0 or NaN: the reference would never terminate
-        left -= ns;
-        // getGravityCenter (adjoiningpixel.cpp:104-118): fp32, list order, truncated
-        float gx = 0.f, gy = 0.f, gw = 0.f;
-        for (int q = 0; q < ns; q++) {
-            int i = S[q];
-            int lin = cidx[i];
-            int y = lin / g.W, x = lin - y * g.W;
-            float v = cval[i];
-            gx = __fadd_rn(gx, __fmul_rn(v, (float)x));
-            gy = __fadd_rn(gy, __fmul_rn(v, (float)y));
-            gw = __fadd_rn(gw, v);
-        }
-        int cx = (int)__fdiv_rn(gx, gw), cy = (int)__fdiv_rn(gy, gw);
-        // isAdjoining against every accepted region
-        for (int q = 0; q < ns; q++) {
-            int4 t = nb[S[q]];
-            if (t.x >= 0 && own[t.x] >= 0) stamp[own[t.x]] = iter;
-            if (t.y >= 0 && own[t.y] >= 0) stamp[own[t.y]] = iter;
-            if (t.z >= 0 && own[t.z] >= 0) stamp[own[t.z]] = iter;
-            if (t.w >= 0 && own[t.w] >= 0) stamp[own[t.w]] = iter;
-        }
-        int blending = 0;
-        for (int a = 0; a < nacc; a++)
-            if (stamp[a] == iter || (acc_gx[a] == cx && acc_gy[a] == cy)) blending++;
-        if (blending == 0) {
-            for (int q = 0; q < ns; q++) own[S[q]] = nacc;
-            acc_gx[nacc] = cx; acc_gy[nacc] = cy; stamp[nacc] = 0;
-            nacc++;
-            out[nout++] = create_star(S, ns, sorted, cidx, cval, g.W);
-        }
-    }
-    return nout;
-}
-
 // ---- K6  one WARP per component ----------------------------------------------------------
 // The component's pixels (k_comp_members: an unordered scatter by label) are staged in shared memory, sorted back into raster
 // order, and their neighbour links are translated to local indices; every traversal of the reference then runs on shared
@@ -577,7 +416,6 @@ k_components(const int *__restrict__ cand_idx, const float *__restrict__ cand_va
     const int *cidx = cand_idx + fb;
     const float *cval = cand_val + fb;
     const int4 *nb = nbr + fb;
-    int *own = owner + fb;
     int *scr = scratch + 12 * fb;
     const float step = ds[f].threshold;
 
@@ -586,15 +424,8 @@ k_components(const int *__restrict__ cand_idx, const float *__restrict__ cand_va
         const int n = comp_size[fb + root];
         const int off = comp_off[fb + c];
         oss_star *out = star_tmp + fb + off;
-        if (n > CW_CAP && n < OSS_DEBLEND_MAX) { // k_components_big: one CTA per component (queued after this kernel)
+        if (n > CW_CAP) { // k_components_big: one CTA per component (queued after this kernel), incl. the >= 10000-px bypass
             if (lane == 0) scr[11ll * g.cap + atomicAdd(&ds[f].nbig, 1)] = c; // [11 cap, 12 cap) of the scratch is nobody's
-            continue;
-        }
-        if (n > CW_CAP) { // the deblender bypass (>= 10000 px, adjoiningpixel.cpp:45-48): one lane replays the DFS over global memory
-            int nout = 0;
-            if (lane == 0) nout = component_serial(c, fb, cidx, cval, nb, own, comp_size, comp_root, comp_off, scr, star_tmp, step, g);
-            if (lane == 0) comp_nstar[fb + c] = nout;
-            __syncwarp();
             continue;
         }
         // ---- stage: members (any order) -> ascending candidate positions (rank sort; positions are distinct)
@@ -745,6 +576,110 @@ k_components(const int *__restrict__ cand_idx, const float *__restrict__ cand_va
 //     warp (coordinates live in global scratch) and handed over by shuffles, the next 32 in flight meanwhile.
 // CB = capacity in pixels: two instances, 2048 (43 KB of shared memory: several CTAs per SM) and OSS_DEBLEND_MAX - 1
 // (210 KB: one CTA per SM, like k_focas); a CTA skips the list entries of the other instance.
+// The deblender bypass (a component of >= 10000 pixels: a satellite trail, a lattice of diffraction spikes) by one CTA over
+// global memory: the reference's DFS (its order decides `value`'s summation order and the ties of the sort) on thread 0, then
+// createStar with the (value, extraction order) sort as a bitonic network over 64-bit keys in the idle DFS stack and the fp
+// chains on lanes 0..3 like everywhere else.  (One thread doing all of it, heap sort included, took ~40 us per pixel.)
+__device__ void big_bypass(int c, int root, int n, int off, long long fb, const int *__restrict__ cand_idx, const float *__restrict__ cand_val,
+                           const int4 *__restrict__ nbr, int *__restrict__ owner, int *__restrict__ scr, oss_star *__restrict__ star_tmp,
+                           int *__restrict__ comp_nstar, float *red, const Geom &g)
+{
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, NT = blockDim.x;
+    const int *cidx = cand_idx + fb;
+    const float *cval = cand_val + fb;
+    const int4 *nb = nbr + fb;
+    int *own = owner + fb;
+    int *list = scr + off;
+    const long long stack_at = 6ll * g.cap + 4ll * off + c; // 4 n + 1 entries
+    int *stack = scr + stack_at;
+    __syncthreads();
+    if (tid == 0) { // detectAdjoiningPixel: explicit-stack DFS, push order up, left, right, down
+        int np = 0, sp = 0;
+        stack[sp++] = root; // the raster-first pixel (the union-find's label)
+        while (sp > 0) {
+            const int i = stack[--sp];
+            if (own[i] != -3) continue;
+            own[i] = -1;
+            list[np++] = i;
+            const int4 q = nb[i];
+            if (q.x >= 0 && own[q.x] == -3) stack[sp++] = q.x;
+            if (q.y >= 0 && own[q.y] == -3) stack[sp++] = q.y;
+            if (q.z >= 0 && own[q.z] == -3) stack[sp++] = q.z;
+            if (q.w >= 0 && own[q.w] == -3) stack[sp++] = q.w;
+        }
+    }
+    __syncthreads();
+    // keys: value bits (positive floats order like their bit patterns) over the extraction position
+    unsigned long long *K = reinterpret_cast<unsigned long long *>(stack + (stack_at & 1));
+    int N = 2;
+    while (N < n) N <<= 1;
+    float peak = -INFINITY;
+    for (int q = tid; q < N; q += NT) {
+        unsigned long long key = ~0ull;
+        if (q < n) {
+            const float v = cval[list[q]];
+            peak = fmaxf(peak, v);
+            key = ((unsigned long long)__float_as_uint(v) << 32) | (unsigned)q;
+        }
+        K[q] = key;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) peak = fmaxf(peak, __shfl_xor_sync(0xffffffffu, peak, o));
+    if (lane == 0) red[wid] = peak;
+    __syncthreads();
+    for (int k2 = 2; k2 <= N; k2 <<= 1)
+        for (int j = k2 >> 1; j > 0; j >>= 1) {
+            for (int t = tid; t < (N >> 1); t += NT) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), l = i | j;
+                const unsigned long long a = K[i], b = K[l];
+                if ((a > b) == ((i & k2) == 0)) { K[i] = b; K[l] = a; }
+            }
+            __syncthreads();
+        }
+    if (wid == 0) {
+        peak = red[0];
+        for (int w2 = 1; w2 < NT / 32; w2++) peak = fmaxf(peak, red[w2]);
+        float acc = 0.f;
+        auto fetch = [&](int q, float &vs, float &ve, int &x, int &y) {
+            vs = ve = 0.f; x = y = 0;
+            if (q < n) {
+                const int i = list[(int)(K[q] & 0xffffffffu)];
+                vs = cval[i];
+                const int lin = cidx[i];
+                y = lin / g.W;
+                x = lin - y * g.W;
+                ve = cval[list[q]];
+            }
+        };
+        float vs0, ve0;
+        int x0, y0;
+        fetch(lane, vs0, ve0, x0, y0);
+        for (int q0 = 0; q0 < n; q0 += 32) {
+            const float vsc = vs0, vec = ve0;
+            const int xc = x0, yc = y0;
+            if (q0 + 32 < n) fetch(q0 + 32 + lane, vs0, ve0, x0, y0);
+            const int cnt = min(32, n - q0);
+            for (int j = 0; j < cnt; j++) {
+                const float v_s = __shfl_sync(0xffffffffu, vsc, j), v_e = __shfl_sync(0xffffffffu, vec, j);
+                const int x = __shfl_sync(0xffffffffu, xc, j), y = __shfl_sync(0xffffffffu, yc, j);
+                const double coord = lane == 0 ? (double)x + 0.5 : (lane == 1 ? (double)y + 0.5 : 1.0);
+                acc = (float)__dadd_rn((double)acc, __dmul_rn(coord, (double)(lane == 3 ? v_e : v_s)));
+            }
+        }
+        const float xa = __shfl_sync(0xffffffffu, acc, 0), ya = __shfl_sync(0xffffffffu, acc, 1);
+        const float wt = __shfl_sync(0xffffffffu, acc, 2), value = __shfl_sync(0xffffffffu, acc, 3);
+        if (lane == 0) {
+            oss_star st;
+            st.area = n; st.peak = peak; st.value = value;
+            st.x = (int)__fdiv_rn(xa, wt);
+            st.y = (int)__fdiv_rn(ya, wt);
+            star_tmp[fb + off] = st;
+            comp_nstar[fb + c] = 1;
+        }
+    }
+    __syncthreads();
+}
+
 #define CBIG_NT 256
 constexpr int kCompBigSmall = 2048;
 template <int CB> struct CompBigSmem {
@@ -763,7 +698,7 @@ template <int CB>
 __global__ void __launch_bounds__(CBIG_NT)
 k_components_big(const int *__restrict__ cand_idx, const float *__restrict__ cand_val, const int4 *__restrict__ nbr,
                  const int *__restrict__ comp_size, const int *__restrict__ comp_root, const int *__restrict__ comp_off,
-                 int *__restrict__ comp_nstar, int *__restrict__ scratch, oss_star *__restrict__ star_tmp,
+                 int *__restrict__ comp_nstar, int *__restrict__ scratch, oss_star *__restrict__ star_tmp, int *__restrict__ owner,
                  const DetectState *__restrict__ ds, int nframes, int lo_excl, Geom g)
 {
     extern __shared__ __align__(16) unsigned char comp_smem_raw[];
@@ -780,9 +715,13 @@ k_components_big(const int *__restrict__ cand_idx, const float *__restrict__ can
         for (int e = 0; e < nbig; e++) {
             const int c = big_list[e];
             const int n = comp_size[fb + comp_root[fb + c]];
-            if (n <= lo_excl || n > CB) continue;
+            if (n <= lo_excl || (n > CB && CB < OSS_DEBLEND_MAX - 1)) continue;
             if ((item++) % (int)gridDim.x != (int)blockIdx.x) continue;
             const int off = comp_off[fb + c];
+            if (n >= OSS_DEBLEND_MAX) { // adjoiningpixel.cpp:45-48: no deblending, ONE star from the whole component
+                if (CB == OSS_DEBLEND_MAX - 1) big_bypass(c, comp_root[fb + c], n, off, fb, cand_idx, cand_val, nbr, owner, scr, star_tmp, comp_nstar, sm.red_v, g);
+                continue;
+            }
             const int *member = scr + off;                        // unordered (k_comp_members)
             int *reg = scr + g.cap + off;                         // accepted region of a pixel
             int *px = scr + 2ll * g.cap + off, *py = scr + 6ll * g.cap + 4ll * off + c;

@@ -907,9 +907,9 @@ static int run_detect_tail(oss_ctx *c, int n, int threshold)
            w.comp_root, w.comp_off, w.comp_nstar, w.scratch, w.star_tmp, w.ds, g);
     // components of more than CW_CAP pixels (listed by k_components): one CTA each, two shared-memory size classes
     LAUNCH("components_big", k_components_big<kCompBigSmall>, 32, CBIG_NT, sizeof(CompBigSmem<kCompBigSmall>), w.cand_idx, w.cand_val, w.nbr,
-           w.comp_size, w.comp_root, w.comp_off, w.comp_nstar, w.scratch, w.star_tmp, w.ds, n, CW_CAP, g);
+           w.comp_size, w.comp_root, w.comp_off, w.comp_nstar, w.scratch, w.star_tmp, w.owner, w.ds, n, CW_CAP, g);
     LAUNCH("components_big", k_components_big<OSS_DEBLEND_MAX - 1>, 8, CBIG_NT, sizeof(CompBigSmem<OSS_DEBLEND_MAX - 1>), w.cand_idx, w.cand_val,
-           w.nbr, w.comp_size, w.comp_root, w.comp_off, w.comp_nstar, w.scratch, w.star_tmp, w.ds, n, kCompBigSmall, g);
+           w.nbr, w.comp_size, w.comp_root, w.comp_off, w.comp_nstar, w.scratch, w.star_tmp, w.owner, w.ds, n, kCompBigSmall, g);
     r = run_scan(c, w.comp_nstar, g.cap, w.comp_staroff, g.cap, ncomp, DS, g.cap, n, nstars, DS);
     if (r) return r;
     LAUNCH("gather_stars", k_gather_stars, dim3(gs, n), 256, 0, w.star_tmp, w.comp_off, w.comp_nstar, w.comp_staroff, w.star_out,

@@ -240,6 +240,27 @@ def test_large_components_match_oracle(eng, seed, t):
     assert counts[0] == counts[2] == len(want)
 
 
+def test_satellite_trail_goes_through_the_deblender_bypass(eng):
+    """A 5-px wide trail across the frame is one component of >= 10000 pixels: no deblending (adjoiningpixel.cpp:45-48), one
+    star whose sums follow the reference's DFS order; here by one CTA (DFS on one thread, bitonic sort, fp chains)."""
+    from scipy import ndimage
+    w, h = 2400, 1600
+    eng.set_geometry(w, h, 1, np.float32, 2)
+    r = np.random.default_rng(31)
+    g = blob_image(w, h, 30, 31).astype(np.float64)
+    yy, xx = np.mgrid[0:h, 0:w]
+    d = np.abs((yy - 100) - 0.55 * (xx - 50)) / np.hypot(1, 0.55)          # distance from the line y = 100 + 0.55 (x - 50)
+    g += (d < 2.6) * (0.5 + 0.1 * np.sin(xx / 37.0) + r.normal(0, 0.02, (h, w)))
+    g = g.astype(np.float32)
+    want, oinfo = oracle.get_stars(g, 5)
+    lab, _ = ndimage.label((g - oracle.sky_background(g)) > np.float32(oinfo.threshold))
+    assert np.bincount(lab.ravel())[1:].max() >= 10000 and max(want["area"]) >= 10000
+    got, info = eng.detect_stars(g, 5)
+    same_stars(got, want)
+    counts = eng.detect_stars_batch([g, g], 5)
+    assert counts[0] == counts[1] == len(want)
+
+
 def test_star_lists_edge_cases(eng):
     w, h = 160, 120
     eng.set_geometry(w, h, 1, np.float32, 2)

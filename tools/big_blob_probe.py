@@ -44,4 +44,21 @@ for seed, t in ((21, 1), (22, 2), (23, 3)):
     t2 = time.perf_counter()
     print(f"lattices seed {seed} t {t}: stars {counts[0]} (oracle {len(o_stars)}), GPU {1e3 * (t1 - t0) / 8:.2f} ms per frame (batch of 8, "
           f"incl. H2D), oracle {1e3 * (t2 - t1):.1f} ms")
+# a satellite trail: one component of ~14 000 px, the deblender bypass
+from test_gpu_parity import blob_image   # noqa: E402
+w, h = 2400, 1600
+eng.set_geometry(w, h, 1, np.float32, 2)
+r = np.random.default_rng(31)
+g = blob_image(w, h, 30, 31).astype(np.float64)
+yy, xx = np.mgrid[0:h, 0:w]
+d = np.abs((yy - 100) - 0.55 * (xx - 50)) / np.hypot(1, 0.55)
+g = (g + (d < 2.6) * (0.5 + 0.1 * np.sin(xx / 37.0) + r.normal(0, 0.02, (h, w)))).astype(np.float32)
+eng.detect_stars(g, 5)
+t0 = time.perf_counter()
+stars, info = eng.detect_stars(g, 5)
+t1 = time.perf_counter()
+o_stars, _ = oracle.get_stars(g, 5)
+t2 = time.perf_counter()
+print(f"trail: stars {len(stars)} (oracle {len(o_stars)}), largest area {max(int(s['area']) for s in stars)}, GPU {1e3 * (t1 - t0):.1f} ms, "
+      f"oracle {1e3 * (t2 - t1):.1f} ms")
 eng.close()
