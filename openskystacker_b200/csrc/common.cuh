@@ -41,7 +41,9 @@ struct DetectState {
     int ncomp;   // components with peak > minPeak
     int nstars;
     int overflow;
-    int nbig;    // components handed to k_components_big (more than CW_CAP pixels, below the deblender bypass)
+    int nbig;    // components above CW_CAP_SMALL pixels, listed by the first k_components instance for the second
+    int nbig2;   // components of CW_CAP + 1 .. kCompBigSmall pixels, listed by the second k_components instance for k_components_big
+    int nbig3;   // ... and the larger ones (second instance of k_components_big, incl. the >= 10000-px bypass)
 };
 
 // Result of the alignment kernel for one light.

@@ -340,28 +340,36 @@ struct CompScratch {
 //   order) ranking that replaces createStar's std::sort.
 // One thread per component over global memory (the first version) made the largest component of a batch its critical
 // path: ~2 us per pixel, 1.3 ms per 17-frame batch; here it is ~0.1 us per pixel.
-#define CW_CAP 256   // pixels per component handled in shared memory (12.5 KB per warp: 4 CTAs per SM); larger ones (and the >= 10000-px bypass) go to component_serial
+// Two instances: CAP = 64 (3.2 KB per warp, 8 warps per CTA: ~48 resident warps per SM — the kernel is latency-bound on lane 0's
+// traversals, so residency is throughput; it walks over ALL components and lists the larger ones) and CAP = 256 (12.5 KB per
+// warp, 4 warps per CTA) over that list; what exceeds 256 pixels stays on the list for k_components_big.
+#define CBIG_SMALL 2048   // first size class of k_components_big
+#define CW_CAP_SMALL 64
+#define CW_WARPS_SMALL 8
+#define CW_CAP 256
 #define CW_WARPS 4
-struct CompWarpSmem {
-    int gidx[CW_CAP];            // candidate-list positions, ascending = raster order
-    float val[CW_CAP];
-    int px[CW_CAP], py[CW_CAP];
-    short nb[CW_CAP][4];         // local neighbours: up, left, right, down (-1: none)
-    short own[CW_CAP];           // -3 unvisited, -1 remaining, -2 dropped, >= 0 accepted region
-    short list[CW_CAP];          // the reference's DFS order
-    short S[CW_CAP];             // region being peeled, extraction order
-    short sorted[CW_CAP];        // positions in S, ascending by (value, extraction order)
-    short stamp[CW_CAP];
-    int acc_gx[CW_CAP], acc_gy[CW_CAP];
-    short stack[4 * CW_CAP + 4];
+template <int CAP> struct CompWarpSmem {
+    int gidx[CAP];            // candidate-list positions, ascending = raster order
+    float val[CAP];
+    int px[CAP], py[CAP];
+    short nb[CAP][4];         // local neighbours: up, left, right, down (-1: none)
+    short own[CAP];           // -3 unvisited, -1 remaining, -2 dropped, >= 0 accepted region
+    short list[CAP];          // the reference's DFS order
+    short S[CAP];             // region being peeled, extraction order
+    short sorted[CAP];        // positions in S, ascending by (value, extraction order)
+    short stamp[CAP];
+    int acc_gx[CAP], acc_gy[CAP];
+    short stack[4 * CAP + 4];
 };
-constexpr int kCompSmemBytes = (int)sizeof(CompWarpSmem) * CW_WARPS;
+constexpr int kCompSmemBytes = (int)sizeof(CompWarpSmem<CW_CAP>) * CW_WARPS;
+constexpr int kCompSmemBytesSmall = (int)sizeof(CompWarpSmem<CW_CAP_SMALL>) * CW_WARPS_SMALL;
 
 // createStar (adjoiningpixel.cpp:120-150) over region S[0..ns) by one warp.  Lanes 0..3 carry one chain each, all with the
 // formula acc = float(double(acc) + coord * double(v)): lanes 0 / 1 the flux-weighted x / y sums (coord = x + 0.5, y + 0.5, in
 // ascending-value order), lane 2 the weight and lane 3 `value` (coord = 1: double(acc) + double(v) rounded once to fp32 IS the
 // fp32 sum — 53 >= 2 * 24 + 2 bits, double rounding is innocuous), lane 3 in extraction order like the reference's first loop.
-__device__ oss_star create_star_warp(CompWarpSmem &sm, int ns, int lane)
+template <int CAP>
+__device__ oss_star create_star_warp(CompWarpSmem<CAP> &sm, int ns, int lane)
 {
     float *sv = (float *)sm.stack; // the region's values in extraction order (the DFS stack is idle here)
     for (int q = lane; q < ns; q += 32) sv[q] = sm.val[sm.S[q]];
@@ -400,7 +408,8 @@ __device__ oss_star create_star_warp(CompWarpSmem &sm, int ns, int lane)
     return st;
 }
 
-__global__ void __launch_bounds__(32 * CW_WARPS)
+template <int CAP, int WARPS, bool FROM_LIST>
+__global__ void __launch_bounds__(32 * WARPS)
 k_components(const int *__restrict__ cand_idx, const float *__restrict__ cand_val, const int4 *__restrict__ nbr,
              int *__restrict__ owner, const int *__restrict__ comp_size, const int *__restrict__ comp_root,
              const int *__restrict__ comp_off, int *__restrict__ comp_nstar, int *__restrict__ scratch,
@@ -410,22 +419,28 @@ k_components(const int *__restrict__ cand_idx, const float *__restrict__ cand_va
     const int f = blockIdx.y;
     if (ds[f].overflow) return;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    CompWarpSmem &sm = ((CompWarpSmem *)comp_smem_raw)[wid];
-    const int ncomp = ds[f].ncomp;
+    CompWarpSmem<CAP> &sm = ((CompWarpSmem<CAP> *)comp_smem_raw)[wid];
     const long long fb = (long long)f * g.cap;
     const int *cidx = cand_idx + fb;
     const float *cval = cand_val + fb;
     const int4 *nb = nbr + fb;
     int *scr = scratch + 12 * fb;
+    int *big_list = scr + 11ll * g.cap; // [11 cap, 12 cap) of the scratch is nobody's: components above CW_CAP_SMALL pixels
     const float step = ds[f].threshold;
+    const int nitems = FROM_LIST ? ds[f].nbig : ds[f].ncomp;
 
-    for (int c = blockIdx.x * CW_WARPS + wid; c < ncomp; c += gridDim.x * CW_WARPS) {
+    for (int e = blockIdx.x * WARPS + wid; e < nitems; e += gridDim.x * WARPS) {
+        const int c = FROM_LIST ? big_list[e] : e;
         const int root = comp_root[fb + c];
         const int n = comp_size[fb + root];
         const int off = comp_off[fb + c];
         oss_star *out = star_tmp + fb + off;
-        if (n > CW_CAP) { // k_components_big: one CTA per component (queued after this kernel), incl. the >= 10000-px bypass
-            if (lane == 0) scr[11ll * g.cap + atomicAdd(&ds[f].nbig, 1)] = c; // [11 cap, 12 cap) of the scratch is nobody's
+        if (n > CAP) { // the next instance (or k_components_big: one CTA per component, incl. the >= 10000-px bypass) takes it
+            if (lane == 0) {
+                if (!FROM_LIST) big_list[atomicAdd(&ds[f].nbig, 1)] = c;
+                else if (n <= CBIG_SMALL) big_list[g.cap / 2 + atomicAdd(&ds[f].nbig2, 1)] = c; // per size class of k_components_big,
+                else big_list[g.cap / 2 + g.cap / 4 + atomicAdd(&ds[f].nbig3, 1)] = c;          // further along the same region
+            }
             continue;
         }
         // ---- stage: members (any order) -> ascending candidate positions (rank sort; positions are distinct)
@@ -470,11 +485,14 @@ k_components(const int *__restrict__ cand_idx, const float *__restrict__ cand_va
                 if (sm.own[i] != -3) continue;
                 sm.own[i] = -1; // REMAINING (for the deblender)
                 sm.list[np++] = (short)i;
-#pragma unroll
-                for (int d = 0; d < 4; d++) {
-                    const int t = sm.nb[i][d];
-                    if (t >= 0 && sm.own[t] == -3) sm.stack[sp++] = (short)t;
-                }
+                // the four links in one load, the four neighbour states in flight together (this loop is a chain of shared-memory
+                // latencies on one lane: with a load pair per neighbour behind a branch each it was 10 deep, now 4)
+                const short4 q = *reinterpret_cast<const short4 *>(sm.nb[i]);
+                const short o0 = sm.own[max((int)q.x, 0)], o1 = sm.own[max((int)q.y, 0)], o2 = sm.own[max((int)q.z, 0)], o3 = sm.own[max((int)q.w, 0)];
+                if (q.x >= 0 && o0 == -3) sm.stack[sp++] = q.x;
+                if (q.y >= 0 && o1 == -3) sm.stack[sp++] = q.y;
+                if (q.z >= 0 && o2 == -3) sm.stack[sp++] = q.z;
+                if (q.w >= 0 && o3 == -3) sm.stack[sp++] = q.w;
             }
         }
         __syncwarp();
@@ -509,14 +527,17 @@ k_components(const int *__restrict__ cand_idx, const float *__restrict__ cand_va
                 sm.stack[sp++] = (short)pk;
                 while (sp > 0) {
                     const int i = sm.stack[--sp];
-                    if (sm.own[i] != -1 || !(sm.val[i] > T)) continue;
+                    const short oi = sm.own[i];
+                    const float vi = sm.val[i];
+                    if (oi != -1 || !(vi > T)) continue;
                     sm.own[i] = -2; // DROPPED unless accepted below
                     sm.S[ns++] = (short)i;
-#pragma unroll
-                    for (int d = 3; d >= 0; d--) {
-                        const int t = sm.nb[i][d];
-                        if (t >= 0 && sm.own[t] == -1) sm.stack[sp++] = (short)t;
-                    }
+                    const short4 q = *reinterpret_cast<const short4 *>(sm.nb[i]);
+                    const short o0 = sm.own[max((int)q.x, 0)], o1 = sm.own[max((int)q.y, 0)], o2 = sm.own[max((int)q.z, 0)], o3 = sm.own[max((int)q.w, 0)];
+                    if (q.w >= 0 && o3 == -1) sm.stack[sp++] = q.w;
+                    if (q.z >= 0 && o2 == -1) sm.stack[sp++] = q.z;
+                    if (q.y >= 0 && o1 == -1) sm.stack[sp++] = q.y;
+                    if (q.x >= 0 && o0 == -1) sm.stack[sp++] = q.x;
                 }
             }
             ns = __shfl_sync(0xffffffffu, ns, 0);
@@ -551,7 +572,7 @@ k_components(const int *__restrict__ cand_idx, const float *__restrict__ cand_va
                 if (lane == 0) { sm.acc_gx[nacc] = cx; sm.acc_gy[nacc] = cy; sm.stamp[nacc] = 0; }
                 nacc++;
                 __syncwarp();
-                const oss_star st = create_star_warp(sm, ns, lane);
+                const oss_star st = create_star_warp<CAP>(sm, ns, lane);
                 if (lane == 0) out[nout] = st;
                 nout++;
             }
@@ -562,7 +583,7 @@ k_components(const int *__restrict__ cand_idx, const float *__restrict__ cand_va
     }
 }
 
-// ---- K6b  one CTA per LARGE component (CW_CAP < n < OSS_DEBLEND_MAX) ----------------------------------------------------------
+// ---- K6b  one CTA per LARGE component (n > CW_CAP) ----------------------------------------------------------
 // Same algorithm and orders as k_components, for the components its per-warp scratch cannot hold (a saturated star with its
 // halo, a galaxy core: hundreds to thousands of pixels).  One thread replaying such a component over global memory costs
 // ~1 us per pixel and peel iteration (37 ms for one 1400-px blob, tools/big_blob_probe.py); here
@@ -681,7 +702,6 @@ __device__ void big_bypass(int c, int root, int n, int off, long long fb, const 
 }
 
 #define CBIG_NT 256
-constexpr int kCompBigSmall = 2048;
 template <int CB> struct CompBigSmem {
     float val[CB];
     short up[CB], dn[CB];
@@ -699,24 +719,26 @@ __global__ void __launch_bounds__(CBIG_NT)
 k_components_big(const int *__restrict__ cand_idx, const float *__restrict__ cand_val, const int4 *__restrict__ nbr,
                  const int *__restrict__ comp_size, const int *__restrict__ comp_root, const int *__restrict__ comp_off,
                  int *__restrict__ comp_nstar, int *__restrict__ scratch, oss_star *__restrict__ star_tmp, int *__restrict__ owner,
-                 const DetectState *__restrict__ ds, int nframes, int lo_excl, Geom g)
+                 const DetectState *__restrict__ ds, int nframes, Geom g)
 {
     extern __shared__ __align__(16) unsigned char comp_smem_raw[];
     CompBigSmem<CB> &sm = *reinterpret_cast<CompBigSmem<CB> *>(comp_smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    int item = 0; // running index over (frame, list entry) pairs of THIS instance's size class
+    constexpr bool kLarge = CB > CBIG_SMALL;
+    const int G = (int)gridDim.x;
+    int base = 0; // (frame, list entry) pairs before this frame: pair k goes to CTA k % G
     for (int f = 0; f < nframes; f++) {
         if (ds[f].overflow) continue;
-        const int nbig = ds[f].nbig;
+        const int nbig = kLarge ? ds[f].nbig3 : ds[f].nbig2;
         const long long fb = (long long)f * g.cap;
         int *scr = scratch + 12 * fb;
-        const int *big_list = scr + 11ll * g.cap;
+        const int *big_list = scr + 11ll * g.cap + g.cap / 2 + (kLarge ? g.cap / 4 : 0);
         const float step = ds[f].threshold;
-        for (int e = 0; e < nbig; e++) {
+        const int e0 = (((int)blockIdx.x - base) % G + G) % G;
+        base += nbig;
+        for (int e = e0; e < nbig; e += G) {
             const int c = big_list[e];
             const int n = comp_size[fb + comp_root[fb + c]];
-            if (n <= lo_excl || (n > CB && CB < OSS_DEBLEND_MAX - 1)) continue;
-            if ((item++) % (int)gridDim.x != (int)blockIdx.x) continue;
             const int off = comp_off[fb + c];
             if (n >= OSS_DEBLEND_MAX) { // adjoiningpixel.cpp:45-48: no deblending, ONE star from the whole component
                 if (CB == OSS_DEBLEND_MAX - 1) big_bypass(c, comp_root[fb + c], n, off, fb, cand_idx, cand_val, nbr, owner, scr, star_tmp, comp_nstar, sm.red_v, g);
@@ -775,10 +797,11 @@ k_components_big(const int *__restrict__ cand_idx, const float *__restrict__ can
                     sm.st[i] = s0 | 1; // REMAINING
                     sm.lpos[i] = (short)np++;
                     const int u = sm.up[i], d = sm.dn[i];
-                    if (u >= 0 && !(sm.st[u] & 3)) sm.stack[sp++] = (short)u;
-                    if ((s0 & 4) && !(sm.st[i - 1] & 3)) sm.stack[sp++] = (short)(i - 1);
-                    if ((s0 & 8) && !(sm.st[i + 1] & 3)) sm.stack[sp++] = (short)(i + 1);
-                    if (d >= 0 && !(sm.st[d] & 3)) sm.stack[sp++] = (short)d;
+                    const unsigned char su = sm.st[max(u, 0)], sl = sm.st[max(i - 1, 0)], sr = sm.st[min(i + 1, n - 1)], sd = sm.st[max(d, 0)];
+                    if (u >= 0 && !(su & 3)) sm.stack[sp++] = (short)u;
+                    if ((s0 & 4) && !(sl & 3)) sm.stack[sp++] = (short)(i - 1);
+                    if ((s0 & 8) && !(sr & 3)) sm.stack[sp++] = (short)(i + 1);
+                    if (d >= 0 && !(sd & 3)) sm.stack[sp++] = (short)d;
                 }
             }
             __syncthreads();
@@ -821,14 +844,16 @@ k_components_big(const int *__restrict__ cand_idx, const float *__restrict__ can
                     while (sp > 0) {
                         const int i = sm.stack[--sp];
                         const unsigned char s0 = sm.st[i];
-                        if ((s0 & 3) != 1 || !(sm.val[i] > T)) continue;
+                        const float vi = sm.val[i];
+                        if ((s0 & 3) != 1 || !(vi > T)) continue;
                         sm.st[i] = (s0 & ~3) | 2; // DROPPED unless accepted below
                         sm.S[ns0++] = (short)i;
                         const int u = sm.up[i], d = sm.dn[i];
-                        if (d >= 0 && (sm.st[d] & 3) == 1) sm.stack[sp++] = (short)d;
-                        if ((s0 & 8) && (sm.st[i + 1] & 3) == 1) sm.stack[sp++] = (short)(i + 1);
-                        if ((s0 & 4) && (sm.st[i - 1] & 3) == 1) sm.stack[sp++] = (short)(i - 1);
-                        if (u >= 0 && (sm.st[u] & 3) == 1) sm.stack[sp++] = (short)u;
+                        const unsigned char su = sm.st[max(u, 0)], sl = sm.st[max(i - 1, 0)], sr = sm.st[min(i + 1, n - 1)], sd = sm.st[max(d, 0)];
+                        if (d >= 0 && (sd & 3) == 1) sm.stack[sp++] = (short)d;
+                        if ((s0 & 8) && (sr & 3) == 1) sm.stack[sp++] = (short)(i + 1);
+                        if ((s0 & 4) && (sl & 3) == 1) sm.stack[sp++] = (short)(i - 1);
+                        if (u >= 0 && (su & 3) == 1) sm.stack[sp++] = (short)u;
                     }
                     sm.bc[0] = ns0;
                 }

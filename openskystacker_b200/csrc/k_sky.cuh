@@ -589,7 +589,7 @@ __global__ void k_finalize_stats(const double *__restrict__ partials, long long 
         d.mean = m; d.sigma = sigma;
         d.threshold = (float)(sigma * (double)threshold_coeff * 1.5);
         d.minpeak = (float)(sigma * (double)threshold_coeff * 2.0);
-        d.ncand = 0; d.nroots = 0; d.ncomp = 0; d.nstars = 0; d.overflow = 0; d.nbig = 0;
+        d.ncand = 0; d.nroots = 0; d.ncomp = 0; d.nstars = 0; d.overflow = 0; d.nbig = 0; d.nbig2 = 0; d.nbig3 = 0;
         ds[f] = d;
     }
 }

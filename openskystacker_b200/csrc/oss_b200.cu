@@ -480,8 +480,9 @@ int oss_create(oss_ctx **out, int device)
         cudaMemcpyToSymbol(d_tri_ijk, ijk.data(), ijk.size() * 4) != cudaSuccess ||
         cudaFuncSetAttribute(k_sky_sub_stats, cudaFuncAttributeMaxDynamicSharedMemorySize, kSkySmemBytes) != cudaSuccess ||
         cudaFuncSetAttribute(k_focas, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FocasSmem)) != cudaSuccess ||
-        cudaFuncSetAttribute(k_components, cudaFuncAttributeMaxDynamicSharedMemorySize, kCompSmemBytes) != cudaSuccess ||
-        cudaFuncSetAttribute(k_components_big<kCompBigSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CompBigSmem<kCompBigSmall>)) != cudaSuccess ||
+        cudaFuncSetAttribute(k_components<CW_CAP, CW_WARPS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCompSmemBytes) != cudaSuccess ||
+        cudaFuncSetAttribute(k_components<CW_CAP_SMALL, CW_WARPS_SMALL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCompSmemBytesSmall) != cudaSuccess ||
+        cudaFuncSetAttribute(k_components_big<CBIG_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CompBigSmem<CBIG_SMALL>)) != cudaSuccess ||
         cudaFuncSetAttribute(k_components_big<OSS_DEBLEND_MAX - 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CompBigSmem<OSS_DEBLEND_MAX - 1>)) != cudaSuccess ||
         cudaFuncSetAttribute(k_warp_accumulate_tiled<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, warp_tiled_smem<3>()) != cudaSuccess ||
         cudaFuncSetAttribute(k_warp_accumulate_tiled<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, warp_tiled_smem<1>()) != cudaSuccess ||
@@ -903,13 +904,17 @@ static int run_detect_tail(oss_ctx *c, int n, int threshold)
     if (r) return r;
     LAUNCH("gather_roots", k_gather_roots, dim3(gs, n), 256, 0, w.flag, w.flagscan, w.comp_staroff, w.comp_root, w.comp_off, w.comp_nstar, w.ds, g);
     LAUNCH("comp_members", k_comp_members, dim3(gs, n), 256, 0, w.parent, w.flag, w.flagscan, w.comp_off, w.comp_nstar, w.scratch, w.ds, g);
-    LAUNCH("components", k_components, dim3(kSparseGrid, n), 32 * CW_WARPS, kCompSmemBytes, w.cand_idx, w.cand_val, w.nbr, w.owner, w.comp_size,
-           w.comp_root, w.comp_off, w.comp_nstar, w.scratch, w.star_tmp, w.ds, g);
-    // components of more than CW_CAP pixels (listed by k_components): one CTA each, two shared-memory size classes
-    LAUNCH("components_big", k_components_big<kCompBigSmall>, 32, CBIG_NT, sizeof(CompBigSmem<kCompBigSmall>), w.cand_idx, w.cand_val, w.nbr,
-           w.comp_size, w.comp_root, w.comp_off, w.comp_nstar, w.scratch, w.star_tmp, w.owner, w.ds, n, CW_CAP, g);
-    LAUNCH("components_big", k_components_big<OSS_DEBLEND_MAX - 1>, 8, CBIG_NT, sizeof(CompBigSmem<OSS_DEBLEND_MAX - 1>), w.cand_idx, w.cand_val,
-           w.nbr, w.comp_size, w.comp_root, w.comp_off, w.comp_nstar, w.scratch, w.star_tmp, w.owner, w.ds, n, kCompBigSmall, g);
+    LAUNCH("components", (k_components<CW_CAP_SMALL, CW_WARPS_SMALL, false>), dim3(kSparseGrid, n), 32 * CW_WARPS_SMALL, kCompSmemBytesSmall, w.cand_idx,
+           w.cand_val, w.nbr, w.owner, w.comp_size, w.comp_root, w.comp_off, w.comp_nstar, w.scratch, w.star_tmp, w.ds, g);
+    LAUNCH("components", (k_components<CW_CAP, CW_WARPS, true>), dim3(kSparseGrid / 2, n), 32 * CW_WARPS, kCompSmemBytes, w.cand_idx, w.cand_val, w.nbr,
+           w.owner, w.comp_size, w.comp_root, w.comp_off, w.comp_nstar, w.scratch, w.star_tmp, w.ds, g);
+    // components of more than CW_CAP pixels (listed by k_components): one CTA each, two shared-memory size classes.  The grids are
+    // what a star-heavy batch needs (61 MP at threshold 5: ~50 components above 256 px per frame, ~0.1 ms each on its CTA's thread 0);
+    // CTAs without work leave at once, but each of the second instance's needs an SM to itself first (210 KB), hence only 16
+    LAUNCH("components_big", k_components_big<CBIG_SMALL>, 296, CBIG_NT, sizeof(CompBigSmem<CBIG_SMALL>), w.cand_idx, w.cand_val, w.nbr,
+           w.comp_size, w.comp_root, w.comp_off, w.comp_nstar, w.scratch, w.star_tmp, w.owner, w.ds, n, g);
+    LAUNCH("components_big", k_components_big<OSS_DEBLEND_MAX - 1>, 16, CBIG_NT, sizeof(CompBigSmem<OSS_DEBLEND_MAX - 1>), w.cand_idx, w.cand_val,
+           w.nbr, w.comp_size, w.comp_root, w.comp_off, w.comp_nstar, w.scratch, w.star_tmp, w.owner, w.ds, n, g);
     r = run_scan(c, w.comp_nstar, g.cap, w.comp_staroff, g.cap, ncomp, DS, g.cap, n, nstars, DS);
     if (r) return r;
     LAUNCH("gather_stars", k_gather_stars, dim3(gs, n), 256, 0, w.star_tmp, w.comp_off, w.comp_nstar, w.comp_staroff, w.star_out,
