@@ -302,33 +302,44 @@ k_root_flags(const int *__restrict__ parent, const int *__restrict__ comp_size, 
     }
 }
 
-// comp_root[c] = list position of component c's first pixel, comp_off[c] = scratch offset
+// comp_root[c] = list position of component c's first pixel, comp_off[c] = scratch offset; components above CW_CAP_SMALL pixels
+// are also listed by size class for the later k_components / k_components_big instances (scratch region [11 cap, 12 cap):
+// nobody else's; counters in DetectState, zeroed by k_finalize_stats)
+#define CBIG_SMALL 2048   // first size class of k_components_big
+#define CW_CAP_SMALL 64
+#define CW_CAP 256
+__device__ __forceinline__ int *class_list(int *scratch, long long fb, const Geom &g, int cls) // 0: 65..256 px, 1: ..2048, 2: larger
+{
+    return scratch + 12 * fb + 11ll * g.cap + (cls == 0 ? 0 : (cls == 1 ? g.cap / 2 : g.cap / 2 + g.cap / 4));
+}
 __global__ void __launch_bounds__(256)
 k_gather_roots(const int *__restrict__ flag, const int *__restrict__ flagscan, const int *__restrict__ sizescan,
-               int *__restrict__ comp_root, int *__restrict__ comp_off, int *__restrict__ fill, const DetectState *__restrict__ ds, Geom g)
+               const int *__restrict__ comp_size, int *__restrict__ comp_root, int *__restrict__ comp_off, int *__restrict__ fill,
+               int *__restrict__ scratch, DetectState *__restrict__ ds, Geom g)
 {
     const int f = blockIdx.y;
     if (ds[f].overflow) return;
     const int n = ds[f].ncand;
+    const long long fb = (long long)f * g.cap;
     for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
-        long long q = (long long)f * g.cap + i;
+        long long q = fb + i;
         if (flag[q]) {
-            long long c = (long long)f * g.cap + flagscan[q];
+            const int ci = flagscan[q];
+            long long c = fb + ci;
             comp_root[c] = i;
             comp_off[c] = sizescan[q];
             fill[c] = 0; // member counter of k_comp_members (the array is comp_nstar: k_components overwrites it afterwards)
+            const int sz = comp_size[q];
+            if (sz > CW_CAP_SMALL) {
+                const int cls = sz <= CW_CAP ? 0 : (sz <= CBIG_SMALL ? 1 : 2);
+                int *cnt = cls == 0 ? &ds[f].nbig : (cls == 1 ? &ds[f].nbig2 : &ds[f].nbig3);
+                class_list(scratch, fb, g, cls)[atomicAdd(cnt, 1)] = ci;
+            }
         }
     }
 }
 
 // ---- K6  per-component replay of the reference's sequential logic -----------------------
-struct CompScratch {
-    int *list;    // [n]   pixels in the reference's DFS order
-    int *stack;   // [4n+1]
-    int *S;       // [n]   current peeled region, extraction order
-    int *sorted;  // [n]
-    int *acc_gx, *acc_gy, *stamp; // [n] per accepted region
-};
 
 // ---- K6  one WARP per component ----------------------------------------------------------
 // The component's pixels (k_comp_members: an unordered scatter by label) are staged in shared memory, sorted back into raster
@@ -341,12 +352,10 @@ struct CompScratch {
 // One thread per component over global memory (the first version) made the largest component of a batch its critical
 // path: ~2 us per pixel, 1.3 ms per 17-frame batch; here it is ~0.1 us per pixel.
 // Two instances: CAP = 64 (3.2 KB per warp, 8 warps per CTA: ~48 resident warps per SM — the kernel is latency-bound on lane 0's
-// traversals, so residency is throughput; it walks over ALL components and lists the larger ones) and CAP = 256 (12.5 KB per
-// warp, 4 warps per CTA) over that list; what exceeds 256 pixels stays on the list for k_components_big.
-#define CBIG_SMALL 2048   // first size class of k_components_big
-#define CW_CAP_SMALL 64
+// traversals, so residency is throughput; it walks over ALL components and skips the larger ones) and CAP = 256 (12.5 KB per
+// warp, 4 warps per CTA) over k_gather_roots' list of the 65..256-px components; the two (and k_components_big) are independent
+// and run side by side on two streams.
 #define CW_WARPS_SMALL 8
-#define CW_CAP 256
 #define CW_WARPS 4
 template <int CAP> struct CompWarpSmem {
     int gidx[CAP];            // candidate-list positions, ascending = raster order
@@ -413,7 +422,7 @@ __global__ void __launch_bounds__(32 * WARPS)
 k_components(const int *__restrict__ cand_idx, const float *__restrict__ cand_val, const int4 *__restrict__ nbr,
              int *__restrict__ owner, const int *__restrict__ comp_size, const int *__restrict__ comp_root,
              const int *__restrict__ comp_off, int *__restrict__ comp_nstar, int *__restrict__ scratch,
-             oss_star *__restrict__ star_tmp, DetectState *__restrict__ ds, Geom g)
+             oss_star *__restrict__ star_tmp, const DetectState *__restrict__ ds, Geom g)
 {
     extern __shared__ __align__(16) unsigned char comp_smem_raw[];
     const int f = blockIdx.y;
@@ -425,24 +434,17 @@ k_components(const int *__restrict__ cand_idx, const float *__restrict__ cand_va
     const float *cval = cand_val + fb;
     const int4 *nb = nbr + fb;
     int *scr = scratch + 12 * fb;
-    int *big_list = scr + 11ll * g.cap; // [11 cap, 12 cap) of the scratch is nobody's: components above CW_CAP_SMALL pixels
+    const int *mid_list = class_list(scratch, fb, g, 0);
     const float step = ds[f].threshold;
     const int nitems = FROM_LIST ? ds[f].nbig : ds[f].ncomp;
 
     for (int e = blockIdx.x * WARPS + wid; e < nitems; e += gridDim.x * WARPS) {
-        const int c = FROM_LIST ? big_list[e] : e;
+        const int c = FROM_LIST ? mid_list[e] : e;
         const int root = comp_root[fb + c];
         const int n = comp_size[fb + root];
         const int off = comp_off[fb + c];
         oss_star *out = star_tmp + fb + off;
-        if (n > CAP) { // the next instance (or k_components_big: one CTA per component, incl. the >= 10000-px bypass) takes it
-            if (lane == 0) {
-                if (!FROM_LIST) big_list[atomicAdd(&ds[f].nbig, 1)] = c;
-                else if (n <= CBIG_SMALL) big_list[g.cap / 2 + atomicAdd(&ds[f].nbig2, 1)] = c; // per size class of k_components_big,
-                else big_list[g.cap / 2 + g.cap / 4 + atomicAdd(&ds[f].nbig3, 1)] = c;          // further along the same region
-            }
-            continue;
-        }
+        if (n > CAP) continue; // another instance's (k_gather_roots' lists)
         // ---- stage: members (any order) -> ascending candidate positions (rank sort; positions are distinct)
         const int *member = scr + off;
         for (int k = lane; k < n; k += 32) sm.px[k] = member[k];
@@ -732,7 +734,7 @@ k_components_big(const int *__restrict__ cand_idx, const float *__restrict__ can
         const int nbig = kLarge ? ds[f].nbig3 : ds[f].nbig2;
         const long long fb = (long long)f * g.cap;
         int *scr = scratch + 12 * fb;
-        const int *big_list = scr + 11ll * g.cap + g.cap / 2 + (kLarge ? g.cap / 4 : 0);
+        const int *big_list = class_list(scratch, fb, g, kLarge ? 2 : 1);
         const float step = ds[f].threshold;
         const int e0 = (((int)blockIdx.x - base) % G + G) % G;
         base += nbig;

@@ -81,11 +81,13 @@ static bool nccl_load(std::string *why)
 struct Pipe {
     cudaStream_t copy_stream = nullptr;  // H2D staging copies of this pipeline
     cudaStream_t chain_stream = nullptr; // high priority: the latency-bound detection tail + alignment of a batch
+    cudaStream_t side_stream = nullptr;  // high priority: the large-component kernels of a batch, beside the small-component one
     Workspace ws{};
     int *d_xy = nullptr, *d_nxy = nullptr;
     unsigned char *raw_stage[2] = {nullptr, nullptr};
     cudaEvent_t copy_done[2] = {nullptr, nullptr}, raw_free[2] = {nullptr, nullptr};
     cudaEvent_t warp_done = nullptr, detect_done = nullptr, sky_done = nullptr, cal_done = nullptr, med_done = nullptr;
+    cudaEvent_t side_fork = nullptr, side_join = nullptr;
     CUtensorMap cal_map;       // [slot][row][column * channel] view of ws.cal for the TMA warp kernel
     bool has_cal_map = false;
     long long batch_counter = 0;
@@ -317,6 +319,8 @@ static void free_geometry(oss_ctx *c)
         if (pp.sky_done) { cudaEventDestroy(pp.sky_done); pp.sky_done = nullptr; }
         if (pp.cal_done) { cudaEventDestroy(pp.cal_done); pp.cal_done = nullptr; }
         if (pp.med_done) { cudaEventDestroy(pp.med_done); pp.med_done = nullptr; }
+        if (pp.side_fork) { cudaEventDestroy(pp.side_fork); pp.side_fork = nullptr; }
+        if (pp.side_join) { cudaEventDestroy(pp.side_join); pp.side_join = nullptr; }
         pp.ws = Workspace{};
         pp.d_xy = pp.d_nxy = nullptr;
         pp.batch_counter = 0;
@@ -454,6 +458,7 @@ int oss_create(oss_ctx **out, int device)
     ok = ok && cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest) == cudaSuccess;
     for (int p = 0; ok && p < OSS_MAX_PIPES; p++)
         ok = cudaStreamCreateWithPriority(&c->pipes[p].chain_stream, cudaStreamNonBlocking, prio_greatest) == cudaSuccess &&
+             cudaStreamCreateWithPriority(&c->pipes[p].side_stream, cudaStreamNonBlocking, prio_greatest) == cudaSuccess &&
              cudaStreamCreateWithPriority(&c->pipes[p].copy_stream, cudaStreamNonBlocking, prio_greatest) == cudaSuccess;
     ok = ok && cudaStreamCreateWithPriority(&c->bulk, cudaStreamNonBlocking, prio_least) == cudaSuccess;
     if (!ok) { oss_destroy(c); return OSS_E_CUDA; } // oss_destroy null-checks every member: fine on a partly built ctx
@@ -507,7 +512,7 @@ void oss_destroy(oss_ctx *c)
     for (auto p : c->h_al_chunks) cudaFreeHost(p);
     prof_flush(c);
     for (auto e : c->event_pool) cudaEventDestroy(e);
-    for (int p = 0; p < OSS_MAX_PIPES; p++) { if (c->pipes[p].copy_stream) cudaStreamDestroy(c->pipes[p].copy_stream); if (c->pipes[p].chain_stream) cudaStreamDestroy(c->pipes[p].chain_stream); }
+    for (int p = 0; p < OSS_MAX_PIPES; p++) { if (c->pipes[p].copy_stream) cudaStreamDestroy(c->pipes[p].copy_stream); if (c->pipes[p].chain_stream) cudaStreamDestroy(c->pipes[p].chain_stream); if (c->pipes[p].side_stream) cudaStreamDestroy(c->pipes[p].side_stream); }
     split_teardown(c);
     for (auto &t : c->tickets) if (t) cudaEventDestroy(t);
     if (c->ticket_stream) cudaStreamDestroy(c->ticket_stream);
@@ -661,6 +666,8 @@ int oss_set_geometry(oss_ctx *c, int W, int H, int C, int sample, int slots)
         CK(cudaEventCreateWithFlags(&pp.sky_done, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&pp.cal_done, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&pp.med_done, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&pp.side_fork, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&pp.side_join, cudaEventDisableTiming));
         pp.has_cal_map = make_cal_map(c, pp, slots);
         pp.batch_counter = 0;
     }
@@ -902,19 +909,32 @@ static int run_detect_tail(oss_ctx *c, int n, int threshold)
     if (r) return r;
     r = run_scan(c, w.comp_staroff, g.cap, w.comp_staroff, g.cap, ncand, DS, g.cap, n, nullptr, 0);
     if (r) return r;
-    LAUNCH("gather_roots", k_gather_roots, dim3(gs, n), 256, 0, w.flag, w.flagscan, w.comp_staroff, w.comp_root, w.comp_off, w.comp_nstar, w.ds, g);
+    LAUNCH("gather_roots", k_gather_roots, dim3(gs, n), 256, 0, w.flag, w.flagscan, w.comp_staroff, w.comp_size, w.comp_root, w.comp_off, w.comp_nstar,
+           w.scratch, w.ds, g);
     LAUNCH("comp_members", k_comp_members, dim3(gs, n), 256, 0, w.parent, w.flag, w.flagscan, w.comp_off, w.comp_nstar, w.scratch, w.ds, g);
-    LAUNCH("components", (k_components<CW_CAP_SMALL, CW_WARPS_SMALL, false>), dim3(kSparseGrid, n), 32 * CW_WARPS_SMALL, kCompSmemBytesSmall, w.cand_idx,
-           w.cand_val, w.nbr, w.owner, w.comp_size, w.comp_root, w.comp_off, w.comp_nstar, w.scratch, w.star_tmp, w.ds, g);
-    LAUNCH("components", (k_components<CW_CAP, CW_WARPS, true>), dim3(kSparseGrid / 2, n), 32 * CW_WARPS, kCompSmemBytes, w.cand_idx, w.cand_val, w.nbr,
-           w.owner, w.comp_size, w.comp_root, w.comp_off, w.comp_nstar, w.scratch, w.star_tmp, w.ds, g);
-    // components of more than CW_CAP pixels (listed by k_components): one CTA each, two shared-memory size classes.  The grids are
-    // what a star-heavy batch needs (61 MP at threshold 5: ~50 components above 256 px per frame, ~0.1 ms each on its CTA's thread 0);
-    // CTAs without work leave at once, but each of the second instance's needs an SM to itself first (210 KB), hence only 16
-    LAUNCH("components_big", k_components_big<CBIG_SMALL>, 296, CBIG_NT, sizeof(CompBigSmem<CBIG_SMALL>), w.cand_idx, w.cand_val, w.nbr,
-           w.comp_size, w.comp_root, w.comp_off, w.comp_nstar, w.scratch, w.star_tmp, w.owner, w.ds, n, g);
-    LAUNCH("components_big", k_components_big<OSS_DEBLEND_MAX - 1>, 16, CBIG_NT, sizeof(CompBigSmem<OSS_DEBLEND_MAX - 1>), w.cand_idx, w.cand_val,
-           w.nbr, w.comp_size, w.comp_root, w.comp_off, w.comp_nstar, w.scratch, w.star_tmp, w.owner, w.ds, n, g);
+    // One warp per component up to 64 px (all components walked, larger ones skipped) on this stream; beside it, on the pipeline's
+    // side stream, the size classes k_gather_roots listed: 65..256 px (one warp each), ..2048 px and larger (one CTA each, the
+    // last one incl. the >= 10000-px bypass).  The big grids are what a star-heavy batch needs (61 MP at threshold 5: ~50 components
+    // above 256 px per frame, ~0.1 ms each on its CTA's thread 0); CTAs without work leave at once, but each of the last instance's
+    // needs an SM to itself first (210 KB), hence only 16.
+    {
+        Pipe &pp = c->pipes[c->cur];
+        cudaStream_t main = c->stream;
+        CK(cudaEventRecord(pp.side_fork, main));
+        LAUNCH("components", (k_components<CW_CAP_SMALL, CW_WARPS_SMALL, false>), dim3(kSparseGrid, n), 32 * CW_WARPS_SMALL, kCompSmemBytesSmall,
+               w.cand_idx, w.cand_val, w.nbr, w.owner, w.comp_size, w.comp_root, w.comp_off, w.comp_nstar, w.scratch, w.star_tmp, w.ds, g);
+        c->stream = pp.side_stream;
+        CK(cudaStreamWaitEvent(c->stream, pp.side_fork, 0));
+        LAUNCH("components_mid", (k_components<CW_CAP, CW_WARPS, true>), dim3(kSparseGrid, n), 32 * CW_WARPS, kCompSmemBytes, w.cand_idx, w.cand_val,
+               w.nbr, w.owner, w.comp_size, w.comp_root, w.comp_off, w.comp_nstar, w.scratch, w.star_tmp, w.ds, g);
+        LAUNCH("components_big", k_components_big<CBIG_SMALL>, 296, CBIG_NT, sizeof(CompBigSmem<CBIG_SMALL>), w.cand_idx, w.cand_val, w.nbr,
+               w.comp_size, w.comp_root, w.comp_off, w.comp_nstar, w.scratch, w.star_tmp, w.owner, w.ds, n, g);
+        LAUNCH("components_big", k_components_big<OSS_DEBLEND_MAX - 1>, 16, CBIG_NT, sizeof(CompBigSmem<OSS_DEBLEND_MAX - 1>), w.cand_idx,
+               w.cand_val, w.nbr, w.comp_size, w.comp_root, w.comp_off, w.comp_nstar, w.scratch, w.star_tmp, w.owner, w.ds, n, g);
+        CK(cudaEventRecord(pp.side_join, c->stream));
+        c->stream = main;
+        CK(cudaStreamWaitEvent(c->stream, pp.side_join, 0));
+    }
     r = run_scan(c, w.comp_nstar, g.cap, w.comp_staroff, g.cap, ncomp, DS, g.cap, n, nstars, DS);
     if (r) return r;
     LAUNCH("gather_stars", k_gather_stars, dim3(gs, n), 256, 0, w.star_tmp, w.comp_off, w.comp_nstar, w.comp_staroff, w.star_out,
