@@ -79,6 +79,29 @@ def _gloo_worker(rank, world, port, out):
     dist.destroy_process_group()
 
 
+def test_host_fed_balance_shares():
+    """bench.py's split of the host-fed lights over ranks with unequal host links (balance_host_fed): every light is handed out
+    exactly once, every rank keeps at least one, ranks finish together within one frame's copy time, and equal links with
+    equal extras give equal shares."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(os.path.dirname(__file__), "..", "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    rates = [23.4] * 4 + [35.9] * 4                     # what this pool's 8-GPU box gives when all ranks copy at once
+    extras = [30 / 8 + 1] + [30 / 8] * 7                # 1/8 of the calibration frames each, the reference on rank 0
+    n = bench.balance_host_fed(rates, extras, 400)
+    assert sum(n) == 400 and min(n) >= 1
+    t = [(k + e) / r for k, e, r in zip(n, extras, rates)]
+    assert max(t) - min(t) <= 1.0 / min(rates) + 1e-9   # finishing times within one frame on the slowest link
+    assert bench.balance_host_fed([50.0] * 4, [2.0] * 4, 200) == [50] * 4
+    assert bench.balance_host_fed([1.0, 1000.0], [0, 0], 10) == [1, 9]
+    for world in (2, 3, 5, 8):
+        for total in (world, 7 * world + 3, 400):
+            r = [10.0 + 3 * i for i in range(world)]
+            n = bench.balance_host_fed(r, [1.0] * world, total)
+            assert sum(n) == total and min(n) >= 1, (world, total, n)
+
+
 def test_two_gloo_ranks_reproduce_the_single_process_stack():
     ds = dataset()
     want = oracle.stack(ds["ref"], ds["lights"], 20, dark_frames=ds["darks"])
