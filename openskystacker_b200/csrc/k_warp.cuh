@@ -284,8 +284,12 @@ k_copy_f32(const float *__restrict__ src, float *__restrict__ dst, long long cou
 // (util.cpp:736,749); the reference frame joins at the end like workingImage += partial
 // (imagestacker.cpp:287,349), then Mat /= n  ==  x * float(1.0/n) (imagestacker.cpp:361).
 __global__ void __launch_bounds__(256)
-k_finalize(const float *__restrict__ sum, const float *__restrict__ ref, float *__restrict__ out, long long count, float r)
+k_finalize(const float *__restrict__ sum, const float *__restrict__ ref, float *__restrict__ out, long long count,
+           const int *__restrict__ valid_lights)
 {
+    // totalValidImages is read where it lives (no host round trip between the last warp and this kernel); the reference frame
+    // counts as one (imagestacker.cpp:304).  Fewer than 2: the host reports the reference's error, whatever lands in `out`.
+    const float r = (float)(1.0 / (double)(*valid_lights + (ref ? 1 : 0)));
     const long long i0 = ((long long)blockIdx.x * 256 + threadIdx.x) * 4;
     if (i0 + 4 <= count) {
         float4 q = ((const float4 *)(sum + i0))[0];

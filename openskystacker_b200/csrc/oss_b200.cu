@@ -1415,20 +1415,33 @@ int oss_get_sum(oss_ctx *c, float *out, int *tv)
 
 int oss_finish(oss_ctx *c, float *out, int *tv)
 {
-    USE_PIPE0();
+    if (!c) return OSS_E_ARG;
+    { int r_ = need_geom(c); if (r_) return r_; }
     if (!c->has_ref) return fail(c, OSS_E_ARG, "no reference");
+    const long long PC = c->g.P * c->g.C;
+    // (sum [+ reference]) * float(1 / totalValidImages), the count taken on the device.  Single GPU: queued straight behind the
+    // last warp, BEFORE the host drains the streams for its checks (an error found there is returned whatever landed in the
+    // result plane); with a communicator the reduce on the comm stream has to be over first.
+    bool queued = false;
+    if (!c->comm_stream) {
+        if (flush_warps(c, 0, 1, nullptr) != OSS_OK) return OSS_E_CUDA;
+        select_pipe(c, 0);
+        LAUNCH("finalize", k_finalize, (unsigned)((PC + 1023) / 1024), 256, 0, c->sum, c->ref_in_sum ? c->ref_cal : (const float *)nullptr,
+               c->result, PC, c->d_valid);
+        queued = true;
+    }
+    USE_PIPE0();
     { int rc = ref_host(c); if (rc) return rc; } // a reference that overflowed the work space invalidates the stack
     CK(cudaStreamSynchronize(c->copy_stream));
     { int rc = check_light_overflow(c); if (rc) return rc; }
+    if (!queued)
+        LAUNCH("finalize", k_finalize, (unsigned)((PC + 1023) / 1024), 256, 0, c->sum, c->ref_in_sum ? c->ref_cal : (const float *)nullptr,
+               c->result, PC, c->d_valid);
     int v;
     int rc = total_valid(c, &v);
     if (rc) return rc;
     if (tv) *tv = v;
     if (v < 2) return fail(c, OSS_E_NO_ALIGNED, "%s", oss_status_string(OSS_E_NO_ALIGNED));
-    const long long PC = c->g.P * c->g.C;
-    const float r = (float)(1.0 / (double)v);
-    LAUNCH("finalize", k_finalize, (unsigned)((PC + 1023) / 1024), 256, 0, c->sum, c->ref_in_sum ? c->ref_cal : (const float *)nullptr,
-           c->result, PC, r);
     if (out) return oss_memcpy_d2h(c, out, c->result, (size_t)PC * sizeof(float));
     CK(cudaStreamSynchronize(c->stream));
     return OSS_OK;
