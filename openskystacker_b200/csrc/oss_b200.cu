@@ -130,6 +130,7 @@ struct oss_ctx {
     float *master[4] = {nullptr, nullptr, nullptr, nullptr};
     float *sum = nullptr, *ref_cal = nullptr, *result = nullptr;
     bool has_ref = false, ref_in_sum = true;
+    bool dirty = true;                   // something was queued on a chain / side stream (or a warp deferred) since the last sync_all
     int threshold = 20;
     int *d_valid = nullptr;
     int extra_valid = 0; // lights counted on other ranks (after oss_comm_reduce)
@@ -214,6 +215,7 @@ static cudaError_t sync_all(oss_ctx *c, bool with_comm = true)
     if (c->bulk) { cudaError_t r = cudaStreamSynchronize(c->bulk); if (r != cudaSuccess) e = r; }
     if (c->fp_stream) { cudaError_t r = cudaStreamSynchronize(c->fp_stream); if (r != cudaSuccess) e = r; }
     if (with_comm && c->comm_stream) { cudaError_t r = cudaStreamSynchronize(c->comm_stream); if (r != cudaSuccess) e = r; }
+    c->dirty = false;
     return e;
 }
 
@@ -282,6 +284,7 @@ static void prof_flush(oss_ctx *c)
             pp_.a = get_event(c); pp_.b = get_event(c);                              \
             cudaEventRecord(pp_.a, c->stream);                                       \
         }                                                                            \
+        if (c->stream != c->bulk) c->dirty = true;                                   \
         kern<<<grid, block, smem, c->stream>>>(__VA_ARGS__);                         \
         c->launches++;                                                               \
         if (c->profiling) { cudaEventRecord(pp_.b, c->stream); c->prof_pending.push_back(pp_); } \
@@ -973,10 +976,14 @@ static int need_geom(oss_ctx *c)
     do {                                                                                       \
         int r_ = need_geom(c);                                                                 \
         if (r_) return r_;                                                                     \
-        cudaError_t e_ = sync_all(c, false);                                                   \
-        if (e_ != cudaSuccess) return fail(c, OSS_E_CUDA, "stream sync failed: %s", cudaGetErrorString(e_)); \
+        if (c->dirty || !c->pending_warps.empty()) {                                           \
+            cudaError_t e_ = sync_all(c, false);                                               \
+            if (e_ != cudaSuccess) return fail(c, OSS_E_CUDA, "stream sync failed: %s", cudaGetErrorString(e_)); \
+        }                                                                                      \
         select_pipe(c, 0);                                                                     \
     } while (0)
+// (not dirty: whatever is still in flight — masters being built, a finalize — sits on the bulk stream, and so does everything
+// these calls queue first: stream order is enough, and the host can run ahead of the GPU instead of draining ~12 streams)
 
 extern "C" {
 
@@ -1106,12 +1113,10 @@ int oss_clear_masters(oss_ctx *c)
 }
 
 // ---- stacking --------------------------------------------------------------------------
-int oss_reset_stack(oss_ctx *c)
+static int reset_stack_async(oss_ctx *c)
 {
-    USE_PIPE0_LOCAL();
     CK(cudaMemsetAsync(c->sum, 0, (size_t)c->g.P * c->g.C * sizeof(float), c->stream));
     CK(cudaMemsetAsync(c->d_valid, 0, 16, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
     c->has_ref = false;
     c->ref_in_sum = true;
     c->nlights = 0;
@@ -1122,11 +1127,20 @@ int oss_reset_stack(oss_ctx *c)
     return OSS_OK;
 }
 
+int oss_reset_stack(oss_ctx *c)
+{
+    USE_PIPE0_LOCAL();
+    int rc = reset_stack_async(c);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(c->stream));
+    return OSS_OK;
+}
+
 int oss_set_reference(oss_ctx *c, const void *frame, int mem, int threshold)
 {
     USE_PIPE0_LOCAL();
     if (!frame) return fail(c, OSS_E_ARG, "null reference frame");
-    int rc = oss_reset_stack(c);
+    int rc = reset_stack_async(c); // on the bulk stream, in front of everything the new stack queues
     if (rc) return rc;
     const Geom &g = c->g;
     Workspace &w = c->ws;
