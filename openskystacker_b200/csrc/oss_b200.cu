@@ -130,6 +130,7 @@ struct oss_ctx {
     float *master[4] = {nullptr, nullptr, nullptr, nullptr};
     float *sum = nullptr, *ref_cal = nullptr, *result = nullptr;
     bool has_ref = false, ref_in_sum = true;
+    bool slot0_is_ref = false;           // oss_debug_copy: the calibrated plane of "slot 0" is the reference's (it lives in ref_cal)
     bool dirty = true;                   // something was queued on a chain / side stream (or a warp deferred) since the last sync_all
     int threshold = 20;
     int *d_valid = nullptr;
@@ -830,6 +831,7 @@ static int run_detect_tail(oss_ctx *c, int n, int threshold);
 //   run_detect_tail   CHAIN stream: thresholding ... star lists
 static int detect_calibrate(oss_ctx *c, const FramePtrs &fp, int n, bool use_masters, int stage_set)
 {
+    c->slot0_is_ref = false;
     if (use_masters && c->masters_ready) CK(cudaStreamWaitEvent(c->stream, c->masters_ready, 0)); // broadcasts in flight
     int r = dispatch_calibrate(c, fp, n, use_masters);
     if (r) return r;
@@ -1148,16 +1150,16 @@ int oss_set_reference(oss_ctx *c, const void *frame, int mem, int threshold)
     int set;
     rc = stage_frames(c, &frame, 1, mem, &fp, &set);
     if (rc) return rc;
+    // the reference's calibrated plane is written where the final combine reads it (imagestacker.cpp:287: workingImage = the
+    // calibrated reference), not into slot 0 of the work space and copied (0.1 ms at 24 MP RGB)
+    float *const ws_cal = w.cal, *const ws_gray = w.gray;
+    w.cal = c->ref_cal;
+    if (g.C == 1) w.gray = c->ref_cal;
     rc = run_detect(c, fp, 1, true, threshold, set);
+    w.cal = ws_cal; w.gray = ws_gray;
     if (rc) return rc;
+    c->slot0_is_ref = true;
     if (set >= 0) CK(cudaEventSynchronize(c->copy_done[set])); // a host frame may be reused as soon as this call returns
-    const long long PC = g.P * g.C;
-    {   // bulk copy: on the pipeline's low-priority stream, ordered behind the calibration there
-        cudaStream_t chain = c->stream;
-        c->stream = bulk_of(c, c->cur);
-        LAUNCH("copy_reference", k_copy_f32, (unsigned)((PC + 1023) / 1024), 256, 0, w.cal, c->ref_cal, PC);
-        c->stream = chain;
-    }
     int *xy_ref = c->d_xy + c->slots * 2 * OSS_NOBJS, *nxy_ref = c->d_nxy + c->slots;
     LAUNCH("pack_xy", k_pack_xy, 1, OSS_NOBJS, 0, w.star_out, w.ds, g.cap, xy_ref, nxy_ref);
     LAUNCH("build_ref_triangles", k_build_ref_triangles, 1, FOCAS_NT, 0, xy_ref, nxy_ref, c->d_ref);
@@ -1965,8 +1967,8 @@ int oss_debug_copy(oss_ctx *c, int what, int slot, float *out)
     const float *src = nullptr;
     size_t count = 0;
     switch (what) {
-    case 0: src = w.cal + slot * w.stridePC; count = (size_t)g.P * g.C; break;
-    case 1: src = g.C == 3 ? w.gray + slot * w.strideP : w.cal + slot * w.stridePC; count = (size_t)g.P; break;
+    case 0: src = (slot == 0 && c->slot0_is_ref) ? c->ref_cal : w.cal + slot * w.stridePC; count = (size_t)g.P * g.C; break;
+    case 1: src = g.C == 3 ? w.gray + slot * w.strideP : ((slot == 0 && c->slot0_is_ref) ? c->ref_cal : w.cal + slot * w.stridePC); count = (size_t)g.P; break;
     case 2: src = w.stars + slot * w.strideP; count = (size_t)g.P; break;
     case 3: src = w.lo + slot * w.strideLo; count = (size_t)g.lw * g.lh; break;
     case 4: src = w.med + slot * w.strideLo; count = (size_t)g.lw * g.lh; break;
