@@ -84,7 +84,7 @@ template <int C>
 __global__ void __launch_bounds__(256, 3)
 k_warp_accumulate_tiled(const float *__restrict__ cal, long long strideCal, const AlignOut *__restrict__ align, int nframes,
                         const int2 *__restrict__ ab, long long strideAB, const int2 *__restrict__ xy, long long strideXY,
-                        float *__restrict__ sum, int W, int H, int ytile0)
+                        float *__restrict__ sum, int W, int H, int ytile0, int zero_init)
 {
     constexpr int ROWF = WT_COLS * C;           // floats per staged row
     constexpr int CHUNKS = ROWF / 4;            // 16-byte chunks per staged row
@@ -109,7 +109,7 @@ k_warp_accumulate_tiled(const float *__restrict__ cal, long long strideCal, cons
     for (int k = 0; k < 8; k++) {
         const int y = y0 + ty + 4 * k;
 #pragma unroll
-        for (int ch = 0; ch < C; ch++) acc[k][ch] = (col_ok && y < H) ? sum[((long long)y * W + x) * C + ch] : 0.f;
+        for (int ch = 0; ch < C; ch++) acc[k][ch] = (col_ok && y < H && !zero_init) ? sum[((long long)y * W + x) * C + ch] : 0.f; // zero_init: the stack's first launch (no memset, no read)
     }
     __syncthreads();
     const int nvalid = valid[0];
@@ -355,7 +355,7 @@ template <int C>
 __global__ void __launch_bounds__(256, 3)
 k_warp_accumulate_tma(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ cal, long long strideCal,
                       const AlignOut *__restrict__ align, int nframes, const int2 *__restrict__ ab, long long strideAB,
-                      const int2 *__restrict__ xy, long long strideXY, float *__restrict__ sum, int W, int H, int ytile0)
+                      const int2 *__restrict__ xy, long long strideXY, float *__restrict__ sum, int W, int H, int ytile0, int zero_init)
 {
     constexpr int ROWF = WT_COLS * C;
     constexpr unsigned TILE_BYTES = WT_ROWS * ROWF * 4;
@@ -382,7 +382,7 @@ k_warp_accumulate_tma(const __grid_constant__ CUtensorMap tmap, const float *__r
     for (int k = 0; k < 8; k++) {
         const int y = y0 + ty + 4 * k;
 #pragma unroll
-        for (int ch = 0; ch < C; ch++) acc[k][ch] = (col_ok && y < H) ? sum[((long long)y * W + x) * C + ch] : 0.f;
+        for (int ch = 0; ch < C; ch++) acc[k][ch] = (col_ok && y < H && !zero_init) ? sum[((long long)y * W + x) * C + ch] : 0.f; // zero_init: the stack's first launch (no memset, no read)
     }
     __syncthreads();
     const int nvalid = sm.valid[0];

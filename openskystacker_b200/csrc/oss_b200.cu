@@ -130,6 +130,7 @@ struct oss_ctx {
     float *master[4] = {nullptr, nullptr, nullptr, nullptr};
     float *sum = nullptr, *ref_cal = nullptr, *result = nullptr;
     bool has_ref = false, ref_in_sum = true;
+    bool sum_unset = false;              // a new stack whose sum plane has not been written yet: the first warp launch starts from 0
     bool slot0_is_ref = false;           // oss_debug_copy: the calibrated plane of "slot 0" is the reference's (it lives in ref_cal)
     bool dirty = true;                   // something was queued on a chain / side stream (or a warp deferred) since the last sync_all
     int threshold = 20;
@@ -1115,9 +1116,19 @@ int oss_clear_masters(oss_ctx *c)
 }
 
 // ---- stacking --------------------------------------------------------------------------
+// the sum plane of a new stack is not cleared: its first warp + accumulate launch starts from zero (zero_init) and writes every
+// tile; whoever reads the plane before that (no lights at all) clears it first
+static int ensure_sum(oss_ctx *c)
+{
+    if (!c->sum_unset) return OSS_OK;
+    CK(cudaMemsetAsync(c->sum, 0, (size_t)c->g.P * c->g.C * sizeof(float), c->bulk));
+    c->sum_unset = false;
+    return OSS_OK;
+}
+
 static int reset_stack_async(oss_ctx *c)
 {
-    CK(cudaMemsetAsync(c->sum, 0, (size_t)c->g.P * c->g.C * sizeof(float), c->stream));
+    c->sum_unset = true;
     CK(cudaMemsetAsync(c->d_valid, 0, 16, c->stream));
     c->has_ref = false;
     c->ref_in_sum = true;
@@ -1222,7 +1233,7 @@ static int check_light_overflow(oss_ctx *c)
 // warp + accumulate of the first nb slots of a pipeline's calibrated planes into `dst`, tile rows [t0, t1).
 // which: OSS_WARP_AUTO = the TMA kernel where the pipeline has a tensor map (rows are 16-byte multiples), else the cp.async
 // one; OSS_WARP_TMA / OSS_WARP_TILED force one of them (tests).  Launches on c->stream.
-static int launch_warp(oss_ctx *c, Pipe &pp, int nb, int t0, int t1, float *dst, int which)
+static int launch_warp(oss_ctx *c, Pipe &pp, int nb, int t0, int t1, float *dst, int which, int zero_init = 0)
 {
     const Geom &g = c->g;
     Workspace &w = pp.ws;
@@ -1232,16 +1243,16 @@ static int launch_warp(oss_ctx *c, Pipe &pp, int nb, int t0, int t1, float *dst,
     const dim3 wgrid((g.W + WT_W - 1) / WT_W, t1 - t0);
     if (tma && g.C == 3) {
         LAUNCH("warp_accumulate", k_warp_accumulate_tma<3>, wgrid, 256, sizeof(WarpTmaSmem<3>) + 128, pp.cal_map, w.cal, w.stridePC, w.align,
-               nb, w.warp_ab, (long long)g.W, w.warp_xy, (long long)g.H, dst, g.W, g.H, t0);
+               nb, w.warp_ab, (long long)g.W, w.warp_xy, (long long)g.H, dst, g.W, g.H, t0, zero_init);
     } else if (tma) {
         LAUNCH("warp_accumulate", k_warp_accumulate_tma<1>, wgrid, 256, sizeof(WarpTmaSmem<1>) + 128, pp.cal_map, w.cal, w.stridePC, w.align,
-               nb, w.warp_ab, (long long)g.W, w.warp_xy, (long long)g.H, dst, g.W, g.H, t0);
+               nb, w.warp_ab, (long long)g.W, w.warp_xy, (long long)g.H, dst, g.W, g.H, t0, zero_init);
     } else if (g.C == 3) {
         LAUNCH("warp_accumulate", k_warp_accumulate_tiled<3>, wgrid, 256, warp_tiled_smem<3>(), w.cal, w.stridePC, w.align, nb,
-               w.warp_ab, (long long)g.W, w.warp_xy, (long long)g.H, dst, g.W, g.H, t0);
+               w.warp_ab, (long long)g.W, w.warp_xy, (long long)g.H, dst, g.W, g.H, t0, zero_init);
     } else {
         LAUNCH("warp_accumulate", k_warp_accumulate_tiled<1>, wgrid, 256, warp_tiled_smem<1>(), w.cal, w.stridePC, w.align, nb,
-               w.warp_ab, (long long)g.W, w.warp_xy, (long long)g.H, dst, g.W, g.H, t0);
+               w.warp_ab, (long long)g.W, w.warp_xy, (long long)g.H, dst, g.W, g.H, t0, zero_init);
     }
     return OSS_OK;
 }
@@ -1267,13 +1278,14 @@ static int flush_warps(oss_ctx *c, size_t keep, int bands = 1, int (*after_band)
         const int tiles_y = (g.H + WT_H - 1) / WT_H, nb = (last && bands > 1) ? bands : 1;
         for (int b = 0; b < nb; b++) {
             const int t0 = (int)((long long)tiles_y * b / nb), t1 = (int)((long long)tiles_y * (b + 1) / nb);
-            if (t1 > t0) { int rc = launch_warp(c, pp, pw.nb, t0, t1, c->sum, OSS_WARP_AUTO); if (rc) return rc; }
+            if (t1 > t0) { int rc = launch_warp(c, pp, pw.nb, t0, t1, c->sum, OSS_WARP_AUTO, c->sum_unset ? 1 : 0); if (rc) return rc; }
             if (nb > 1 && after_band) {
                 const int r0 = t0 * WT_H, r1 = t1 * WT_H < g.H ? t1 * WT_H : g.H;
                 int rc = after_band(c, r0, r1 - r0);
                 if (rc) return rc;
             }
         }
+        c->sum_unset = false; // every tile of the plane has been written by this batch's launch(es)
         CK(cudaEventRecord(pp.warp_done, c->stream));
         c->stream = saved;
     }
@@ -1424,6 +1436,7 @@ static int total_valid(oss_ctx *c, int *out)
 int oss_get_sum(oss_ctx *c, float *out, int *tv)
 {
     USE_PIPE0();
+    { int rc = ensure_sum(c); if (rc) return rc; }
     if (tv) { int rc = total_valid(c, tv); if (rc) return rc; }
     if (out) return oss_memcpy_d2h(c, out, c->sum, (size_t)c->g.P * c->g.C * sizeof(float));
     return OSS_OK;
@@ -1442,6 +1455,7 @@ int oss_finish(oss_ctx *c, float *out, int *tv)
     if (!c->comm_stream) {
         if (flush_warps(c, 0, 1, nullptr) != OSS_OK) return OSS_E_CUDA;
         select_pipe(c, 0);
+        { int rc = ensure_sum(c); if (rc) return rc; }
         LAUNCH("finalize", k_finalize, (unsigned)((PC + 1023) / 1024), 256, 0, c->sum, c->ref_in_sum ? c->ref_cal : (const float *)nullptr,
                c->result, PC, c->d_valid);
         queued = true;
@@ -1450,6 +1464,7 @@ int oss_finish(oss_ctx *c, float *out, int *tv)
     { int rc = ref_host(c); if (rc) return rc; } // a reference that overflowed the work space invalidates the stack
     CK(cudaStreamSynchronize(c->copy_stream));
     { int rc = check_light_overflow(c); if (rc) return rc; }
+    { int rc = ensure_sum(c); if (rc) return rc; }
     if (!queued)
         LAUNCH("finalize", k_finalize, (unsigned)((PC + 1023) / 1024), 256, 0, c->sum, c->ref_in_sum ? c->ref_cal : (const float *)nullptr,
                c->result, PC, c->d_valid);
@@ -1826,6 +1841,7 @@ int oss_comm_reduce(oss_ctx *c, int root)
         int rc = flush_warps(c, 0, OSS_REDUCE_BANDS, reduce_band);
         if (rc) return rc;
     } else {
+        { int rc = ensure_sum(c); if (rc) return rc; } // a rank without any light contributes zeros
         for (int b = 0; b < OSS_REDUCE_BANDS; b++) { // same band boundaries as flush_warps
             const int t0 = (int)((long long)tiles_y * b / OSS_REDUCE_BANDS), t1 = (int)((long long)tiles_y * (b + 1) / OSS_REDUCE_BANDS);
             const int r0 = t0 * WT_H, r1 = t1 * WT_H < c->g.H ? t1 * WT_H : c->g.H;
