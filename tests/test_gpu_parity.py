@@ -490,6 +490,26 @@ def test_no_light_aligns_is_the_reference_error(eng):
     with pytest.raises(ob.OssError) as e:
         eng.finish()
     assert e.value.status == -6 and "No images could be aligned" in str(e.value)
+    # the sum plane of a stack is never cleared up front (its first warp launch starts from zero): a stack nobody added a
+    # light to, and one whose lights all failed, must still read as zeros — also right after a stack that did accumulate
+    w, h = 640, 480
+    good = synth.dataset(w, h, 2, 1, nstars=80)
+    darks = [synth.dark(w, h, i, 1) for i in range(2)]
+    eng.set_geometry(w, h, 1, np.uint16, 2)
+    eng.set_reference(good["ref"], 20)
+    eng.add_lights(good["lights"])
+    acc, tv = eng.get_sum()
+    assert tv == 3 and float(np.abs(acc).max()) > 0
+    eng.set_reference(good["ref"], 20)
+    acc, tv = eng.get_sum()
+    assert tv == 1 and not acc.any()
+    with pytest.raises(ob.OssError) as e:
+        eng.finish()
+    assert e.value.status == -6
+    eng.set_reference(good["ref"], 20)
+    eng.add_lights(darks)
+    acc, tv = eng.get_sum()
+    assert tv == 1 and not acc.any()
 
 
 def test_device_resident_frames_give_the_same_stack(eng):
