@@ -1,4 +1,5 @@
-// Qt adapter sketch (NOT compiled in this repository: Qt is absent from the build image).
+// Qt adapter (Qt is absent from the build image: tests/test_host_layer.py type-checks this header against minimal stand-ins of the
+// Qt / OpenCV classes it touches, tests/qt_stub; it is not linked into anything here).
 // In a Qt build this header turns the callback-style openskystacker::ImageStacker of
 // imagestacker.hpp back into the QObject the reference's CLI, GUI and tests connect to
 // (cl/cl.cpp:18-23, openskystacker/ui/mainwindow.cpp:71-88, test/testoss.cpp:20-23), so that

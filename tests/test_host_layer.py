@@ -408,6 +408,36 @@ def test_cli_shards_the_lights_over_two_gpus(host, tmp_path):
     assert rb.stdout.splitlines()[-1] == r0_stdout.splitlines()[-1].replace("stack2", "stack_bal")  # "File saved to ..."
 
 
+def test_qt_adapter_compiles_against_stub_headers(tmp_path):
+    """csrc/host/imagestacker_qt.hpp (the QObject face of the facade for a Qt build: signals finished / updateProgress /
+    processingError / doneDetectingStars, slots process / detectStars, the reference's setters with QString / QStringList,
+    imagestacker.h:20-114) is only a header here — Qt and C++ OpenCV are absent from the image.  Syntax- and type-check it
+    against minimal stand-ins of the Qt / OpenCV classes it touches (tests/qt_stub), so that it cannot rot unnoticed."""
+    import shutil
+    cxx = shutil.which("g++")
+    if not cxx:
+        pytest.skip("no g++")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "qt_check.cpp"
+    src.write_text('''#include "imagestacker_qt.hpp"
+int main()
+{
+    openskystacker::QImageStacker s;
+    s.setUseDarks(true); s.setUseFlats(false); s.setUseBias(true); s.setUseDarkFlats(false);
+    s.setRefImageFileName(QString::fromStdString("ref.tif"));
+    QStringList l; l.push_back(QString::fromStdString("a.tif"));
+    s.setTargetImageFileNames(l); s.setDarkFrameFileNames(l); s.setDarkFlatFrameFileNames(l); s.setFlatFrameFileNames(l); s.setBiasFrameFileNames(l);
+    s.process(20, 4);
+    s.detectStars(QString::fromStdString("ref.tif"), 20);
+    return 0;
+}
+''')
+    r = subprocess.run([cxx, "-std=c++17", "-fsyntax-only", "-Wall", "-DOSS_WITH_QT", "-I", os.path.join(root, "tests", "qt_stub"),
+                        "-I", os.path.join(root, "openskystacker_b200", "csrc", "host"), "-I", os.path.join(root, "include"), str(src)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
 # ---- FITS (fitsToMat, libstacker/src/util.cpp:300-346) -----------------------------------------------------------------
 def write_fits(path, data, bitpix, bzero=None, extra_axis=None):
     """Minimal primary HDU: 80-byte cards, 2880-byte blocks, big-endian samples."""
