@@ -427,6 +427,13 @@ int main()
     s.setRefImageFileName(QString::fromStdString("ref.tif"));
     QStringList l; l.push_back(QString::fromStdString("a.tif"));
     s.setTargetImageFileNames(l); s.setDarkFrameFileNames(l); s.setDarkFlatFrameFileNames(l); s.setFlatFrameFileNames(l); s.setBiasFrameFileNames(l);
+    s.setSaveFilePath(s.getSaveFilePath());
+    s.setWorkingImage(s.getWorkingImage()); s.setRefImage(s.getRefImage()); s.setFinalImage(s.getFinalImage());
+    QStringList all = s.getTargetImageFileNames();
+    (void)s.getDarkFrameFileNames(); (void)s.getDarkFlatFrameFileNames(); (void)s.getFlatFrameFileNames(); (void)s.getBiasFrameFileNames();
+    bool any = s.getUseDarks() || s.getUseDarkFlats() || s.getUseFlats() || s.getUseBias() || s.cancel || all.empty();
+    (void)any; (void)s.getRefImageFileName();
+    s.engine().setDynamicSharding(true);
     s.process(20, 4);
     s.detectStars(QString::fromStdString("ref.tif"), 20);
     return 0;
