@@ -305,11 +305,11 @@ def test_threshold_sweep_matches_per_threshold_detection(eng):
     w, h = 600, 400
     eng.set_geometry(w, h, 1, np.float32, 1)
     g = blob_image(w, h, 80, seed=11)
-    ts = list(range(1, 41))
+    ts = list(range(1, 101))               # the whole range the CLI accepts (cl/cl.cpp:178-184)
     counts = eng.detect_sweep(g, ts[0], ts[-1])
-    for t in (1, 2, 5, 13, 20, 40):
+    for t in (1, 2, 5, 13, 20, 40, 61, 100):
         assert counts[t - 1] == len(oracle.get_stars(g, t)[0])
-    assert counts[0] > counts[-1]
+    assert counts[0] > counts[39] >= counts[-1]
 
 
 # ------------------------------------------------------------------------------- K7
@@ -584,6 +584,12 @@ def test_full_size_61mp_mono_star_heavy(eng):
     assert len(want) > 3000
     assert np.float32(info.threshold) == np.float32(oinfo.threshold) and info.ncomponents == oinfo.ncomponents
     same_stars(got, want)
+    # config 5's sweep at full size: sky / sigma once, thresholding + components + deblending per threshold
+    counts = eng.detect_sweep(frame, 1, 100)
+    assert counts[4] == len(want)
+    f32 = oracle.u16_to_f32(frame)
+    for t in (1, 20, 100):
+        assert counts[t - 1] == len(oracle.get_stars(f32, t)[0]), t
 
 
 def test_many_small_batches_over_three_pipelines(eng):
