@@ -23,6 +23,9 @@ struct ImageInfo {
 bool probeImage(const std::string &path, ImageInfo *info, std::string *err);
 // decode into dst (info->bytes() bytes, e.g. pinned memory from oss_host_alloc)
 bool readImageInto(const std::string &path, const ImageInfo &expect, void *dst, std::string *err);
+// band `band` of `nbands` of a frame (TIFF: a share of its strips, which are independent; other formats: band 0 decodes the whole
+// file, the other bands return at once): lets several decode workers share one large frame
+bool readImageBandInto(const std::string &path, const ImageInfo &expect, void *dst, int band, int nbands, std::string *err);
 bool readImage(const std::string &path, ImageInfo *info, std::vector<uint8_t> *pixels, std::string *err);
 // float32 / uint16 TIFF, channel order flipped back to RGB like cv::imwrite does
 bool writeTiffF32(const std::string &path, const float *hwc_bgr, int width, int height, int channels, std::string *err);

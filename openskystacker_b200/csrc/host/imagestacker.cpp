@@ -56,19 +56,23 @@ public:
 
 namespace {
 
-// decode files[i] into dst[i] with `threads` workers, strided like util.cpp:738
+// decode files[i] into dst[i] with `threads` workers, strided like util.cpp:738.  More workers than files: a file is shared by
+// several of them (readImageBandInto: a TIFF's strips are independent), so that a batch of 5 large frames still uses -j 16
 bool decodeMany(const std::vector<std::string> &files, size_t first, size_t count, const ImageInfo &info, void *const *dst,
                 int threads, std::string *err)
 {
     std::atomic<bool> ok(true);
     std::mutex emu;
-    int nt = std::max(1, std::min<int>(threads, (int)count));
+    const int bands = count ? std::max(1, std::min(16, threads / (int)count)) : 1;
+    const size_t tasks = count * (size_t)bands;
+    int nt = std::max(1, std::min<int>(threads, (int)tasks));
     std::vector<std::thread> pool;
     for (int t = 0; t < nt; t++)
         pool.emplace_back([&, t] {
-            for (size_t k = (size_t)t; k < count && ok; k += (size_t)nt) {
+            for (size_t k = (size_t)t; k < tasks && ok; k += (size_t)nt) {
+                const size_t file = k / (size_t)bands;
                 std::string e;
-                if (!readImageInto(files[first + k], info, dst[k], &e)) {
+                if (!readImageBandInto(files[first + file], info, dst[file], (int)(k % (size_t)bands), bands, &e)) {
                     std::lock_guard<std::mutex> lk(emu);
                     if (ok.exchange(false) && err) *err = e;
                 }

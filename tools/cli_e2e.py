@@ -1,0 +1,101 @@
+"""Dev aid (GPU box): `openskystacker-cl` end to end FROM FILES — a config-2-shaped stack (24 MP RGB16 TIFFs: lights + darks +
+flats + bias, uncompressed, freshly written so they sit in the page cache) through the Qt-free CLI on 1 GPU and, when the box has
+more, on all of them with the static stride and with --balance.  Wall clock of the whole process (CUDA context, allocations, file
+decode by -j workers, H2D, kernels, float32 TIFF written) and the N-GPU result against the 1-GPU one.
+
+    python tools/cli_e2e.py --lights 50 --ncal 5 > gpurun_out/cli_e2e.txt
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+from concurrent.futures import ProcessPoolExecutor
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+CLI = os.path.join(ROOT, "openskystacker_b200", "csrc", "openskystacker-cl")
+
+
+def make(job):
+    import cv2
+    from openskystacker_b200 import synth
+    kind, i, path, w, h, nstars, b, d = job
+    if kind == "light":
+        frame = synth.light(synth.Field(w, h, nstars, 1234), i, 3, d, b, True)
+    elif kind == "dark":
+        frame = synth.dark(w, h, i, 3, 300.0, b)
+    elif kind == "bias":
+        frame = synth.bias(w, h, i, 3)
+    else:
+        frame = synth.flat(w, h, i, 3, b)
+    cv2.imwrite(path, frame, [cv2.IMWRITE_TIFF_COMPRESSION, 1])
+    return path
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--lights", type=int, default=50)
+    ap.add_argument("--ncal", type=int, default=5)
+    ap.add_argument("--width", type=int, default=6000)
+    ap.add_argument("--height", type=int, default=4000)
+    ap.add_argument("--dir", default="/tmp/oss_cli_e2e")
+    ap.add_argument("--threads", type=int, default=os.cpu_count() or 8)
+    a = ap.parse_args()
+    import cv2
+    import torch
+    ngpu = torch.cuda.device_count()
+    os.makedirs(a.dir, exist_ok=True)
+    w, h = a.width, a.height
+    nstars = max(60, int(600 * w * h / 24e6))
+    b, d = (100.0, 300.0) if a.ncal else (0.0, 0.0)
+    jobs, entries = [], []
+    for i in range(a.lights + 1):
+        name = "ref.tif" if i == 0 else f"light{i}.tif"
+        jobs.append(("light", i, os.path.join(a.dir, name), w, h, nstars, b, d))
+        entries.append({"filename": name, "type": "ref" if i == 0 else "light", "checked": True})
+    for kind in ("dark", "flat", "bias"):
+        for i in range(a.ncal):
+            name = f"{kind}{i}.tif"
+            jobs.append((kind, i, os.path.join(a.dir, name), w, h, nstars, b, d))
+            entries.append({"filename": name, "type": kind, "checked": True})
+    t0 = time.perf_counter()
+    with ProcessPoolExecutor(min(a.threads, 16)) as ex:
+        list(ex.map(make, jobs))
+    lst = os.path.join(a.dir, "list.json")
+    with open(lst, "w") as f:
+        json.dump(entries, f)
+    nbytes = sum(os.path.getsize(j[2]) for j in jobs)
+    print(f"{len(jobs)} TIFFs of {w}x{h} RGB16 ({nbytes / 1e9:.2f} GB) written in {time.perf_counter() - t0:.1f} s; {ngpu} GPU(s), -j {a.threads}")
+
+    def run(tag, extra):
+        out = os.path.join(a.dir, "stack_" + tag)
+        best = None
+        for rep in range(2):     # the first run pays the driver's first-touch costs
+            t = time.perf_counter()
+            r = subprocess.run([CLI, "-f", lst, "-o", out, "-t", "20", "-j", str(a.threads)] + extra, capture_output=True, text=True)
+            dt = time.perf_counter() - t
+            if r.returncode != 0:
+                print(tag, "FAILED:", (r.stdout + r.stderr)[-400:])
+                return None
+            best = dt if best is None else min(best, dt)
+        img = cv2.imread(out + ".tif", cv2.IMREAD_ANYDEPTH | cv2.IMREAD_ANYCOLOR)
+        print(f"{tag:22s} wall {best:6.2f} s = {(a.lights + 1) / best:6.1f} frames/s of {len(jobs)} files ({nbytes / best / 1e9:.2f} GB/s of TIFF bytes), "
+              f"last line: {r.stdout.strip().splitlines()[-1]}")
+        return img
+
+    one = run("1 GPU (--device 0)", ["--device", "0"])
+    if ngpu > 1 and one is not None:
+        for tag, extra in ((f"{ngpu} GPUs, static stride", ["--devices", "all"]), (f"{ngpu} GPUs, --balance", ["--devices", "all", "--balance"])):
+            img = run(tag, extra)
+            if img is not None:
+                print(f"{'':22s} max |N-GPU stack - 1-GPU stack| = {float(np.max(np.abs(img - one))):.3g}")
+    for j in jobs:
+        os.remove(j[2])
+
+
+if __name__ == "__main__":
+    main()
