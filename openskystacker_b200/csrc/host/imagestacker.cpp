@@ -8,6 +8,7 @@
 #include <array>
 #include <atomic>
 #include <chrono>
+#include <cstdio>
 #include <cmath>
 #include <condition_variable>
 #include <cstring>
@@ -138,7 +139,12 @@ ACCESSOR(std::vector<std::string>, getDarkFlatFrameFileNames, setDarkFlatFrameFi
 ACCESSOR(std::vector<std::string>, getFlatFrameFileNames, setFlatFrameFileNames, flatFrameFileNames)
 ACCESSOR(std::vector<std::string>, getBiasFrameFileNames, setBiasFrameFileNames, biasFrameFileNames)
 ACCESSOR(std::string, getSaveFilePath, setSaveFilePath, saveFilePath)
-ACCESSOR(Image, getWorkingImage, setWorkingImage, workingImage)
+Image ImageStacker::getWorkingImage() const
+{
+    std::lock_guard<std::mutex> lk(d_ptr->mutex);
+    return d_ptr->workingImage.data.empty() ? d_ptr->finalImage : d_ptr->workingImage;
+}
+void ImageStacker::setWorkingImage(const Image &value) { std::lock_guard<std::mutex> lk(d_ptr->mutex); d_ptr->workingImage = value; }
 ACCESSOR(Image, getRefImage, setRefImage, refImage)
 ACCESSOR(Image, getFinalImage, setFinalImage, finalImage)
 #undef ACCESSOR
@@ -205,6 +211,11 @@ void ImageStacker::process(int tolerance, int threads)
     auto error = [&](const std::string &m) { std::lock_guard<std::mutex> lk(sig); if (processingError) processingError(m); };
     auto progress = [&](const std::string &m, int pct) { std::lock_guard<std::mutex> lk(sig); if (updateProgress) updateProgress(m, pct); };
     const auto started = std::chrono::steady_clock::now();
+    // dev aid: OSS_STACKER_TIMING=1 prints where the wall clock of process() goes (stderr)
+    const bool timing = getenv("OSS_STACKER_TIMING") != nullptr;
+    auto mark = [&](const char *what) {
+        if (timing) fprintf(stderr, "[oss timing] %-28s %8.3f s\n", what, std::chrono::duration<double>(std::chrono::steady_clock::now() - started).count());
+    };
 
     // imagestacker.cpp:236-246
     ImageType refType = getImageType(d->refImageFileName);
@@ -235,6 +246,7 @@ void ImageStacker::process(int tolerance, int threads)
     if (d->useDarks && !sameSize(d->darkFrameFileNames)) return;
     if (d->useDarkFlats && !sameSize(d->darkFlatFrameFileNames)) return;
     if (d->useFlats && !sameSize(d->flatFrameFileNames)) return;
+    mark("headers checked");
 
     struct MasterJob { bool use; const std::vector<std::string> *files; int kind; const char *message; };
     const MasterJob masters[4] = { // the reference's order (imagestacker.cpp:262-281)
@@ -258,6 +270,7 @@ void ImageStacker::process(int tolerance, int threads)
             d->ctx_device[r] = devs[r];
             d->comm_ready = false;
         }
+    mark("contexts");
     const size_t frame_bytes = ref.bytes();
     // frames in flight per pipeline: about 0.75 GB of raw frames per batch (24 MP RGB16: 5, the host-fed optimum measured by
     // bench.py), at least 2, at most 16; 3 pipelines
@@ -292,13 +305,8 @@ void ImageStacker::process(int tolerance, int threads)
         ChunkRing ring;
         bool any_master = false;
         for (const MasterJob &m : masters) any_master |= m.use;
-        for (int r = 0; r < N; r++)
-            for (int s2 = 0; s2 < 2; s2++)
-                for (int i = 0; i < slots; i++) {
-                    void *p = pinned(frame_bytes);
-                    if (!p) { error("out of pinned host memory"); return OSS_E_NOMEM; }
-                    stage[r][s2].push_back(p);
-                }
+        // (pinning memory costs ~0.5 s per GB: the calibration chunks, idle once the masters are built — every GPU has passed the
+        // barrier behind the last master by then —, double as GPU 0's two sets for the lights)
         if (any_master)
             for (int s2 = 0; s2 < 2; s2++)
                 for (int i = 0; i < slots; i++) {
@@ -306,7 +314,16 @@ void ImageStacker::process(int tolerance, int threads)
                     if (!p) { error("out of pinned host memory"); return OSS_E_NOMEM; }
                     ring.chunk[s2].buf.push_back(p);
                 }
-
+        for (int r = 0; r < N; r++)
+            for (int s2 = 0; s2 < 2; s2++) {
+                if (r == 0 && any_master) { stage[r][s2] = ring.chunk[s2].buf; continue; }
+                for (int i = 0; i < slots; i++) {
+                    void *p = pinned(frame_bytes);
+                    if (!p) { error("out of pinned host memory"); return OSS_E_NOMEM; }
+                    stage[r][s2].push_back(p);
+                }
+            }
+        mark("pinned staging allocated");
         // producer: decodes the calibration frames of every enabled master, chunk by chunk, two chunks ahead of the GPUs
         std::thread producer([&] {
             int slot = 0;
@@ -343,6 +360,7 @@ void ImageStacker::process(int tolerance, int threads)
             bool ok = ck(oss_set_candidate_capacity(ctx, capacity_one_in)) &&
                       ck(oss_set_geometry(ctx, ref.width, ref.height, ref.channels, (int)ref.sample, slots)) && ck(oss_clear_masters(ctx));
             if (N > 1 && !d->comm_ready && ok) ok = ck(oss_comm_init(ctx, nccl_id, r, N));
+            if (r == 0) mark("geometry (device work space)");
             bar.wait();
             if (status) return;
             int row0 = 0, rows = 0;
@@ -376,6 +394,7 @@ void ImageStacker::process(int tolerance, int threads)
                 if (N > 1) ok = ck(oss_comm_allgather_master(ctx, m.kind));
             }
             // ---- reference (imagestacker.cpp:286-287)
+            if (r == 0) mark("masters queued");
             if (r == 0) {
                 progress("Stacking light frames...", 100 * d->currentOperation++ / d->totalOperations);
                 std::string e;
@@ -411,6 +430,7 @@ void ImageStacker::process(int tolerance, int threads)
                 d->lightsDone += (int)nb;
                 progress("Stacking light frames...", 100 * (d->currentOperation + d->lightsDone.load()) / d->totalOperations);
             }
+            if (r == 0) mark("lights queued (this GPU)");
             bar.wait();
             if (status) return;
             if (N > 1) ok = ck(oss_comm_reduce(ctx, 0));
@@ -418,6 +438,7 @@ void ImageStacker::process(int tolerance, int threads)
                 out->width = ref.width; out->height = ref.height; out->channels = ref.channels;
                 out->data.resize((size_t)ref.width * ref.height * ref.channels);
                 if (ok) ck(oss_finish(ctx, out->data.data(), valid_out));
+                mark("finished (result on the host)");
             } else if (ok) ck(oss_sync(ctx));
             // per-light outcomes of this GPU (also after a failed finish: they say why)
             std::vector<LightReport> &mineRep = (*reps)[r];
@@ -477,14 +498,17 @@ void ImageStacker::process(int tolerance, int threads)
                 if (i < takenIdx[r].size() && takenIdx[r][i] < lights.size()) d->reports[takenIdx[r][i]] = reps[r][i]; // back to list order
     }
     d->releasePinned();
+    mark("pinned staging released");
     if (st) return; // OSS_E_NO_ALIGNED carries the reference's text (imagestacker.cpp:355-359)
     {
         std::lock_guard<std::mutex> lk(d->mutex);
-        d->workingImage = out;
-        d->finalImage = out;
+        d->finalImage = out;          // one copy (288 MB at 24 MP RGB): getWorkingImage() hands out the final image as long as
+        d->workingImage = Image();    // nobody has set another working image (the reference's two cv::Mat share their pixels)
     }
     int seconds = (int)std::chrono::duration_cast<std::chrono::seconds>(std::chrono::steady_clock::now() - started).count();
+    mark("images kept");
     if (finished) finished(out, "Stacking completed in " + getTimeString(seconds) + ".");
+    mark("finished() returned");
 }
 
 std::vector<Star> ImageStacker::getStars(const std::string &filename, int threshold)
