@@ -59,6 +59,84 @@ def test_tiff_reader_matches_imread(host, tmp_path, dtype, channels, compression
     assert got.dtype == want.dtype and got.shape == want.shape and np.array_equal(got, want)
 
 
+def test_tiff_reader_randomised_against_imread(host, tmp_path):
+    """Shapes from 1x1 up, noise / ramps / constants / few-valued content (short and maximal LZW strings, table resets, KwKwK
+    codes), uncompressed / LZW / Deflate, grey and RGB, 8 and 16 bits, files whose directory sits behind the pixel data (libtiff)
+    and far beyond the probe's first window: every pixel equals cv::imread's."""
+    rng = np.random.default_rng(2024)
+    kinds = ("noise", "ramp", "const", "few", "runs")
+    for it in range(60):
+        h, w = (int(rng.integers(1, 40)), int(rng.integers(1, 40))) if it % 3 else (int(rng.integers(200, 420)), int(rng.integers(200, 420)))
+        c = int(rng.choice([1, 3]))
+        dtype = [np.uint8, np.uint16][int(rng.integers(0, 2))]
+        top = np.iinfo(dtype).max
+        shape = (h, w) if c == 1 else (h, w, c)
+        kind = kinds[it % len(kinds)]
+        if kind == "noise":
+            img = rng.integers(0, top + 1, shape)
+        elif kind == "ramp":
+            img = (np.arange(h)[:, None] * 7 + np.arange(w)[None, :] * 3)
+            img = img if c == 1 else np.stack([img, img + 1, img * 2], 2)
+        elif kind == "const":
+            img = np.full(shape, int(rng.integers(0, top + 1)))
+        elif kind == "few":
+            img = rng.integers(0, 3, shape) * (top // 2)
+        else:
+            img = np.repeat(rng.integers(0, top + 1, (h, (w + 15) // 16) + ((c,) if c == 3 else ())), 16, axis=1)[:, :w]
+        img = (np.asarray(img) % (top + 1)).astype(dtype)
+        comp = int(rng.choice([1, 5, 8]))
+        path = str(tmp_path / f"r{it}.tif")
+        assert cv2.imwrite(path, img, [cv2.IMWRITE_TIFF_COMPRESSION, comp])
+        want = cv2.imread(path, cv2.IMREAD_ANYDEPTH | cv2.IMREAD_ANYCOLOR)
+        got = read_tiff(host, path)
+        assert got.dtype == want.dtype and got.shape == want.shape and np.array_equal(got, want), (it, shape, dtype, kind, comp)
+
+
+def test_tiff_strips_can_be_shared_between_decode_workers(tmp_path):
+    """readImageBandInto: band k of n decodes its share of the strips (they are independent: compression and predictor restart
+    per strip) — the bands together are the whole frame, for every band count, compressed or not; a PNG is decoded by band 0."""
+    src = tmp_path / "bands.cpp"
+    src.write_text('''#include "image_io.hpp"
+#include <cstdio>
+#include <cstring>
+#include <vector>
+using namespace openskystacker;
+int main(int argc, char **argv)
+{
+    for (int a = 1; a < argc; a++) {
+        ImageInfo info; std::string err;
+        if (!probeImage(argv[a], &info, &err)) { printf("probe %s: %s\\n", argv[a], err.c_str()); return 1; }
+        std::vector<unsigned char> whole(info.bytes()), parts(info.bytes());
+        if (!readImageInto(argv[a], info, whole.data(), &err)) { printf("read: %s\\n", err.c_str()); return 1; }
+        for (int n : {1, 2, 3, 7, 16, 1000}) {
+            memset(parts.data(), 0xA5, parts.size());
+            for (int k = n - 1; k >= 0; k--)
+                if (!readImageBandInto(argv[a], info, parts.data(), k, n, &err)) { printf("band: %s\\n", err.c_str()); return 1; }
+            if (memcmp(whole.data(), parts.data(), whole.size())) { printf("%s: %d bands differ from the whole frame\\n", argv[a], n); return 1; }
+        }
+    }
+    printf("ok\\n");
+    return 0;
+}
+''')
+    rng = np.random.default_rng(9)
+    files = []
+    for i, (shape, comp) in enumerate([((301, 417, 3), 1), ((301, 417, 3), 5), ((97, 64), 8), ((5, 9, 3), 5), ((1, 1), 1)]):
+        img = (rng.integers(0, 50, shape) + np.arange(shape[1])[None, :, None][..., 0 if len(shape) == 2 else slice(None)] * 11).astype(np.uint16)
+        path = str(tmp_path / f"b{i}.tif")
+        assert cv2.imwrite(path, img, [cv2.IMWRITE_TIFF_COMPRESSION, comp])
+        files.append(path)
+    png = str(tmp_path / "b.png")
+    assert cv2.imwrite(png, rng.integers(0, 60000, (33, 47, 3)).astype(np.uint16))
+    files.append(png)
+    exe = str(tmp_path / "bands")
+    r = subprocess.run(["g++", "-std=c++17", "-O1", "-I", os.path.join(CSRC, "host"), "-I", os.path.join(os.path.dirname(CSRC), "..", "include"),
+                        str(src), "-o", exe, "-L", CSRC, "-loss_stacker", "-loss_b200", "-Wl,-rpath," + CSRC], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe] + files, capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.strip() == "ok", r.stdout + r.stderr
+
+
 def test_float_tiff_writer_round_trips_through_cv2(host, tmp_path):
     rng = np.random.default_rng(3)
     for shape in [(31, 45, 3), (31, 45)]:
