@@ -27,6 +27,23 @@ def test_header_symbols_are_exported(so):
     assert declared == set(binding.EXPORTS), declared ^ set(binding.EXPORTS)
 
 
+def test_header_is_plain_c(tmp_path):
+    """The boundary is a C ABI: include/oss_b200.h must compile as C99 (what cgo / a C caller / a bindgen run would see), with
+    plain pointers and sizes only — no C++ or torch types in any signature."""
+    import shutil
+    import subprocess
+    cc = shutil.which("gcc")
+    if not cc:
+        pytest.skip("no gcc")
+    src = tmp_path / "abi.c"
+    src.write_text('#include "oss_b200.h"\nint main(void) { oss_ctx *c = 0; oss_star s; oss_frame_report r; (void)c; (void)s; (void)r; return oss_device_count() < 0; }\n')
+    r = subprocess.run([cc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), str(src)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    code = re.sub(r"/\*.*?\*/|//[^\n]*", "", open(os.path.join(ROOT, "include", "oss_b200.h")).read(), flags=re.S)   # comments aside
+    assert "std::" not in code and "torch" not in code.lower() and "at::" not in code and "class " not in code
+
+
 def test_error_strings_match_the_reference():
     L = ob.lib()
     assert L.oss_status_string(-3) == b"Images must be the same type."                      # imagestacker.cpp:243
