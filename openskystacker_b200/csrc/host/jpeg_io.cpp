@@ -78,7 +78,7 @@ struct Decoder {
     HuffTable dc[4], ac[4];
     Component comp[3];
     int ncomp = 0, width = 0, height = 0, hmax = 1, vmax = 1;
-    bool progressive = false, have_frame = false;
+    bool progressive = false, have_frame = false, headers_only = false;
     int restart_interval = 0, orientation = 1;
     bool adobe = false;
     int adobe_transform = 0;
@@ -347,6 +347,7 @@ struct Decoder {
             if (hmax % c.h || vmax % c.v) return fail("non-integral chroma sampling ratios are not supported");
             c.bw = mcux * c.h; c.bh = mcuy * c.v;
             c.dw = (width * c.h + hmax - 1) / hmax; c.dh = (height * c.v + vmax - 1) / vmax;
+            if (headers_only) continue; // a probe needs the geometry, not 36 MB of cleared planes per 24 MP file
             c.plane.assign((size_t)c.bw * 8 * c.bh * 8, 0);
             if (progressive) c.coef.assign((size_t)c.bw * c.bh * 64, 0);
         }
@@ -435,6 +436,7 @@ struct Decoder {
 
     bool run(const uint8_t *data, size_t n, bool header_only)
     {
+        headers_only = header_only;
         p = data; end = data + n;
         if (n < 4 || p[0] != 0xff || p[1] != 0xd8) return fail("not a JPEG file");
         p += 2;
@@ -584,16 +586,16 @@ bool isJpegFile(const std::string &path)
 
 bool probeJpeg(const std::string &path, ImageInfo *info, std::string *err)
 {
+    // the frame header follows the APPn / table segments: usually within the first KBs, behind an EXIF thumbnail within the first
+    // MB, rarely later (a very large APPn block) — read 64 KB, then 1 MB, then the whole file
     std::vector<uint8_t> buf;
-    if (!loadWhole(path, &buf, 1 << 20, err)) return false; // the frame header follows the APPn / table segments
     Decoder d;
-    d.err = err;
-    if (!d.run(buf.data(), buf.size(), true)) {
-        if (buf.size() < (1u << 20)) return false;
-        if (!loadWhole(path, &buf, 0, err)) return false;  // (a very large APPn block in front of the frame header)
+    for (size_t limit : {(size_t)1 << 16, (size_t)1 << 20, (size_t)0}) {
+        if (!loadWhole(path, &buf, limit, err)) return false;
         d = Decoder();
         d.err = err;
-        if (!d.run(buf.data(), buf.size(), true)) return false;
+        if (d.run(buf.data(), buf.size(), true)) break;
+        if (!limit || buf.size() < limit) return false; // the whole file has been seen
     }
     describe(d, info);
     return true;
