@@ -163,6 +163,13 @@ struct Decoder {
         int ws[64];
         auto descale = [](long x, int n) { return (int)((x + (1L << (n - 1))) >> n); };
         for (int c = 0; c < 8; c++) {
+            // the library's shortcut for a column without AC terms (most columns of a dark frame): the full formula gives
+            // descale(d0 << CB, CB - P1) = d0 << P1 in every row
+            if ((in[8 + c] | in[16 + c] | in[24 + c] | in[32 + c] | in[40 + c] | in[48 + c] | in[56 + c]) == 0) {
+                const int dc = (int)((long)in[c] * q[c] * (1L << P1));
+                for (int r = 0; r < 8; r++) ws[8 * r + c] = dc;
+                continue;
+            }
             long d[8];
             for (int r = 0; r < 8; r++) d[r] = (long)in[8 * r + c] * q[8 * r + c];
             long z2 = d[2], z3 = d[6];
@@ -185,6 +192,11 @@ struct Decoder {
         }
         for (int r = 0; r < 8; r++) {
             const int *w = ws + 8 * r;
+            if ((w[1] | w[2] | w[3] | w[4] | w[5] | w[6] | w[7]) == 0) { // likewise for a row: descale(w0 << CB, CB + P1 + 3) = descale(w0, P1 + 3)
+                const uint8_t v = range_limit(descale((long)w[0], P1 + 3));
+                memset(out + (size_t)r * stride, v, 8);
+                continue;
+            }
             long z2 = w[2], z3 = w[6];
             long z1 = (z2 + z3) * F0541;
             long tmp2 = z1 + z3 * (-F1847), tmp3 = z1 + z2 * F0765;
